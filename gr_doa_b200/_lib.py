@@ -1,0 +1,73 @@
+"""ctypes binding of libdoa_cuda.so (include/doa_cuda.h).  Fails loudly when the library is missing: there is no
+fallback path of any kind in this package."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdoa_cuda.so")
+_lib = None
+
+OK, EINVAL, ECUDA, ENOMEM, ECAPACITY = 0, -1, -2, -3, -4
+
+# every symbol include/doa_cuda.h declares: name -> (restype, argtypes)
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_hp = C.POINTER(C.c_void_p)
+SYMBOLS = {
+    "doa_cuda_abi_version": (_i, []),
+    "doa_cuda_last_error": (C.c_char_p, [_vp]),
+    "doa_cuda_device_count": (_i, []),
+    "doa_cuda_autocorrelate_create": (_i, [_hp, _i, _i, _i, _i, _i, _i]),
+    "doa_cuda_autocorrelate_run": (_i, [_vp, _hp, _i, _vp]),
+    "doa_cuda_autocorrelate_run_device": (_i, [_vp, _vp, _ll, _ll, _i, _vp, _vp]),
+    "doa_cuda_autocorrelate_forecast": (_i, [_vp, _i]),
+    "doa_cuda_music_create": (_i, [_hp, _f, _i, _i, _i, _i, _i]),
+    "doa_cuda_music_run": (_i, [_vp, _vp, _i, _vp]),
+    "doa_cuda_music_run_device": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "doa_cuda_music_get_tables": (_i, [_vp, _vp, _vp, _vp]),
+    "doa_cuda_rootmusic_create": (_i, [_hp, _f, _i, _i, _i, _i]),
+    "doa_cuda_rootmusic_run": (_i, [_vp, _vp, _i, _vp]),
+    "doa_cuda_rootmusic_run_device": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "doa_cuda_find_local_max_create": (_i, [_hp, _i, _i, _f, _f, _i, _i]),
+    "doa_cuda_find_local_max_run": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "doa_cuda_find_local_max_run_device": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "doa_cuda_chain_create": (_i, [_hp, _i, _i, _i, _i, _f, _i, _i, _i, _f, _f, _i, _i]),
+    "doa_cuda_chain_run_device": (_i, [_vp, _vp, _ll, _ll, _i, _vp, _vp, _vp, _vp]),
+    "doa_cuda_chain_run": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "doa_cuda_chain_run_streams": (_i, [_vp, _hp, _i, _vp, _vp, _vp]),
+    "doa_cuda_last_launch_count": (_i, [_vp]),
+    "doa_cuda_set_profiling": (_i, [_vp, _i]),
+    "doa_cuda_chain_stage_ms": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f)]),
+    "doa_cuda_destroy": (None, [_vp]),
+}
+
+
+class DoaCudaError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"libdoa_cuda error {code}: {text}")
+        self.code = code
+
+
+def lib():
+    """Load libdoa_cuda.so (built in-tree by gr_doa_b200.build).  Raises if absent: no fallback exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not found: build it with `python -m gr_doa_b200.build` "
+                          "(libdoa_cuda is the only compute path; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(L, name)   # AttributeError if the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    L.doa_cuda_dev_set.restype = _i
+    L.doa_cuda_dev_set.argtypes = [C.c_char_p, _i]
+    _lib = L
+    return L
+
+
+def check(rc, handle=None):
+    if rc != OK:
+        txt = lib().doa_cuda_last_error(handle)
+        raise DoaCudaError(rc, txt.decode() if txt else "")
+    return rc

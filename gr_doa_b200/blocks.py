@@ -1,0 +1,262 @@
+"""Host-side mirror of the four gr-doa blocks on the DoA hot path, over libdoa_cuda's C ABI.
+
+Same names, constructor parameters and port semantics as the reference's python namespace `doa`
+(swig/doa_swig.i:22-36; grc/doa_*.xml <make> lines), so the parity tests read like python/qa_*.py:
+
+    doa.autocorrelate(inputs, snapshot_size, overlap_size, avg_method)            include/doa/autocorrelate.h:56
+    doa.MUSIC_lin_array(norm_spacing, num_targets, num_ant_ele, pspectrum_len)    include/doa/MUSIC_lin_array.h:56
+    doa.rootMUSIC_linear_array(norm_spacing, num_targets, num_ant_ele)            include/doa/rootMUSIC_linear_array.h:54
+    doa.find_local_max(num_max_vals, vector_len, x_min, x_max)                    include/doa/find_local_max.h:56
+
+`work(...)` takes/returns numpy arrays in host memory (what a GNU Radio scheduler hands to work()) and goes through
+the *_run entry points; `work_device(...)` takes/returns torch CUDA tensors and goes through *_run_device on torch's
+current stream.  torch is used for device memory and streams only.  DoaChain is the fused
+autocorrelate -> MUSIC_lin_array -> find_local_max path (peaks only).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _Block:
+    def __init__(self):
+        self._h = C.c_void_p()
+        self._L = _lib.lib()
+
+    def _created(self, rc):
+        if rc != 0:
+            txt = self._L.doa_cuda_last_error(None)
+            raise _lib.DoaCudaError(rc, txt.decode() if txt else "")
+
+    def launches(self):
+        return int(self._L.doa_cuda_last_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.doa_cuda_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class autocorrelate(_Block):
+    """gr::doa::autocorrelate (lib/autocorrelate_impl.cc:47-118)."""
+
+    def __init__(self, inputs, snapshot_size, overlap_size, avg_method, device=0, max_frames=4096):
+        super().__init__()
+        self.inputs, self.snapshot_size, self.overlap_size, self.avg_method = inputs, snapshot_size, overlap_size, int(avg_method)
+        self.hop = snapshot_size - overlap_size
+        self.max_frames = max_frames
+        self._created(self._L.doa_cuda_autocorrelate_create(C.byref(self._h), inputs, snapshot_size, overlap_size,
+                                                            int(avg_method), device, max_frames))
+
+    def history(self):
+        return self.overlap_size + 1          # set_history(), lib/autocorrelate_impl.cc:57
+
+    def forecast(self, noutput_items):
+        return int(self._L.doa_cuda_autocorrelate_forecast(self._h, noutput_items))
+
+    def general_work(self, noutput_items, input_items):
+        """input_items: M arrays of complex64, each with >= hop*(n-1)+snapshot_size samples (history included).
+        Returns ([n][M*M] complex64, consumed_per_port = hop*n) like general_work() + consume_each()."""
+        xs = [_np(x, np.complex64) for x in input_items]
+        need = (noutput_items - 1) * self.hop + self.snapshot_size if noutput_items > 0 else 0
+        for x in xs:
+            if x.size < need:
+                raise ValueError("not enough input items for noutput_items")
+        out = np.empty((noutput_items, self.inputs * self.inputs), np.complex64)
+        ptrs = (C.c_void_p * self.inputs)(*[x.ctypes.data for x in xs])
+        check(self._L.doa_cuda_autocorrelate_run(self._h, ptrs, noutput_items, out.ctypes.data), self._h)
+        return out, self.hop * noutput_items
+
+    def work(self, streams):
+        """Whole-stream convenience: streams [M][L] -> all complete frames."""
+        x = _np(streams, np.complex64)
+        L = x.shape[1]
+        n = (L - self.snapshot_size) // self.hop + 1 if L >= self.snapshot_size else 0
+        outs = []
+        for f0 in range(0, n, self.max_frames):
+            nf = min(self.max_frames, n - f0)
+            o, _ = self.general_work(nf, [x[k, f0 * self.hop:] for k in range(self.inputs)])
+            outs.append(o)
+        return np.concatenate(outs) if outs else np.empty((0, self.inputs ** 2), np.complex64)
+
+    def work_device(self, x, frame_stride=None, chan_stride=None, nframes=None):
+        """x: torch complex64 CUDA tensor, [B][M][N] independent frames (default strides) or any strided layout."""
+        import torch
+        if frame_stride is None:
+            B, M, N = x.shape
+            frame_stride, chan_stride, nframes = M * N, N, B
+        out = torch.empty((nframes, self.inputs * self.inputs), dtype=torch.complex64, device=x.device)
+        check(self._L.doa_cuda_autocorrelate_run_device(self._h, x.data_ptr(), frame_stride, chan_stride, nframes,
+                                                        out.data_ptr(), _stream_ptr()), self._h)
+        return out
+
+
+class MUSIC_lin_array(_Block):
+    """gr::doa::MUSIC_lin_array (lib/MUSIC_lin_array_impl.cc:47-150)."""
+
+    def __init__(self, norm_spacing, num_targets, num_ant_ele, pspectrum_len, device=0, max_frames=4096):
+        super().__init__()
+        self.norm_spacing, self.num_targets, self.num_ant_ele, self.pspectrum_len = norm_spacing, num_targets, num_ant_ele, pspectrum_len
+        self.max_frames = max_frames
+        self.nout_items_total = 0             # public counter of the reference block (lib/MUSIC_lin_array_impl.h:47)
+        self._created(self._L.doa_cuda_music_create(C.byref(self._h), C.c_float(norm_spacing), num_targets, num_ant_ele,
+                                                    pspectrum_len, device, max_frames))
+
+    def tables(self):
+        M, P = self.num_ant_ele, self.pspectrum_len
+        loc, th, V = np.empty(M, np.float32), np.empty(P, np.float32), np.empty((P, M), np.complex64)
+        check(self._L.doa_cuda_music_get_tables(self._h, loc.ctypes.data, th.ctypes.data, V.ctypes.data), self._h)
+        return loc, th, V
+
+    def work(self, R):
+        M = self.num_ant_ele
+        R = _np(R, np.complex64).reshape(-1, M * M)
+        out = np.empty((R.shape[0], self.pspectrum_len), np.float32)
+        for f0 in range(0, R.shape[0], self.max_frames):
+            nf = min(self.max_frames, R.shape[0] - f0)
+            check(self._L.doa_cuda_music_run(self._h, R[f0:].ctypes.data, nf, out[f0:].ctypes.data), self._h)
+        self.nout_items_total += R.shape[0]
+        return out
+
+    def work_device(self, R):
+        import torch
+        n = R.shape[0]
+        out = torch.empty((n, self.pspectrum_len), dtype=torch.float32, device=R.device)
+        check(self._L.doa_cuda_music_run_device(self._h, R.data_ptr(), n, out.data_ptr(), _stream_ptr()), self._h)
+        self.nout_items_total += n
+        return out
+
+
+class rootMUSIC_linear_array(_Block):
+    """gr::doa::rootMUSIC_linear_array (lib/rootMUSIC_linear_array_impl.cc:46-152)."""
+
+    def __init__(self, norm_spacing, num_targets, num_ant_ele, device=0, max_frames=4096):
+        super().__init__()
+        self.norm_spacing, self.num_targets, self.num_ant_ele = norm_spacing, num_targets, num_ant_ele
+        self.max_frames = max_frames
+        self._created(self._L.doa_cuda_rootmusic_create(C.byref(self._h), C.c_float(norm_spacing), num_targets, num_ant_ele,
+                                                        device, max_frames))
+
+    def work(self, R):
+        M = self.num_ant_ele
+        R = _np(R, np.complex64).reshape(-1, M * M)
+        out = np.empty((R.shape[0], self.num_targets), np.float32)
+        for f0 in range(0, R.shape[0], self.max_frames):
+            nf = min(self.max_frames, R.shape[0] - f0)
+            check(self._L.doa_cuda_rootmusic_run(self._h, R[f0:].ctypes.data, nf, out[f0:].ctypes.data), self._h)
+        return out
+
+    def work_device(self, R):
+        import torch
+        n = R.shape[0]
+        out = torch.empty((n, self.num_targets), dtype=torch.float32, device=R.device)
+        check(self._L.doa_cuda_rootmusic_run_device(self._h, R.data_ptr(), n, out.data_ptr(), _stream_ptr()), self._h)
+        return out
+
+
+class find_local_max(_Block):
+    """gr::doa::find_local_max (lib/find_local_max_impl.cc:47-194).  Returns (out0 peak values, out1 locations[, bins])."""
+
+    def __init__(self, num_max_vals, vector_len, x_min, x_max, device=0, max_frames=4096):
+        super().__init__()
+        self.num_max_vals, self.vector_len, self.x_min, self.x_max = num_max_vals, vector_len, x_min, x_max
+        self.max_frames = max_frames
+        self._created(self._L.doa_cuda_find_local_max_create(C.byref(self._h), num_max_vals, vector_len, C.c_float(x_min),
+                                                             C.c_float(x_max), device, max_frames))
+
+    def work(self, vecs, return_bins=False):
+        v = _np(vecs, np.float32).reshape(-1, self.vector_len)
+        n, K = v.shape[0], self.num_max_vals
+        val, loc, bins = np.empty((n, K), np.float32), np.empty((n, K), np.float32), np.empty((n, K), np.int32)
+        for f0 in range(0, n, self.max_frames):
+            nf = min(self.max_frames, n - f0)
+            check(self._L.doa_cuda_find_local_max_run(self._h, v[f0:].ctypes.data, nf, val[f0:].ctypes.data,
+                                                      loc[f0:].ctypes.data, bins[f0:].ctypes.data), self._h)
+        return (val, loc, bins) if return_bins else (val, loc)
+
+    def work_device(self, vecs):
+        import torch
+        n, K = vecs.shape[0], self.num_max_vals
+        val = torch.empty((n, K), dtype=torch.float32, device=vecs.device)
+        loc = torch.empty_like(val)
+        bins = torch.empty((n, K), dtype=torch.int32, device=vecs.device)
+        check(self._L.doa_cuda_find_local_max_run_device(self._h, vecs.data_ptr(), n, val.data_ptr(), loc.data_ptr(),
+                                                         bins.data_ptr(), _stream_ptr()), self._h)
+        return val, loc, bins
+
+
+class DoaChain(_Block):
+    """autocorrelate -> MUSIC_lin_array -> find_local_max(K, P, x_min, x_max) in one call, peaks only."""
+
+    def __init__(self, inputs, snapshot_size, overlap_size, avg_method, norm_spacing, num_targets, pspectrum_len,
+                 num_max_vals, x_min=0.0, x_max=180.0, device=0, max_frames=4096):
+        super().__init__()
+        self.inputs, self.snapshot_size, self.overlap_size = inputs, snapshot_size, overlap_size
+        self.hop = snapshot_size - overlap_size
+        self.K, self.max_frames = num_max_vals, max_frames
+        self._created(self._L.doa_cuda_chain_create(C.byref(self._h), inputs, snapshot_size, overlap_size, int(avg_method),
+                                                    C.c_float(norm_spacing), num_targets, pspectrum_len, num_max_vals,
+                                                    C.c_float(x_min), C.c_float(x_max), device, max_frames))
+
+    def set_profiling(self, on=True):
+        check(self._L.doa_cuda_set_profiling(self._h, int(on)), self._h)
+
+    def stage_ms(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        check(self._L.doa_cuda_chain_stage_ms(self._h, C.byref(a), C.byref(b), C.byref(c)), self._h)
+        return a.value, b.value, c.value
+
+    def run_device(self, x, out=None, frame_stride=None, chan_stride=None, nframes=None):
+        """x: torch complex64 CUDA tensor [B][M][N] (or explicit strides).  Returns (val, loc, bins) CUDA tensors."""
+        import torch
+        if frame_stride is None:
+            B, M, N = x.shape
+            frame_stride, chan_stride, nframes = M * N, N, B
+        if out is None:
+            val = torch.empty((nframes, self.K), dtype=torch.float32, device=x.device)
+            out = (val, torch.empty_like(val), torch.empty((nframes, self.K), dtype=torch.int32, device=x.device))
+        val, loc, bins = out
+        check(self._L.doa_cuda_chain_run_device(self._h, x.data_ptr(), frame_stride, chan_stride, nframes, val.data_ptr(),
+                                                loc.data_ptr(), bins.data_ptr(), _stream_ptr()), self._h)
+        return val, loc, bins
+
+    def run_host(self, frames, out=None):
+        """frames: host complex64 [B][M][N] (numpy, or a pinned torch tensor).  Returns numpy (val, loc, bins)."""
+        if hasattr(frames, "data_ptr"):
+            ptr, B = frames.data_ptr(), frames.shape[0]
+        else:
+            frames = _np(frames, np.complex64)
+            ptr, B = frames.ctypes.data, frames.shape[0]
+        if out is None:
+            out = (np.empty((B, self.K), np.float32), np.empty((B, self.K), np.float32), np.empty((B, self.K), np.int32))
+        val, loc, bins = out
+        p = [o.data_ptr() if hasattr(o, "data_ptr") else o.ctypes.data for o in (val, loc, bins)]
+        check(self._L.doa_cuda_chain_run(self._h, ptr, B, p[0], p[1], p[2]), self._h)
+        return val, loc, bins
+
+    def run_streams(self, streams, nframes):
+        xs = [_np(x, np.complex64) for x in streams]
+        val, loc, bins = (np.empty((nframes, self.K), np.float32), np.empty((nframes, self.K), np.float32),
+                          np.empty((nframes, self.K), np.int32))
+        ptrs = (C.c_void_p * self.inputs)(*[x.ctypes.data for x in xs])
+        check(self._L.doa_cuda_chain_run_streams(self._h, ptrs, nframes, val.ctypes.data, loc.ctypes.data, bins.ctypes.data),
+              self._h)
+        return val, loc, bins

@@ -1,0 +1,65 @@
+"""Build libdoa_cuda.so in-tree with nvcc for sm_100a (no torch, no cmake: four .cu files, one shared library).
+
+    python -m gr_doa_b200.build [--force]
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.  cudart is linked statically so the
+library has no run-time dependency beyond the driver.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libdoa_cuda.so")
+SOURCES = ["doa_cuda.cu", "cov.cu", "eig.cu", "scan.cu", "root.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+              "-Xptxas", "-v"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _deps_mtime():
+    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "doa_cuda.h")]
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
+        return LIB
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        srcp = os.path.join(CSRC, src)
+        hdr_m = max(os.path.getmtime(os.path.join(CSRC, "doa_internal.h")),
+                    os.path.getmtime(os.path.join(HERE, "..", "include", "doa_cuda.h")))
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(srcp), hdr_m):
+            return obj, ""
+        r = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", srcp, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    if verbose:
+        for _, log in results:
+            sys.stderr.write(log)
+    objs = [o for o, _ in results]
+    r = subprocess.run([nvcc, "-shared", "-o", LIB] + objs + ["-cudart", "static"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

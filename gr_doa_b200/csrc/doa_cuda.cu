@@ -1,0 +1,542 @@
+// doa_cuda.cu -- the C ABI of libdoa_cuda (include/doa_cuda.h): handles, constructor tables, staging, stage plumbing.
+//
+// One handle = one GNU Radio block instance: it owns its CUDA stream(s), device buffers sized for max_frames and the
+// constructor tables.  cudaSetDevice() is called on entry to every function (GNU Radio may call work() from a thread
+// other than the constructor's).  There is no global mutable state besides the error text of a failed *_create.
+#include "doa_internal.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+namespace doa {
+
+// ---- development knobs ---------------------------------------------------------------------------------------------
+static std::mutex g_opt_mu;
+static std::map<std::string, int> g_opts;
+int dev_option(const char* key, int dflt) {
+  std::lock_guard<std::mutex> lk(g_opt_mu);
+  auto it = g_opts.find(key);
+  return it == g_opts.end() ? dflt : it->second;
+}
+
+// ---- constructor tables (host) -----------------------------------------------------------------------------------
+// MUSIC_lin_array_impl constructor, gr-doa lib/MUSIC_lin_array_impl.cc:56-86, with its float/double mixing:
+//   array_loc[nn] = float(d*0.5*(M-1-2nn));  theta accumulates as float(theta_prev + 180.0/P);
+//   theta_rad = float(pi*theta/180.0);  s = float(-1.0*2*pi*cos(theta_rad));  V[nn] = (cosf, sinf)(s*array_loc[nn]).
+// z is not in the reference: it is the per-element phase step of that table, e^{-j s d}, used by the coarse scan.
+void build_music_tables(float norm_spacing, int M, int P, std::vector<float>& array_loc, std::vector<float>& theta,
+                        std::vector<float2>& V, std::vector<float2>& z) {
+  const double pi = 3.14159265358979323846;
+  array_loc.resize(M); theta.resize(P); V.resize((size_t)M * P); z.resize(P);
+  for (int nn = 0; nn < M; ++nn) array_loc[nn] = (float)(norm_spacing * 0.5 * (M - 1 - 2 * nn));
+  theta[0] = 0.0f;
+  float prev = 0.0f;
+  for (int ii = 1; ii < P; ++ii) {
+    const float th = (float)(prev + 180.0 / P);
+    prev = th;
+    theta[ii] = (float)(pi * th / 180.0);
+  }
+  for (int ii = 0; ii < P; ++ii) {
+    const float s = (float)(-1.0 * 2 * pi * std::cos((double)theta[ii]));
+    for (int nn = 0; nn < M; ++nn) {
+      const float phi = s * array_loc[nn];
+      V[(size_t)ii * M + nn] = make_float2(cosf(phi), sinf(phi));
+    }
+    const double psi = -(double)s * (double)norm_spacing;
+    z[ii] = make_float2((float)std::cos(psi), (float)std::sin(psi));
+  }
+}
+
+// find_local_max_impl constructor, lib/find_local_max_impl.cc:60-69 (all float, accumulated).
+void build_x_axis(int len, float x_min, float x_max, std::vector<float>& x) {
+  x.resize(len);
+  x[0] = x_min;
+  float prev = x_min;
+  const float range = x_max - x_min;
+  for (int ii = 1; ii < len; ++ii) { const float v = prev + range / len; prev = v; x[ii] = v; }
+}
+
+}  // namespace doa
+
+using namespace doa;
+
+enum Kind { K_AUTOCORR = 1, K_MUSIC, K_ROOTMUSIC, K_FLM, K_CHAIN };
+
+struct Lane {   // one stream's worth of buffers (the chain's host path double-buffers two of these)
+  cudaStream_t stream = nullptr;
+  float2* in = nullptr; size_t in_elems = 0;   // staged samples
+  float2* R = nullptr; float2* G = nullptr; float2* u = nullptr;
+  float* spec = nullptr; float* val = nullptr; float* loc = nullptr; int* bin = nullptr; float* aoa = nullptr;
+  float* vecs = nullptr;
+  double2* scratch = nullptr;
+  int frames = 0;
+};
+
+struct doa_cuda_handle {
+  int kind = 0, device = 0, max_frames = 0;
+  int M = 0, N = 0, overlap = 0, hop = 0, avg = 0, T = 0, P = 0, K = 0;
+  float d = 0.f, x_min = 0.f, x_max = 0.f;
+  Lane lane[2];
+  int nlanes = 1;
+  float2* d_z = nullptr; float2* d_V = nullptr; float* d_x = nullptr;
+  std::vector<float> h_loc, h_theta, h_x; std::vector<float2> h_V, h_z;
+  std::string err;
+  int launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(h, call)                                                                                    \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) {                                                                           \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                   \
+      return DOA_CUDA_ECUDA;                                                                           \
+    }                                                                                                  \
+  } while (0)
+
+static int fail(doa_cuda_handle* h, int code, const std::string& msg) { if (h) h->err = msg; else g_create_err = msg; return code; }
+
+static void free_lane(Lane& l) {
+  cudaFree(l.in); cudaFree(l.R); cudaFree(l.G); cudaFree(l.u); cudaFree(l.spec); cudaFree(l.val); cudaFree(l.loc);
+  cudaFree(l.bin); cudaFree(l.aoa); cudaFree(l.vecs); cudaFree(l.scratch);
+  if (l.stream) cudaStreamDestroy(l.stream);
+  l = Lane();
+}
+
+extern "C" void doa_cuda_destroy(doa_cuda_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (int i = 0; i < 2; ++i) free_lane(h->lane[i]);
+  cudaFree(h->d_z); cudaFree(h->d_V); cudaFree(h->d_x);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  delete h;
+}
+
+static int begin_create(doa_cuda_handle** out, doa_cuda_handle*& h, int kind, int device, int max_frames) {
+  if (!out) return fail(nullptr, DOA_CUDA_EINVAL, "null handle pointer");
+  *out = nullptr;
+  if (max_frames < 1) return fail(nullptr, DOA_CUDA_EINVAL, "max_frames must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(nullptr, DOA_CUDA_ECUDA, "no CUDA device available (libdoa_cuda has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(nullptr, DOA_CUDA_EINVAL, "device index out of range");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, DOA_CUDA_ECUDA, "cudaSetDevice failed");
+  h = new doa_cuda_handle();
+  h->kind = kind; h->device = device; h->max_frames = max_frames;
+  return DOA_CUDA_OK;
+}
+
+template <typename Tp>
+static bool dalloc(Tp** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(Tp)) == cudaSuccess; }
+
+static int finish_create(doa_cuda_handle** out, doa_cuda_handle* h, bool ok) {
+  if (!ok) {
+    g_create_err = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+    doa_cuda_destroy(h);
+    return DOA_CUDA_ENOMEM;
+  }
+  *out = h;
+  return DOA_CUDA_OK;
+}
+
+static bool upload_scan_tables(doa_cuda_handle* h, bool need_steering, bool need_x) {
+  bool ok = true;
+  if (need_steering) {
+    build_music_tables(h->d, h->M, h->P, h->h_loc, h->h_theta, h->h_V, h->h_z);
+    ok = ok && dalloc(&h->d_z, (size_t)h->P) && dalloc(&h->d_V, (size_t)h->P * h->M);
+    if (ok) {
+      ok = cudaMemcpy(h->d_z, h->h_z.data(), sizeof(float2) * h->P, cudaMemcpyHostToDevice) == cudaSuccess &&
+           cudaMemcpy(h->d_V, h->h_V.data(), sizeof(float2) * (size_t)h->P * h->M, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+  }
+  if (need_x && ok) {
+    const int len = h->P;
+    build_x_axis(len, h->x_min, h->x_max, h->h_x);
+    ok = dalloc(&h->d_x, (size_t)len) &&
+         cudaMemcpy(h->d_x, h->h_x.data(), sizeof(float) * len, cudaMemcpyHostToDevice) == cudaSuccess;
+  }
+  return ok;
+}
+
+static ScanTables tables_of(const doa_cuda_handle* h) {
+  ScanTables t; t.M = h->M; t.P = h->P; t.z = h->d_z; t.V = h->d_V; t.xaxis = h->d_x; return t;
+}
+
+extern "C" {
+
+int doa_cuda_abi_version(void) { return 1; }
+const char* doa_cuda_last_error(const doa_cuda_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+int doa_cuda_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+int doa_cuda_last_launch_count(const doa_cuda_handle* h) { return h ? h->launches : 0; }
+int doa_cuda_dev_set(const char* key, int value) {
+  std::lock_guard<std::mutex> lk(g_opt_mu);
+  g_opts[key] = value;
+  return 0;
+}
+
+// ---- autocorrelate ------------------------------------------------------------------------------------------------
+int doa_cuda_autocorrelate_create(doa_cuda_handle** out, int inputs, int snapshot_size, int overlap_size, int avg_method,
+                                  int device, int max_frames) {
+  if (inputs < 1 || inputs > 64) return fail(nullptr, DOA_CUDA_EINVAL, "inputs must be in [1, 64]");
+  if (snapshot_size < 1) return fail(nullptr, DOA_CUDA_EINVAL, "snapshot_size must be > 0");
+  if (overlap_size < 0 || overlap_size >= snapshot_size) return fail(nullptr, DOA_CUDA_EINVAL, "need 0 <= overlap_size < snapshot_size");
+  if (avg_method != 0 && avg_method != 1) return fail(nullptr, DOA_CUDA_EINVAL, "avg_method must be 0 (forward) or 1 (forward-backward)");
+  doa_cuda_handle* h = nullptr;
+  int rc = begin_create(out, h, K_AUTOCORR, device, max_frames);
+  if (rc) return rc;
+  h->M = inputs; h->N = snapshot_size; h->overlap = overlap_size; h->hop = snapshot_size - overlap_size; h->avg = avg_method;
+  Lane& l = h->lane[0];
+  const size_t Lpad = (((size_t)(max_frames - 1) * h->hop + h->N) + 1) & ~(size_t)1;
+  l.in_elems = Lpad * h->M;
+  bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess && dalloc(&l.in, l.in_elems) &&
+            dalloc(&l.R, (size_t)max_frames * h->M * h->M);
+  return finish_create(out, h, ok);
+}
+
+int doa_cuda_autocorrelate_forecast(const doa_cuda_handle* h, int noutput_items) {
+  if (!h || h->kind != K_AUTOCORR) return DOA_CUDA_EINVAL;
+  return h->hop * noutput_items;   // lib/autocorrelate_impl.cc:79
+}
+
+int doa_cuda_autocorrelate_run_device(doa_cuda_handle* h, const void* in_dev, long long frame_stride, long long chan_stride,
+                                      int nframes, void* out_dev, void* cuda_stream) {
+  if (!h || (h->kind != K_AUTOCORR && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
+  if (nframes < 0) return fail(h, DOA_CUDA_EINVAL, "nframes < 0");
+  CK(h, cudaSetDevice(h->device));
+  int n = launch_covariance((const float2*)in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, (float2*)out_dev,
+                            (cudaStream_t)cuda_stream);
+  if (n < 0) return fail(h, n, "covariance launch rejected");
+  h->launches = n;
+  CK(h, cudaGetLastError());
+  return DOA_CUDA_OK;
+}
+
+// Copy `inputs` host channel streams into lane.in as [M][Lpad]; returns Lpad.
+static int stage_streams(doa_cuda_handle* h, Lane& l, const void* const* in_host, int nframes, size_t* Lpad_out) {
+  const size_t L = (size_t)(nframes - 1) * h->hop + h->N;
+  const size_t Lpad = (L + 1) & ~(size_t)1;
+  if (Lpad * h->M > l.in_elems) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  for (int k = 0; k < h->M; ++k)
+    CK(h, cudaMemcpyAsync(l.in + (size_t)k * Lpad, in_host[k], L * sizeof(float2), cudaMemcpyHostToDevice, l.stream));
+  *Lpad_out = Lpad;
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_autocorrelate_run(doa_cuda_handle* h, const void* const* in_host, int nframes, void* out_host) {
+  if (!h || h->kind != K_AUTOCORR) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  Lane& l = h->lane[0];
+  size_t Lpad = 0;
+  int rc = stage_streams(h, l, in_host, nframes, &Lpad);
+  if (rc) return rc;
+  rc = doa_cuda_autocorrelate_run_device(h, l.in, h->hop, (long long)Lpad, nframes, l.R, l.stream);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(out_host, l.R, sizeof(float2) * (size_t)nframes * h->M * h->M, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaStreamSynchronize(l.stream));
+  return DOA_CUDA_OK;
+}
+
+// ---- MUSIC -----------------------------------------------------------------------------------------------------------
+static int check_array(float norm_spacing, int num_targets, int num_ant_ele) {
+  if (num_ant_ele < 2 || num_ant_ele > 64) return fail(nullptr, DOA_CUDA_EINVAL, "num_ant_ele must be in [2, 64]");
+  if (num_targets < 1 || num_targets >= num_ant_ele) return fail(nullptr, DOA_CUDA_EINVAL, "need 1 <= num_targets < num_ant_ele");
+  if (!(norm_spacing > 0.0f) || norm_spacing > 0.5f) return fail(nullptr, DOA_CUDA_EINVAL, "need 0 < norm_spacing <= 0.5");
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_music_create(doa_cuda_handle** out, float norm_spacing, int num_targets, int num_ant_ele, int pspectrum_len,
+                          int device, int max_frames) {
+  int rc = check_array(norm_spacing, num_targets, num_ant_ele);
+  if (rc) return rc;
+  if (pspectrum_len < 2) return fail(nullptr, DOA_CUDA_EINVAL, "pspectrum_len must be >= 2");
+  doa_cuda_handle* h = nullptr;
+  rc = begin_create(out, h, K_MUSIC, device, max_frames);
+  if (rc) return rc;
+  h->d = norm_spacing; h->T = num_targets; h->M = num_ant_ele; h->P = pspectrum_len;
+  Lane& l = h->lane[0];
+  const size_t mm = (size_t)h->M * h->M;
+  bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess &&
+            dalloc(&l.R, max_frames * mm) && dalloc(&l.u, (size_t)max_frames * h->M) &&
+            dalloc(&l.spec, (size_t)max_frames * h->P) && upload_scan_tables(h, true, false);
+  return finish_create(out, h, ok);
+}
+
+int doa_cuda_music_get_tables(const doa_cuda_handle* h, float* array_loc, float* theta_rad, float* steering) {
+  if (!h || (h->kind != K_MUSIC && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
+  if (array_loc) memcpy(array_loc, h->h_loc.data(), sizeof(float) * h->M);
+  if (theta_rad) memcpy(theta_rad, h->h_theta.data(), sizeof(float) * h->P);
+  if (steering) memcpy(steering, h->h_V.data(), sizeof(float2) * (size_t)h->P * h->M);
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_music_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_dev, void* cuda_stream) {
+  if (!h || h->kind != K_MUSIC) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  Lane& l = h->lane[0];
+  int a = launch_noise_subspace((const float2*)in_dev, h->M, h->T, nframes, nullptr, l.u, nullptr, st);
+  if (a < 0) return fail(h, a, "eigendecomposition launch rejected");
+  int b = launch_scan_spectrum(l.u, nullptr, tables_of(h), nframes, (float*)out_dev, st);
+  if (b < 0) return fail(h, b, "spectrum launch rejected");
+  h->launches = a + b;
+  CK(h, cudaGetLastError());
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_music_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_host) {
+  if (!h || h->kind != K_MUSIC) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  Lane& l = h->lane[0];
+  const size_t mm = (size_t)h->M * h->M;
+  CK(h, cudaMemcpyAsync(l.R, in_host, sizeof(float2) * nframes * mm, cudaMemcpyHostToDevice, l.stream));
+  int rc = doa_cuda_music_run_device(h, l.R, nframes, l.spec, l.stream);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(out_host, l.spec, sizeof(float) * (size_t)nframes * h->P, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaStreamSynchronize(l.stream));
+  return DOA_CUDA_OK;
+}
+
+// ---- Root-MUSIC ------------------------------------------------------------------------------------------------------
+int doa_cuda_rootmusic_create(doa_cuda_handle** out, float norm_spacing, int num_targets, int num_ant_ele, int device,
+                              int max_frames) {
+  int rc = check_array(norm_spacing, num_targets, num_ant_ele);
+  if (rc) return rc;
+  doa_cuda_handle* h = nullptr;
+  rc = begin_create(out, h, K_ROOTMUSIC, device, max_frames);
+  if (rc) return rc;
+  h->d = norm_spacing; h->T = num_targets; h->M = num_ant_ele;
+  Lane& l = h->lane[0];
+  const size_t mm = (size_t)h->M * h->M, n = 2 * (size_t)h->M - 2;
+  bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess &&
+            dalloc(&l.R, max_frames * mm) && dalloc(&l.u, (size_t)max_frames * h->M) &&
+            dalloc(&l.aoa, (size_t)max_frames * h->T) && dalloc(&l.scratch, n * n * (size_t)max_frames);
+  return finish_create(out, h, ok);
+}
+
+int doa_cuda_rootmusic_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_dev, void* cuda_stream) {
+  if (!h || h->kind != K_ROOTMUSIC) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  Lane& l = h->lane[0];
+  int a = launch_noise_subspace((const float2*)in_dev, h->M, h->T, nframes, nullptr, l.u, nullptr, st);
+  if (a < 0) return fail(h, a, "eigendecomposition launch rejected");
+  int b = launch_rootmusic_scratch(l.u, h->M, h->T, h->d, nframes, l.scratch, h->max_frames, (float*)out_dev, st);
+  if (b < 0) return fail(h, b, "root finder launch rejected");
+  h->launches = a + b;
+  CK(h, cudaGetLastError());
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_rootmusic_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_host) {
+  if (!h || h->kind != K_ROOTMUSIC) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  Lane& l = h->lane[0];
+  const size_t mm = (size_t)h->M * h->M;
+  CK(h, cudaMemcpyAsync(l.R, in_host, sizeof(float2) * nframes * mm, cudaMemcpyHostToDevice, l.stream));
+  int rc = doa_cuda_rootmusic_run_device(h, l.R, nframes, l.aoa, l.stream);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(out_host, l.aoa, sizeof(float) * (size_t)nframes * h->T, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaStreamSynchronize(l.stream));
+  return DOA_CUDA_OK;
+}
+
+// ---- find_local_max ----------------------------------------------------------------------------------------------------
+int doa_cuda_find_local_max_create(doa_cuda_handle** out, int num_max_vals, int vector_len, float x_min, float x_max,
+                                   int device, int max_frames) {
+  if (num_max_vals < 1 || num_max_vals > 16) return fail(nullptr, DOA_CUDA_EINVAL, "num_max_vals must be in [1, 16]");
+  if (vector_len < 2) return fail(nullptr, DOA_CUDA_EINVAL, "vector_len must be >= 2");
+  doa_cuda_handle* h = nullptr;
+  int rc = begin_create(out, h, K_FLM, device, max_frames);
+  if (rc) return rc;
+  h->K = num_max_vals; h->P = vector_len; h->x_min = x_min; h->x_max = x_max;
+  Lane& l = h->lane[0];
+  bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess &&
+            dalloc(&l.vecs, (size_t)max_frames * h->P) && dalloc(&l.val, (size_t)max_frames * h->K) &&
+            dalloc(&l.loc, (size_t)max_frames * h->K) && dalloc(&l.bin, (size_t)max_frames * h->K) &&
+            upload_scan_tables(h, false, true);
+  return finish_create(out, h, ok);
+}
+
+int doa_cuda_find_local_max_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_val_dev,
+                                       void* out_loc_dev, void* out_bin_dev, void* cuda_stream) {
+  if (!h || h->kind != K_FLM) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0) return fail(h, DOA_CUDA_EINVAL, "nframes < 0");
+  CK(h, cudaSetDevice(h->device));
+  int a = launch_find_local_max((const float*)in_dev, h->P, nframes, h->K, h->d_x, (float*)out_val_dev, (float*)out_loc_dev,
+                                (int*)out_bin_dev, (cudaStream_t)cuda_stream);
+  if (a < 0) return fail(h, a, "find_local_max launch rejected (vector_len too large for shared memory?)");
+  h->launches = a;
+  CK(h, cudaGetLastError());
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_find_local_max_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_val_host,
+                                void* out_loc_host, void* out_bin_host) {
+  if (!h || h->kind != K_FLM) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  Lane& l = h->lane[0];
+  CK(h, cudaMemcpyAsync(l.vecs, in_host, sizeof(float) * (size_t)nframes * h->P, cudaMemcpyHostToDevice, l.stream));
+  int rc = doa_cuda_find_local_max_run_device(h, l.vecs, nframes, l.val, l.loc, l.bin, l.stream);
+  if (rc) return rc;
+  const size_t nk = (size_t)nframes * h->K;
+  CK(h, cudaMemcpyAsync(out_val_host, l.val, sizeof(float) * nk, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaMemcpyAsync(out_loc_host, l.loc, sizeof(float) * nk, cudaMemcpyDeviceToHost, l.stream));
+  if (out_bin_host) CK(h, cudaMemcpyAsync(out_bin_host, l.bin, sizeof(int) * nk, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaStreamSynchronize(l.stream));
+  return DOA_CUDA_OK;
+}
+
+// ---- fused chain -----------------------------------------------------------------------------------------------------
+static const int CHAIN_HOST_CHUNK_BYTES = 256 << 20;   // H2D granularity of the host path
+
+int doa_cuda_chain_create(doa_cuda_handle** out, int inputs, int snapshot_size, int overlap_size, int avg_method,
+                          float norm_spacing, int num_targets, int pspectrum_len, int num_max_vals, float x_min,
+                          float x_max, int device, int max_frames) {
+  if (inputs < 2 || inputs > 64) return fail(nullptr, DOA_CUDA_EINVAL, "inputs must be in [2, 64]");
+  if (snapshot_size < 1) return fail(nullptr, DOA_CUDA_EINVAL, "snapshot_size must be > 0");
+  if (overlap_size < 0 || overlap_size >= snapshot_size) return fail(nullptr, DOA_CUDA_EINVAL, "need 0 <= overlap_size < snapshot_size");
+  if (avg_method != 0 && avg_method != 1) return fail(nullptr, DOA_CUDA_EINVAL, "avg_method must be 0 or 1");
+  int rc = check_array(norm_spacing, num_targets, inputs);
+  if (rc) return rc;
+  if (pspectrum_len < 2) return fail(nullptr, DOA_CUDA_EINVAL, "pspectrum_len must be >= 2");
+  if (num_max_vals < 1 || num_max_vals > 16) return fail(nullptr, DOA_CUDA_EINVAL, "num_max_vals must be in [1, 16]");
+  doa_cuda_handle* h = nullptr;
+  rc = begin_create(out, h, K_CHAIN, device, max_frames);
+  if (rc) return rc;
+  h->M = inputs; h->N = snapshot_size; h->overlap = overlap_size; h->hop = snapshot_size - overlap_size; h->avg = avg_method;
+  h->d = norm_spacing; h->T = num_targets; h->P = pspectrum_len; h->K = num_max_vals; h->x_min = x_min; h->x_max = x_max;
+  h->nlanes = 2;
+  const size_t mm = (size_t)h->M * h->M;
+  const size_t frame_bytes = sizeof(float2) * (size_t)h->M * h->N;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_frames, CHAIN_HOST_CHUNK_BYTES / frame_bytes));
+  bool ok = upload_scan_tables(h, true, true);
+  for (int i = 0; i < 2 && ok; ++i) {
+    Lane& l = h->lane[i];
+    // lane 0 carries the intermediates for a full device-resident batch; lane 1 only ever sees host chunks
+    const size_t nf = (i == 0) ? (size_t)max_frames : (size_t)chunk;
+    l.frames = (int)nf;
+    l.in_elems = (size_t)chunk * h->M * h->N + 2 * (size_t)h->M;   // host staging (frames layout or [M][Lpad] streams)
+    ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess && dalloc(&l.in, l.in_elems) &&
+         dalloc(&l.R, nf * mm) && dalloc(&l.G, nf * mm) && dalloc(&l.u, nf * h->M) && dalloc(&l.val, nf * h->K) &&
+         dalloc(&l.loc, nf * h->K) && dalloc(&l.bin, nf * h->K);
+  }
+  for (auto& e : h->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+  return finish_create(out, h, ok);
+}
+
+static int chain_on_lane(doa_cuda_handle* h, Lane& l, const float2* in_dev, long long frame_stride, long long chan_stride,
+                         int nframes, float* val, float* loc, int* bin, cudaStream_t st, bool prof) {
+  if (prof) CK(h, cudaEventRecord(h->ev[0], st));
+  int a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st);
+  if (a < 0) return fail(h, a, "covariance launch rejected");
+  if (prof) CK(h, cudaEventRecord(h->ev[1], st));
+  int b = launch_noise_subspace(l.R, h->M, h->T, nframes, l.G, l.u, nullptr, st);
+  if (b < 0) return fail(h, b, "eigendecomposition launch rejected");
+  if (prof) CK(h, cudaEventRecord(h->ev[2], st));
+  int c = launch_scan_peaks(l.u, l.G, tables_of(h), nframes, h->K, val, loc, bin, st);
+  if (c < 0) return fail(h, c, "scan launch rejected (pspectrum_len too large for shared memory?)");
+  if (prof) CK(h, cudaEventRecord(h->ev[3], st));
+  h->launches += a + b + c;
+  CK(h, cudaGetLastError());
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_chain_run_device(doa_cuda_handle* h, const void* in_dev, long long frame_stride, long long chan_stride,
+                              int nframes, void* out_val_dev, void* out_loc_dev, void* out_bin_dev, void* cuda_stream) {
+  if (!h || h->kind != K_CHAIN) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  h->launches = 0;
+  return chain_on_lane(h, h->lane[0], (const float2*)in_dev, frame_stride, chan_stride, nframes, (float*)out_val_dev,
+                       (float*)out_loc_dev, (int*)out_bin_dev, (cudaStream_t)cuda_stream, h->profiling);
+}
+
+int doa_cuda_chain_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_val_host, void* out_loc_host,
+                       void* out_bin_host) {
+  if (!h || h->kind != K_CHAIN) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  h->launches = 0;
+  const size_t fe = (size_t)h->M * h->N;
+  const int chunk = h->lane[1].frames;
+  const float2* src = (const float2*)in_host;
+  int c = 0;
+  for (int f0 = 0; f0 < nframes; f0 += chunk, ++c) {
+    Lane& l = h->lane[c & 1];
+    const int nf = std::min(chunk, nframes - f0);
+    CK(h, cudaMemcpyAsync(l.in, src + (size_t)f0 * fe, sizeof(float2) * nf * fe, cudaMemcpyHostToDevice, l.stream));
+    int rc = chain_on_lane(h, l, l.in, (long long)fe, h->N, nf, l.val, l.loc, l.bin, l.stream, false);
+    if (rc) return rc;
+    const size_t nk = (size_t)nf * h->K, off = (size_t)f0 * h->K;
+    CK(h, cudaMemcpyAsync((float*)out_val_host + off, l.val, sizeof(float) * nk, cudaMemcpyDeviceToHost, l.stream));
+    CK(h, cudaMemcpyAsync((float*)out_loc_host + off, l.loc, sizeof(float) * nk, cudaMemcpyDeviceToHost, l.stream));
+    if (out_bin_host) CK(h, cudaMemcpyAsync((int*)out_bin_host + off, l.bin, sizeof(int) * nk, cudaMemcpyDeviceToHost, l.stream));
+  }
+  CK(h, cudaStreamSynchronize(h->lane[0].stream));
+  CK(h, cudaStreamSynchronize(h->lane[1].stream));
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_chain_run_streams(doa_cuda_handle* h, const void* const* in_host, int nframes, void* out_val_host,
+                               void* out_loc_host, void* out_bin_host) {
+  if (!h || h->kind != K_CHAIN) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  h->launches = 0;
+  Lane& l = h->lane[0];
+  size_t Lpad = 0;
+  int rc = stage_streams(h, l, in_host, nframes, &Lpad);
+  if (rc) return rc;
+  rc = chain_on_lane(h, l, l.in, h->hop, (long long)Lpad, nframes, l.val, l.loc, l.bin, l.stream, false);
+  if (rc) return rc;
+  const size_t nk = (size_t)nframes * h->K;
+  CK(h, cudaMemcpyAsync(out_val_host, l.val, sizeof(float) * nk, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaMemcpyAsync(out_loc_host, l.loc, sizeof(float) * nk, cudaMemcpyDeviceToHost, l.stream));
+  if (out_bin_host) CK(h, cudaMemcpyAsync(out_bin_host, l.bin, sizeof(int) * nk, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaStreamSynchronize(l.stream));
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_set_profiling(doa_cuda_handle* h, int on) {
+  if (!h) return DOA_CUDA_EINVAL;
+  h->profiling = on != 0;
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_chain_stage_ms(doa_cuda_handle* h, float* cov_ms, float* eig_ms, float* scan_ms) {
+  if (!h || h->kind != K_CHAIN || !h->profiling) return DOA_CUDA_EINVAL;
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaEventSynchronize(h->ev[3]));
+  float a = 0, b = 0, c = 0;
+  CK(h, cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+  CK(h, cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+  CK(h, cudaEventElapsedTime(&c, h->ev[2], h->ev[3]));
+  if (cov_ms) *cov_ms = a;
+  if (eig_ms) *eig_ms = b;
+  if (scan_ms) *scan_ms = c;
+  return DOA_CUDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// doa_internal.h -- shared declarations of libdoa_cuda's translation units (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/doa_cuda.h"
+
+namespace doa {
+
+// ---- launch interfaces (one per kernel family; each returns the number of kernel launches it issued or <0) ----
+
+// Stage 1.  Sample (f,k,t) at in[f*frame_stride + k*chan_stride + t]; out[f][r + c*M] column-major.
+int launch_covariance(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
+                      int avg_method, float2* out, cudaStream_t st);
+
+// Stage 2a.  Hermitian EVD (batched Jacobi) of R (upper triangle read, like cheevd 'U') and the noise subspace:
+//   G[f][r + c*M] = sum_{n < M-T} e_n[r] conj(e_n[c])   (may be null)
+//   u[f][l]       = sum_r G[r][r+l], l = 0..M-1          (complex, u[0] real; may be null)
+//   w[f][M]       eigenvalues ascending                  (may be null)
+int launch_noise_subspace(const float2* R, int M, int T, int nframes, float2* G, float2* u, float* w, cudaStream_t st);
+
+// Tables built on the host by the plan constructor (music_tables.cpp), uploaded once.
+struct ScanTables {
+  int M = 0, P = 0;
+  const float2* z = nullptr;      // [P]   e^{j*psi_i}, psi_i = 2*pi*d*cos(theta_i): the ULA phase step per element
+  const float2* V = nullptr;      // [P][M] steering table exactly as the reference constructor builds it
+  const float* xaxis = nullptr;   // [P]   find_local_max x-axis (float-accumulated)
+};
+
+// Stage 2b+4 fused: coarse null-spectrum scan (ULA polynomial form) + local-minimum pick + refinement of the
+// picked bins with the reference's own v^H G v arithmetic + dB conversion.  Outputs per frame K values/locs/bins.
+int launch_scan_peaks(const float2* u, const float2* G, const ScanTables& tb, int nframes, int K, float* out_val,
+                      float* out_loc, int* out_bin, cudaStream_t st);
+
+// Stage 2b standalone: the full dB pseudo-spectrum [nframes][P].
+int launch_scan_spectrum(const float2* u, const float2* G, const ScanTables& tb, int nframes, float* out,
+                         cudaStream_t st);
+
+// Stage 4 standalone on arbitrary float vectors.
+int launch_find_local_max(const float* in, int len, int nframes, int K, const float* xaxis, float* out_val,
+                          float* out_loc, int* out_bin, cudaStream_t st);
+
+// Stage 3: polynomial (from u) -> companion-matrix eigenvalues -> root selection -> angles.
+// scratch: (2M-2)^2 * stride double2 (frame-interleaved working matrices), stride >= nframes.
+int launch_rootmusic_scratch(const float2* u, int M, int T, float norm_spacing, int nframes, double2* scratch,
+                             long long stride, float* out, cudaStream_t st);
+
+// Development knobs (doa_cuda_dev_set): kernel-variant selection for A/B measurements; defaults are the shipped path.
+int dev_option(const char* key, int dflt);
+
+// Host-side table construction (reference constructor arithmetic).
+void build_music_tables(float norm_spacing, int M, int P, std::vector<float>& array_loc, std::vector<float>& theta,
+                        std::vector<float2>& V, std::vector<float2>& z);
+void build_x_axis(int len, float x_min, float x_max, std::vector<float>& x);
+
+}  // namespace doa

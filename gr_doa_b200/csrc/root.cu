@@ -1,0 +1,164 @@
+// root.cu -- stage 3: Root-MUSIC polynomial roots as eigenvalues of the Frobenius companion matrix.
+//
+// Replaces get_roots_polynomial() + the root selection of rootMUSIC_linear_array_impl::work
+// (gr-doa lib/rootMUSIC_linear_array_impl.cc:68-87,119-145; LAPACK cgeev there).
+//
+// The polynomial sum_k a_k x^k, a_{M-1+l} = u_l, a_{M-1-l} = conj(u_l) (u_l = l-th diagonal sum of U_N U_N^H, :74-79)
+// is normalised by -1/a_n (:80) into the last column of the (2M-2)x(2M-2) companion matrix (ones on the first
+// sub-diagonal, :55-58,83).  The matrix is already upper Hessenberg, so its eigenvalues come from a shifted complex QR
+// iteration with deflation, one thread per frame, in float64: the reference's float32 cgeev is itself only good to
+// ~1e-2 degree on these nearly-double roots, float64 roots agree with a float64 LAPACK twin to ~1e-6 degree (tests).
+// The working matrix lives in a frame-interleaved global scratch (element (i,j) of frame f at ((i*n+j)*stride + f)),
+// so neighbouring threads touch neighbouring addresses; it stays L1/L2 resident for the sizes gr-doa uses (n = 6..30).
+// Root selection repeats the reference's float arithmetic (:122-141): dist = 1 - |z| in float, strictly inside only,
+// the T closest to the circle, angle = 180*acos(arg(z)/(2 pi d))/pi with the double math of :136, ascending sort.
+#include "doa_internal.h"
+
+namespace doa {
+namespace {
+
+struct cplx { double x, y; };
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cplx cconj(cplx a) { return {a.x, -a.y}; }
+__device__ __forceinline__ cplx cneg(cplx a) { return {-a.x, -a.y}; }
+__device__ __forceinline__ double cabs1(cplx a) { return fabs(a.x) + fabs(a.y); }
+__device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
+  const double d = b.x * b.x + b.y * b.y;
+  return {(a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d};
+}
+__device__ __forceinline__ cplx csqrt_(cplx a) {
+  const double m = hypot(a.x, a.y);
+  if (m == 0.0) return {0.0, 0.0};
+  double re = sqrt(0.5 * (m + fabs(a.x)));
+  double im = 0.5 * a.y / re;
+  if (a.x < 0.0) { const double t = re; re = fabs(im); im = (a.y < 0.0) ? -t : t; }
+  return {re, im};
+}
+
+struct Hmat {
+  double2* base; long long stride; int n;
+  __device__ __forceinline__ cplx get(int i, int j) const { const double2 v = base[((long long)i * n + j) * stride]; return {v.x, v.y}; }
+  __device__ __forceinline__ void set(int i, int j, cplx v) const { base[((long long)i * n + j) * stride] = make_double2(v.x, v.y); }
+};
+
+__global__ void __launch_bounds__(128)
+rootmusic_kernel(const float2* __restrict__ u, int M, int T, float norm_spacing, int nframes, double2* __restrict__ scratch,
+                 long long stride, float* __restrict__ out) {
+  const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nframes) return;
+  const int n = 2 * M - 2;
+  Hmat H{scratch + f, stride, n};
+  const float2* uf = u + f * M;
+
+  // companion matrix
+  const cplx an = {(double)uf[M - 1].x, (double)uf[M - 1].y};       // a_n = u_{M-1}
+  const cplx scale = cdiv({-1.0, 0.0}, an);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) H.set(i, j, {(i == j + 1) ? 1.0 : 0.0, 0.0});
+  for (int k = 0; k < n; ++k) {
+    const int l = k - (M - 1);
+    cplx a;
+    if (l >= 0) a = {(double)uf[l].x, l == 0 ? 0.0 : (double)uf[l].y};
+    else a = {(double)uf[-l].x, -(double)uf[-l].y};
+    H.set(k, n - 1, cmul(scale, a));
+  }
+
+  // shifted QR with deflation on the active window [l, hi]
+  const double eps = 2.220446049250313e-16;
+  bool failed = false;
+  int hi = n - 1, iter = 0;
+  while (hi >= 0) {
+    int l = hi;
+    while (l > 0) {
+      double s = cabs1(H.get(l - 1, l - 1)) + cabs1(H.get(l, l));
+      if (s == 0.0) s = 1.0;
+      if (cabs1(H.get(l, l - 1)) < eps * s) { H.set(l, l - 1, {0.0, 0.0}); break; }
+      --l;
+    }
+    if (l == hi) { --hi; iter = 0; continue; }
+    if (iter >= 60) { failed = true; break; }
+    cplx sigma;
+    if (iter == 10 || iter == 20 || iter == 40) {
+      sigma = {fabs(H.get(hi, hi - 1).x) + (hi >= 2 ? fabs(H.get(hi - 1, hi - 2).x) : 0.0), 0.0};
+    } else {   // Wilkinson: eigenvalue of the trailing 2x2 closest to its last diagonal entry
+      const cplx a = H.get(hi - 1, hi - 1), b = H.get(hi - 1, hi), c = H.get(hi, hi - 1), d = H.get(hi, hi);
+      const cplx hd = {0.5 * (a.x - d.x), 0.5 * (a.y - d.y)};
+      const cplx disc = csqrt_(cadd(cmul(hd, hd), cmul(b, c)));
+      const cplx mid = {0.5 * (a.x + d.x), 0.5 * (a.y + d.y)};
+      const cplx e1 = cadd(mid, disc), e2 = csub(mid, disc);
+      sigma = (cabs1(csub(e1, d)) <= cabs1(csub(e2, d))) ? e1 : e2;
+    }
+    ++iter;
+    for (int i = l; i <= hi; ++i) H.set(i, i, csub(H.get(i, i), sigma));
+    cplx pc = {1.0, 0.0}, ps = {0.0, 0.0};   // previous rotation
+    for (int k = l; k < hi; ++k) {
+      const cplx x = H.get(k, k), y = H.get(k + 1, k);
+      const double r = sqrt(x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y);
+      cplx c = {1.0, 0.0}, s = {0.0, 0.0};
+      if (r > 0.0) { c = {x.x / r, x.y / r}; s = {y.x / r, y.y / r}; }
+      // rows k, k+1 <- [[conj(c), conj(s)], [-s, c]] * rows
+      for (int j = k; j <= hi; ++j) {
+        const cplx a = H.get(k, j), b = H.get(k + 1, j);
+        H.set(k, j, cadd(cmul(cconj(c), a), cmul(cconj(s), b)));
+        H.set(k + 1, j, cadd(cmul(cneg(s), a), cmul(c, b)));
+      }
+      if (k > l) {   // columns k-1, k <- cols * [[pc, -conj(ps)], [ps, conj(pc)]], rows l..k
+        for (int i = l; i <= k; ++i) {
+          const cplx a = H.get(i, k - 1), b = H.get(i, k);
+          H.set(i, k - 1, cadd(cmul(a, pc), cmul(b, ps)));
+          H.set(i, k, cadd(cmul(cneg(a), cconj(ps)), cmul(b, cconj(pc))));
+        }
+      }
+      pc = c; ps = s;
+    }
+    for (int i = l; i <= hi; ++i) {
+      const cplx a = H.get(i, hi - 1), b = H.get(i, hi);
+      H.set(i, hi - 1, cadd(cmul(a, pc), cmul(b, ps)));
+      H.set(i, hi, cadd(cmul(cneg(a), cconj(ps)), cmul(b, cconj(pc))));
+    }
+    for (int i = l; i <= hi; ++i) H.set(i, i, cadd(H.get(i, i), sigma));
+  }
+
+  // root selection, float arithmetic of the reference
+  float* of = out + f * T;
+  unsigned long long used0 = 0ull, used1 = 0ull;
+  const double two_pi_d = 2.0 * 3.14159265358979323846 * (double)norm_spacing;
+  for (int ii = 0; ii < T; ++ii) {
+    float best = INFINITY; int bk = -1; float bre = 0.f, bim = 0.f;
+    if (!failed) {
+      for (int k = 0; k < n; ++k) {
+        const bool used = (k < 64) ? ((used0 >> k) & 1ull) : ((used1 >> (k - 64)) & 1ull);
+        if (used) continue;
+        const cplx z = H.get(k, k);
+        const float re = (float)z.x, im = (float)z.y;
+        const float dist = 1.0f - hypotf(re, im);
+        if (dist > 0.0f && dist < best) { best = dist; bk = k; bre = re; bim = im; }
+      }
+    }
+    float aoa = __int_as_float(0x7fc00000);   // NaN: fewer than T roots strictly inside (reference undefined there)
+    if (bk >= 0) {
+      if (bk < 64) used0 |= 1ull << bk; else used1 |= 1ull << (bk - 64);
+      aoa = (float)(180.0 * acos((double)atan2f(bim, bre) / two_pi_d) / 3.14159265358979323846);
+    }
+    // insertion into the ascending prefix of[0..ii) (NaNs stay at the end)
+    int pos = ii;
+    while (pos > 0 && !(of[pos - 1] <= aoa) && !(aoa != aoa)) { of[pos] = of[pos - 1]; --pos; }
+    of[pos] = aoa;
+  }
+}
+
+}  // namespace
+
+// scratch: caller-provided, at least (2M-2)^2 * stride double2, stride >= nframes.
+int launch_rootmusic_scratch(const float2* u, int M, int T, float norm_spacing, int nframes, double2* scratch,
+                             long long stride, float* out, cudaStream_t st) {
+  if (nframes <= 0) return 0;
+  const int threads = 128;
+  const int blocks = (nframes + threads - 1) / threads;
+  rootmusic_kernel<<<blocks, threads, 0, st>>>(u, M, T, norm_spacing, nframes, scratch, stride, out);
+  return 1;
+}
+
+}  // namespace doa

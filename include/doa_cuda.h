@@ -1,0 +1,109 @@
+/* doa_cuda.h -- C ABI of libdoa_cuda, the B200 (sm_100a) implementation of gr-doa's DoA hot path.
+ *
+ * One opaque handle per GNU Radio block instance.  Every entry point takes plain pointers and sizes; complex
+ * samples are interleaved float pairs (gr_complex).  Every function returns 0 on success or a negative
+ * DOA_CUDA_E* code; doa_cuda_last_error(handle) gives the text.  No exception crosses this boundary and no
+ * CPU fallback exists behind it: without a usable CUDA device, *_create fails.
+ *
+ * Each stage S in {autocorrelate, music, rootmusic, find_local_max} has
+ *     doa_cuda_S_create      the block constructor   (same parameters as S::make in the reference)
+ *     doa_cuda_S_run         the body of work()/general_work(): HOST pointers, synchronous
+ *     doa_cuda_S_run_device  the same on DEVICE pointers, asynchronous on the caller's stream
+ *     doa_cuda_S_destroy
+ * plus doa_cuda_chain_* = autocorrelate -> MUSIC_lin_array -> find_local_max fused, peaks only.
+ *
+ * Reference interfaces replaced (paths relative to the gr-doa tree):
+ *     autocorrelate::make / general_work / forecast     include/doa/autocorrelate.h:56, lib/autocorrelate_impl.cc:47-118
+ *     MUSIC_lin_array::make / work                      include/doa/MUSIC_lin_array.h:56, lib/MUSIC_lin_array_impl.cc:47-150
+ *     rootMUSIC_linear_array::make / work               include/doa/rootMUSIC_linear_array.h:54, lib/rootMUSIC_linear_array_impl.cc:46-152
+ *     find_local_max::make / work                       include/doa/find_local_max.h:56, lib/find_local_max_impl.cc:47-194
+ */
+#ifndef DOA_CUDA_H
+#define DOA_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOA_CUDA_OK 0
+#define DOA_CUDA_EINVAL (-1)    /* bad argument (also the GRC <check>s: overlap < snapshot, inputs > targets, spacing <= 0.5) */
+#define DOA_CUDA_ECUDA (-2)     /* a CUDA runtime call failed */
+#define DOA_CUDA_ENOMEM (-3)    /* host or device allocation failed */
+#define DOA_CUDA_ECAPACITY (-4) /* nframes exceeds the max_frames given at create */
+
+typedef struct doa_cuda_handle doa_cuda_handle; /* opaque; one per block instance, owns a stream + staging */
+
+int doa_cuda_abi_version(void);
+/* Text of the last error on this handle (or of the last failed *_create when handle == NULL). */
+const char* doa_cuda_last_error(const doa_cuda_handle* h);
+int doa_cuda_device_count(void);
+
+/* ---- stage 1: autocorrelate (lib/autocorrelate_impl.cc) --------------------------------------------------
+ * R[r,c] = (1/N) sum_t x_r[t] conj(x_c[t]); avg_method 1 adds the reference's forward-backward term
+ * 0.5 R + (0.5/N) J conj(R) J (including its extra 1/N).  Output: nframes x (M*M) complex, column-major. */
+int doa_cuda_autocorrelate_create(doa_cuda_handle** h, int inputs, int snapshot_size, int overlap_size, int avg_method,
+                                  int device, int max_frames);
+/* in_host: `inputs` pointers, each to hop*(nframes-1)+snapshot_size complex samples (hop = snapshot-overlap;
+ * frame i of channel k starts at in_host[k] + i*hop, exactly as general_work() reads them). */
+int doa_cuda_autocorrelate_run(doa_cuda_handle* h, const void* const* in_host, int nframes, void* out_host);
+/* Device form.  Sample (frame f, channel k, time t) is at in_dev[f*frame_stride + k*chan_stride + t] (strides in
+ * complex samples): streaming = (hop, stream_len); independent frames [B][M][N] = (M*N, N). */
+int doa_cuda_autocorrelate_run_device(doa_cuda_handle* h, const void* in_dev, long long frame_stride, long long chan_stride,
+                                      int nframes, void* out_dev, void* cuda_stream);
+/* forecast(): input items required per port for noutput_items (lib/autocorrelate_impl.cc:74-80). */
+int doa_cuda_autocorrelate_forecast(const doa_cuda_handle* h, int noutput_items);
+
+/* ---- stage 2: MUSIC_lin_array (lib/MUSIC_lin_array_impl.cc) ------------------------------------------------
+ * in: nframes x (M*M) complex column-major covariance; out: nframes x pspectrum_len float, dB, peak = 0. */
+int doa_cuda_music_create(doa_cuda_handle** h, float norm_spacing, int num_targets, int num_ant_ele, int pspectrum_len,
+                          int device, int max_frames);
+int doa_cuda_music_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_host);
+int doa_cuda_music_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_dev, void* cuda_stream);
+/* Host copies of the constructor tables (for table-parity tests): array_loc[M], theta_rad[P], steering[P][M] complex. */
+int doa_cuda_music_get_tables(const doa_cuda_handle* h, float* array_loc, float* theta_rad, float* steering);
+
+/* ---- stage 3: rootMUSIC_linear_array (lib/rootMUSIC_linear_array_impl.cc) ------------------------------------
+ * in: nframes x (M*M) complex; out: nframes x num_targets float, degrees ascending (NaN where the reference is
+ * undefined: fewer than num_targets roots strictly inside the unit circle). */
+int doa_cuda_rootmusic_create(doa_cuda_handle** h, float norm_spacing, int num_targets, int num_ant_ele, int device,
+                              int max_frames);
+int doa_cuda_rootmusic_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_host);
+int doa_cuda_rootmusic_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_dev, void* cuda_stream);
+
+/* ---- stage 4: find_local_max (lib/find_local_max_impl.cc) ----------------------------------------------------
+ * in: nframes x vector_len float; out_val: nframes x K peak heights (descending), out_loc: nframes x K x-axis
+ * locations (descending by x, as the reference sorts them), out_bin (optional, may be NULL): nframes x K int32
+ * peak bins in out_val order (not a block port; exported for bit-exact comparisons). */
+int doa_cuda_find_local_max_create(doa_cuda_handle** h, int num_max_vals, int vector_len, float x_min, float x_max,
+                                   int device, int max_frames);
+int doa_cuda_find_local_max_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_val_host,
+                                void* out_loc_host, void* out_bin_host);
+int doa_cuda_find_local_max_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_val_dev,
+                                       void* out_loc_dev, void* out_bin_dev, void* cuda_stream);
+
+/* ---- fused chain: autocorrelate -> MUSIC_lin_array -> find_local_max(K, P, x_min, x_max), peaks only ----------- */
+int doa_cuda_chain_create(doa_cuda_handle** h, int inputs, int snapshot_size, int overlap_size, int avg_method,
+                          float norm_spacing, int num_targets, int pspectrum_len, int num_max_vals, float x_min,
+                          float x_max, int device, int max_frames);
+int doa_cuda_chain_run_device(doa_cuda_handle* h, const void* in_dev, long long frame_stride, long long chan_stride,
+                              int nframes, void* out_val_dev, void* out_loc_dev, void* out_bin_dev, void* cuda_stream);
+/* Host form on independent frames [nframes][inputs][snapshot_size] complex (pageable or pinned): copies are
+ * chunked and overlapped with the kernels on the handle's own streams; returns when the outputs are in host memory. */
+int doa_cuda_chain_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_val_host, void* out_loc_host,
+                       void* out_bin_host);
+/* Streaming host form (what an autocorrelate block feeding the chain sees): `inputs` channel pointers. */
+int doa_cuda_chain_run_streams(doa_cuda_handle* h, const void* const* in_host, int nframes, void* out_val_host,
+                               void* out_loc_host, void* out_bin_host);
+/* Number of kernel launches issued by the last run on this handle (for bench accounting). */
+int doa_cuda_last_launch_count(const doa_cuda_handle* h);
+/* CUDA-event time in ms of each stage of the last chain run_device (cov, eig, scan); needs a prior
+ * doa_cuda_set_profiling(h, 1).  Timing is on the stream the kernels ran on. */
+int doa_cuda_set_profiling(doa_cuda_handle* h, int on);
+int doa_cuda_chain_stage_ms(doa_cuda_handle* h, float* cov_ms, float* eig_ms, float* scan_ms);
+
+void doa_cuda_destroy(doa_cuda_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOA_CUDA_H */
