@@ -24,6 +24,7 @@ SYMBOLS = {
     "doa_cuda_music_run": (_i, [_vp, _vp, _i, _vp]),
     "doa_cuda_music_run_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "doa_cuda_music_get_tables": (_i, [_vp, _vp, _vp, _vp]),
+    "doa_cuda_music_noise_subspace_device": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "doa_cuda_rootmusic_create": (_i, [_hp, _f, _i, _i, _i, _i]),
     "doa_cuda_rootmusic_run": (_i, [_vp, _vp, _i, _vp]),
     "doa_cuda_rootmusic_run_device": (_i, [_vp, _vp, _i, _vp, _vp]),

@@ -126,6 +126,17 @@ class MUSIC_lin_array(_Block):
         check(self._L.doa_cuda_music_get_tables(self._h, loc.ctypes.data, th.ctypes.data, V.ctypes.data), self._h)
         return loc, th, V
 
+    def noise_subspace_device(self, R):
+        """eig_sym + U_N*trans(U_N) only: returns (G [n][M*M] c64, u [n][M] c64, eigenvalues [n][M] f32) CUDA tensors."""
+        import torch
+        n, M = R.shape[0], self.num_ant_ele
+        G = torch.empty((n, M * M), dtype=torch.complex64, device=R.device)
+        u = torch.empty((n, M), dtype=torch.complex64, device=R.device)
+        w = torch.empty((n, M), dtype=torch.float32, device=R.device)
+        check(self._L.doa_cuda_music_noise_subspace_device(self._h, R.data_ptr(), n, G.data_ptr(), u.data_ptr(), w.data_ptr(),
+                                                           _stream_ptr()), self._h)
+        return G, u, w
+
     def work(self, R):
         M = self.num_ant_ele
         R = _np(R, np.complex64).reshape(-1, M * M)
@@ -220,8 +231,11 @@ class DoaChain(_Block):
         check(self._L.doa_cuda_set_profiling(self._h, int(on)), self._h)
 
     def stage_ms(self):
+        """Mean (cov, eig, scan) CUDA-event ms over the run_device calls since set_profiling(True)."""
         a, b, c = C.c_float(), C.c_float(), C.c_float()
-        check(self._L.doa_cuda_chain_stage_ms(self._h, C.byref(a), C.byref(b), C.byref(c)), self._h)
+        n = self._L.doa_cuda_chain_stage_ms(self._h, C.byref(a), C.byref(b), C.byref(c))
+        if n < 0:
+            check(n, self._h)
         return a.value, b.value, c.value
 
     def run_device(self, x, out=None, frame_stride=None, chan_stride=None, nframes=None):

@@ -86,8 +86,10 @@ struct doa_cuda_handle {
   std::string err;
   int launches = 0;
   bool profiling = false;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> ev;   // profiling: 4 events per recorded chain call (ring of PROF_SETS calls)
+  int prof_calls = 0;
 };
+static const int PROF_SETS = 256;
 
 static thread_local std::string g_create_err;
 
@@ -277,6 +279,19 @@ int doa_cuda_music_get_tables(const doa_cuda_handle* h, float* array_loc, float*
   return DOA_CUDA_OK;
 }
 
+int doa_cuda_music_noise_subspace_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* G_dev, void* u_dev,
+                                         void* w_dev, void* cuda_stream) {
+  if (!h || (h->kind != K_MUSIC && h->kind != K_ROOTMUSIC && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
+  if (nframes <= 0) return nframes == 0 ? DOA_CUDA_OK : fail(h, DOA_CUDA_EINVAL, "nframes < 0");
+  CK(h, cudaSetDevice(h->device));
+  int a = launch_noise_subspace((const float2*)in_dev, h->M, h->T, nframes, (float2*)G_dev, (float2*)u_dev, (float*)w_dev,
+                                (cudaStream_t)cuda_stream);
+  if (a < 0) return fail(h, a, "eigendecomposition launch rejected");
+  h->launches = a;
+  CK(h, cudaGetLastError());
+  return DOA_CUDA_OK;
+}
+
 int doa_cuda_music_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_dev, void* cuda_stream) {
   if (!h || h->kind != K_MUSIC) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
@@ -439,22 +454,23 @@ int doa_cuda_chain_create(doa_cuda_handle** out, int inputs, int snapshot_size, 
          dalloc(&l.R, nf * mm) && dalloc(&l.G, nf * mm) && dalloc(&l.u, nf * h->M) && dalloc(&l.val, nf * h->K) &&
          dalloc(&l.loc, nf * h->K) && dalloc(&l.bin, nf * h->K);
   }
-  for (auto& e : h->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
   return finish_create(out, h, ok);
 }
 
 static int chain_on_lane(doa_cuda_handle* h, Lane& l, const float2* in_dev, long long frame_stride, long long chan_stride,
                          int nframes, float* val, float* loc, int* bin, cudaStream_t st, bool prof) {
-  if (prof) CK(h, cudaEventRecord(h->ev[0], st));
+  cudaEvent_t* ev = nullptr;
+  if (prof) { ev = &h->ev[(size_t)(h->prof_calls % PROF_SETS) * 4]; ++h->prof_calls; }
+  if (prof) CK(h, cudaEventRecord(ev[0], st));
   int a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st);
   if (a < 0) return fail(h, a, "covariance launch rejected");
-  if (prof) CK(h, cudaEventRecord(h->ev[1], st));
+  if (prof) CK(h, cudaEventRecord(ev[1], st));
   int b = launch_noise_subspace(l.R, h->M, h->T, nframes, l.G, l.u, nullptr, st);
   if (b < 0) return fail(h, b, "eigendecomposition launch rejected");
-  if (prof) CK(h, cudaEventRecord(h->ev[2], st));
+  if (prof) CK(h, cudaEventRecord(ev[2], st));
   int c = launch_scan_peaks(l.u, l.G, tables_of(h), nframes, h->K, val, loc, bin, st);
   if (c < 0) return fail(h, c, "scan launch rejected (pspectrum_len too large for shared memory?)");
-  if (prof) CK(h, cudaEventRecord(h->ev[3], st));
+  if (prof) CK(h, cudaEventRecord(ev[3], st));
   h->launches += a + b + c;
   CK(h, cudaGetLastError());
   return DOA_CUDA_OK;
@@ -520,23 +536,38 @@ int doa_cuda_chain_run_streams(doa_cuda_handle* h, const void* const* in_host, i
 }
 
 int doa_cuda_set_profiling(doa_cuda_handle* h, int on) {
-  if (!h) return DOA_CUDA_EINVAL;
+  if (!h || h->kind != K_CHAIN) return DOA_CUDA_EINVAL;
+  CK(h, cudaSetDevice(h->device));
+  if (on && h->ev.empty()) {
+    h->ev.assign((size_t)PROF_SETS * 4, nullptr);
+    for (auto& e : h->ev) CK(h, cudaEventCreate(&e));
+  }
   h->profiling = on != 0;
+  h->prof_calls = 0;
   return DOA_CUDA_OK;
 }
 
+// Mean CUDA-event time of each stage over the chain run_device calls recorded since profiling was switched on
+// (the last PROF_SETS of them); returns the number of calls averaged, or a negative error.
 int doa_cuda_chain_stage_ms(doa_cuda_handle* h, float* cov_ms, float* eig_ms, float* scan_ms) {
-  if (!h || h->kind != K_CHAIN || !h->profiling) return DOA_CUDA_EINVAL;
+  if (!h || h->kind != K_CHAIN || h->ev.empty()) return DOA_CUDA_EINVAL;
   CK(h, cudaSetDevice(h->device));
-  CK(h, cudaEventSynchronize(h->ev[3]));
-  float a = 0, b = 0, c = 0;
-  CK(h, cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
-  CK(h, cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
-  CK(h, cudaEventElapsedTime(&c, h->ev[2], h->ev[3]));
-  if (cov_ms) *cov_ms = a;
-  if (eig_ms) *eig_ms = b;
-  if (scan_ms) *scan_ms = c;
-  return DOA_CUDA_OK;
+  const int n = std::min(h->prof_calls, PROF_SETS);
+  double a = 0, b = 0, c = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaEvent_t* ev = &h->ev[(size_t)i * 4];
+    CK(h, cudaEventSynchronize(ev[3]));
+    float x = 0, y = 0, z = 0;
+    CK(h, cudaEventElapsedTime(&x, ev[0], ev[1]));
+    CK(h, cudaEventElapsedTime(&y, ev[1], ev[2]));
+    CK(h, cudaEventElapsedTime(&z, ev[2], ev[3]));
+    a += x; b += y; c += z;
+  }
+  if (n > 0) { a /= n; b /= n; c /= n; }
+  if (cov_ms) *cov_ms = (float)a;
+  if (eig_ms) *eig_ms = (float)b;
+  if (scan_ms) *scan_ms = (float)c;
+  return n;
 }
 
 }  // extern "C"

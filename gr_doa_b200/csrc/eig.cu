@@ -47,7 +47,7 @@ template <int M> __host__ __device__ constexpr int pair_p(int s, int k) { return
 template <int M> __host__ __device__ constexpr int pair_q(int s, int k) { return pair_a<M>(s, k) < pair_b<M>(s, k) ? pair_b<M>(s, k) : pair_a<M>(s, k); }
 
 template <int M, int S>
-__device__ __forceinline__ void jacobi_step(float2 (&a)[M], float2 (&v)[M], const int j) {
+__device__ __forceinline__ void jacobi_step(float2 (&a)[M], float2 (&v)[M], const int j, const bool frozen) {
   constexpr int HP = M / 2;
   constexpr unsigned FULL = 0xffffffffu;
   // my diagonal entry, my partner, my role and my copy of the pivot
@@ -63,7 +63,8 @@ __device__ __forceinline__ void jacobi_step(float2 (&a)[M], float2 (&v)[M], cons
     if (j == q) { partner = p; is_p = false; piv = a[p]; }
   }
   const float dpart = __shfl_sync(FULL, dj, partner, M);
-  const Rot mine = make_rotation(is_p ? dj : dpart, is_p ? dpart : dj, piv);
+  Rot mine = make_rotation(is_p ? dj : dpart, is_p ? dpart : dj, piv);
+  if (frozen) { mine.c = 1.0f; mine.sx = 0.0f; mine.sy = 0.0f; }
   // the M/2 rotations of this step, as lane p_k computed them
   float ck[HP], sxk[HP], syk[HP];
 #pragma unroll
@@ -104,10 +105,10 @@ __device__ __forceinline__ void jacobi_step(float2 (&a)[M], float2 (&v)[M], cons
 }
 
 template <int M, int S>
-__device__ __forceinline__ void jacobi_sweep(float2 (&a)[M], float2 (&v)[M], const int j) {
+__device__ __forceinline__ void jacobi_sweep(float2 (&a)[M], float2 (&v)[M], const int j, const bool frozen) {
   if constexpr (S < M - 1) {
-    jacobi_step<M, S>(a, v, j);
-    jacobi_sweep<M, S + 1>(a, v, j);
+    jacobi_step<M, S>(a, v, j, frozen);
+    jacobi_sweep<M, S + 1>(a, v, j, frozen);
   }
 }
 
@@ -146,8 +147,10 @@ jacobi_group_kernel(const float2* __restrict__ R, int T, int nframes, float2* __
   }
   __syncwarp();
 
+  // Convergence is decided PER MATRIX and latched: a converged matrix only sees identity rotations (exact no-ops) while
+  // its warp-mates finish, so a frame's result never depends on which other frames share its warp.
+  bool done = false;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    // convergence: off-diagonal mass against the diagonal mass, per matrix
     float off = 0.0f, dg = 0.0f;
 #pragma unroll
     for (int i = 0; i < M; ++i) {
@@ -161,9 +164,9 @@ jacobi_group_kernel(const float2* __restrict__ R, int T, int nframes, float2* __
     }
     // fp32 rotations leave off-diagonal mass of order M^2 * eps^2 * dg; once within ~4x of that floor the next sweep
     // (quadratic convergence) cannot improve the subspace any further
-    const bool conv = off <= dg * (1.5e-14f * M * M);
-    if (__all_sync(FULL, conv)) break;
-    jacobi_sweep<M, 0>(a, v, j);
+    done = done || (off <= dg * (1.5e-14f * M * M));
+    if (__all_sync(FULL, done)) break;
+    jacobi_sweep<M, 0>(a, v, j, done);
   }
 
   // eigenvalue of this lane's column, its ascending rank (ties by column index)

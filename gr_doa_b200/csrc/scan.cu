@@ -9,7 +9,7 @@
 // of the M*(M+1) of the literal v^H G v.  The scan evaluates it by Horner with z read from a per-plan table
 // (the grid is uniform in theta, not in psi, so z has no recurrence).  The bins the chain reports are then
 // re-evaluated with the reference's own arithmetic -- v^H G v on the steering table the constructor builds, same
-// operation order as the oracle -- in a +-2 bin window, so peak bins and peak heights follow the reference's rounding.
+// operation order as a plain C++ loop (row = v^H G, then row . v) -- in a +-2 bin window, so peak bins and peak heights follow the reference's rounding.
 //
 // Mapping: one warp per frame, lane L owns the contiguous bins [L*S, (L+1)*S), S = ceil(P/32).  Peak picking is a
 // sequential state machine per lane (rise .. plateau .. fall, the plateau rule of find_local_max_impl.cc:92-107),
@@ -167,7 +167,7 @@ __device__ __forceinline__ float q_coarse(const float2 (&u)[MT > 0 ? MT : 1], co
   }
 }
 
-// v^H G v in the reference's operation order (row = v^H G first, then row . v), plain fp32 multiplies and adds.
+// v^H G v in the reference operation order (row = v^H G first, then row . v), plain fp32 multiplies and adds.
 __device__ __forceinline__ float q_faithful(const float2* __restrict__ G, const float2* __restrict__ v, int M) {
   float qx = 0.0f, qy = 0.0f;
   for (int c = 0; c < M; ++c) {

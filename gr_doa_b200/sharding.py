@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing for the DoA chain: frames are independent (the reference's work() loops never carry state
+across frames: lib/autocorrelate_impl.cc:92, lib/MUSIC_lin_array_impl.cc:121, lib/find_local_max_impl.cc:179), so the
+path shards by frame index with no data-path collective.  One process per GPU (torchrun); rank r owns the contiguous
+block of frames shard_range(B, r, world).  The only exchange is ONE gather of the per-frame peaks (value, location, bin
+= 12*K bytes per frame) to rank 0, over torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+
+Streaming inputs (hop < snapshot) shard the same way: rank r additionally needs the `overlap` samples that precede
+its first frame's end -- the host hands every rank its slab plus that halo (stream_slab), exactly GNU Radio's
+history()-1 (lib/autocorrelate_impl.cc:57); no inter-GPU sample exchange exists.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(nframes: int, rank: int, world: int):
+    """Contiguous, balanced block of frame indices [lo, hi) for `rank`; the first nframes % world ranks get one more."""
+    base, rem = divmod(nframes, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def stream_slab(nframes: int, rank: int, world: int, snapshot_size: int, overlap_size: int):
+    """Sample range [s_lo, s_hi) of each channel stream that rank needs for its frames (halo included)."""
+    lo, hi = shard_range(nframes, rank, world)
+    hop = snapshot_size - overlap_size
+    if hi == lo:
+        return lo * hop, lo * hop
+    return lo * hop, (hi - 1) * hop + snapshot_size
+
+
+def pack_peaks(val: torch.Tensor, loc: torch.Tensor, bins: torch.Tensor) -> torch.Tensor:
+    """[n][K] f32, [n][K] f32, [n][K] i32 -> one [n][3K] int32 payload (bit-preserving)."""
+    return torch.cat([val.contiguous().view(torch.int32), loc.contiguous().view(torch.int32), bins.to(torch.int32)], dim=1)
+
+
+def unpack_peaks(payload: torch.Tensor, K: int):
+    return (payload[:, :K].contiguous().view(torch.float32), payload[:, K:2 * K].contiguous().view(torch.float32),
+            payload[:, 2 * K:].contiguous())
+
+
+def gather_peaks(val, loc, bins, nframes_total: int, dst: int = 0, group=None):
+    """One collective: every rank contributes its shard's peaks; rank `dst` returns (val, loc, bins) for all
+    nframes_total frames in frame order, the other ranks return None.  Shards may differ in length by one frame, so
+    the payload is padded to the longest shard (the pad rows are dropped on dst)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    K = val.shape[1]
+    if world == 1:
+        return val, loc, bins
+    rank = dist.get_rank(group)
+    longest = -(-nframes_total // world)
+    payload = pack_peaks(val, loc, bins)
+    if payload.shape[0] < longest:
+        payload = torch.cat([payload, payload.new_zeros((longest - payload.shape[0], 3 * K))], dim=0)
+    if rank == dst:
+        bufs = [torch.empty_like(payload) for _ in range(world)]
+        dist.gather(payload, bufs, dst=dst, group=group)
+        parts = []
+        for r in range(world):
+            lo, hi = shard_range(nframes_total, r, world)
+            parts.append(bufs[r][: hi - lo])
+        return unpack_peaks(torch.cat(parts, dim=0), K)
+    dist.gather(payload, None, dst=dst, group=group)
+    return None
+
+
+def run_sharded(chain_fn, frames_local, nframes_total: int, dst: int = 0, group=None):
+    """chain_fn(frames_local) -> (val, loc, bins) for this rank's frames; returns the gathered result on dst."""
+    val, loc, bins = chain_fn(frames_local)
+    return gather_peaks(val, loc, bins, nframes_total, dst=dst, group=group)

@@ -6,7 +6,7 @@
     s_k[t] = exp(j*(w_k*t + phase_k)),  w_k = pi/(k+2)         tone model of music_test_input_gen.m:36-37,97
     w ~ CN(0, 1)
 
-Two generators: numpy (host, seeded Philox; used by the parity tests so oracle and GPU see the same bytes)
+Two generators: numpy (host, seeded Philox; used by the parity tests so the CPU checker and the GPU see the same bytes)
 and torch (any device; used by bench.py to fill HBM without a host round trip).
 """
 import math

@@ -59,6 +59,11 @@ int doa_cuda_music_create(doa_cuda_handle** h, float norm_spacing, int num_targe
                           int device, int max_frames);
 int doa_cuda_music_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_host);
 int doa_cuda_music_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_dev, void* cuda_stream);
+/* The eigendecomposition half of the stage on its own (eig_sym + U_N*trans(U_N), lib/MUSIC_lin_array_impl.cc:128-133):
+ * G_dev nframes x (M*M) complex noise-subspace projector, u_dev nframes x M complex diagonal sums of G, w_dev nframes x M
+ * eigenvalues ascending; any of the three may be NULL.  Valid on music, rootmusic and chain handles. */
+int doa_cuda_music_noise_subspace_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* G_dev, void* u_dev,
+                                         void* w_dev, void* cuda_stream);
 /* Host copies of the constructor tables (for table-parity tests): array_loc[M], theta_rad[P], steering[P][M] complex. */
 int doa_cuda_music_get_tables(const doa_cuda_handle* h, float* array_loc, float* theta_rad, float* steering);
 
@@ -96,8 +101,10 @@ int doa_cuda_chain_run_streams(doa_cuda_handle* h, const void* const* in_host, i
                                void* out_loc_host, void* out_bin_host);
 /* Number of kernel launches issued by the last run on this handle (for bench accounting). */
 int doa_cuda_last_launch_count(const doa_cuda_handle* h);
-/* CUDA-event time in ms of each stage of the last chain run_device (cov, eig, scan); needs a prior
- * doa_cuda_set_profiling(h, 1).  Timing is on the stream the kernels ran on. */
+/* Stage timing of the chain's run_device calls: after doa_cuda_set_profiling(h, 1) every call brackets its three stages
+ * (covariance, eigendecomposition, scan+peaks) with CUDA events on the stream the kernels run on;
+ * doa_cuda_chain_stage_ms returns the number of calls recorded since then (the last 256 at most) and their mean stage
+ * times in ms, or a negative error. */
 int doa_cuda_set_profiling(doa_cuda_handle* h, int on);
 int doa_cuda_chain_stage_ms(doa_cuda_handle* h, float* cov_ms, float* eig_ms, float* scan_ms);
 

@@ -173,9 +173,10 @@ void noise_projector_f32(const cf* R, int M, int T, cf* G, std::vector<cf>& A, s
 // ---- stage 4 (lib/find_local_max_impl.cc:80-165, lib/find_local_max_impl.h:53-56) -----------------
 struct Packet { float val; unsigned idx; };
 
+// index_max(): Armadillo's direct_max starts from the most negative float and keeps the FIRST strictly greater value.
 unsigned index_max_first(const float* v, int len) {
-  unsigned best = 0; float bv = v[0];
-  for (int i = 1; i < len; ++i) if (v[i] > bv) { bv = v[i]; best = i; }
+  unsigned best = 0; float bv = -std::numeric_limits<float>::infinity();
+  for (int i = 0; i < len; ++i) if (v[i] > bv) { bv = v[i]; best = i; }
   return best;
 }
 

@@ -1,0 +1,262 @@
+"""GPU (-m gpu): libdoa_cuda through its C ABI against the CPU oracle and the committed golden fixtures.
+Tolerances: tests/parity.py (from BASELINE.json's north_star).  Every case goes through the host-pointer *_run entry
+points (what a GNU Radio work() calls) or the *_run_device ones; nothing here has a CPU path to fall back to."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from tests import parity
+from tests.test_golden import CASES, GOLDEN, load
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def test_native_library_is_loaded(doa):
+    from gr_doa_b200 import _lib
+    L = _lib.lib()
+    assert L.doa_cuda_device_count() >= 1
+    assert os.path.basename(_lib.LIB_PATH) == "libdoa_cuda.so"
+    with open("/proc/self/maps") as f:
+        assert "libdoa_cuda.so" in f.read()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASES)
+def test_golden_stage_by_stage(doa, name):
+    z, p = load(name)
+    M, T, N, P, K, d = p["M"], p["T"], p["N"], p["P"], p["K"], p["d"]
+    # stage 1
+    ac = doa.autocorrelate(M, N, p["overlap"], p["avg"], max_frames=64)
+    if p["stream"]:
+        assert ac.history() == p["overlap"] + 1 and ac.forecast(5) == 5 * (N - p["overlap"])
+        R, consumed = ac.general_work(p["nframes"], list(z["x"]))
+        assert consumed == (N - p["overlap"]) * p["nframes"]
+    else:
+        import torch
+        R = ac.work_device(torch.from_numpy(z["x"]).cuda()).cpu().numpy()
+    assert parity.rel_fro(R, z["R"]) <= parity.COV_REL_FRO
+    # stage 2 on the golden covariance (stage isolation)
+    mus = doa.MUSIC_lin_array(d, T, M, P, max_frames=64)
+    spec = mus.work(z["R"])
+    assert spec.shape == z["spec"].shape and spec.max() == 0.0
+    assert parity.spectrum_db_error(spec, z["spec"], z["q64"]) <= parity.SPECTRUM_DB
+    assert mus.nout_items_total == p["nframes"]
+    # stage 4 on the golden spectrum: bit-exact
+    flm = doa.find_local_max(K, P, 0.0, 180.0, max_frames=64)
+    val, loc, bins = flm.work(z["spec"], return_bins=True)
+    assert np.array_equal(val, z["val"]) and np.array_equal(loc, z["loc"]) and np.array_equal(bins, z["bins"])
+    # stage 3 on the golden covariance
+    rm = doa.rootMUSIC_linear_array(d, T, M, max_frames=64)
+    aoa = rm.work(z["R"])
+    assert np.abs(aoa - z["aoa64"]).max() <= parity.ROOT_DEG
+    assert np.abs(aoa - z["aoa"]).max() <= max(parity.ROOT_DEG, 2.0 * np.abs(z["aoa"] - z["aoa64"]).max())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_chain(doa, name):
+    z, p = load(name)
+    ch = doa.DoaChain(p["M"], p["N"], p["overlap"], p["avg"], p["d"], p["T"], p["P"], p["K"], max_frames=64)
+    val, loc, bins = ch.run_streams(list(z["x"]), p["nframes"]) if p["stream"] else ch.run_host(z["x"])
+    ndiff, unexplained = parity.classify_bins(bins, z["bins"], z["q64"], z["q32"])
+    assert unexplained == []
+    same = (np.sort(bins, 1) == np.sort(z["bins"], 1)).all(1)
+    assert np.array_equal(loc[same], z["loc"][same])                      # x-axis table and port-1 ordering are exact
+    assert np.all(val[:, 0] == 0.0)                                       # highest peak is the 0 dB reference
+    bound = parity.peak_value_bound_db(z["q64"], z["bins"], z["q32"])
+    assert np.all(np.abs(val[same] - z["val"][same]) <= bound[same])
+    assert ch.launches() == 3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+CONFIGS = [
+    # (M, T, N, P, K, thetas, avg, B)
+    (8, 3, 2048, 4096, 3, [40.0, 90.0, 140.0], 0, 2048),      # BASELINE configs[2] shape
+    (4, 1, 2048, 2048, 1, [60.0], 1, 1024),                   # configs[0] shape, independent frames
+    (4, 2, 2048, 1024, 2, [50.0, 110.0], 1, 1024),            # configs[1] shape
+    (16, 3, 1024, 4096, 3, [40.0, 90.0, 140.0], 0, 512),      # configs[4] shape
+]
+
+
+@pytest.mark.parametrize("M,T,N,P,K,thetas,avg,B", CONFIGS)
+def test_seeded_batch_against_oracle(doa, oracle, torch_cuda, M, T, N, P, K, thetas, avg, B):
+    from gr_doa_b200 import synth
+    fr, truth = synth.frames_numpy(B, M, N, thetas, jitter_deg=5.0 if T > 1 else 20.0, snr_db=10.0, seed=synth.SEED_BASE + 100 + M + T)
+    nt = oracle.max_threads()
+    R_o = oracle.autocorrelate_frames(fr, avg, nthreads=nt)
+    spec_o = oracle.music(R_o, 0.5, T, M, P, nthreads=nt)
+    q32 = oracle.music_q(R_o, 0.5, T, M, P, nthreads=nt)
+    q64 = oracle.music_f64(R_o, 0.5, T, M, P, nthreads=nt)
+    val_o, loc_o, bins_o = oracle.find_local_max(spec_o, K, 0.0, 180.0, nthreads=nt)
+
+    x = torch_cuda.from_numpy(fr).cuda()
+    ac = doa.autocorrelate(M, N, 0, avg, max_frames=B)
+    R_g = ac.work_device(x)
+    assert parity.rel_fro(R_g.cpu().numpy(), R_o) <= parity.COV_REL_FRO
+
+    mus = doa.MUSIC_lin_array(0.5, T, M, P, max_frames=B)
+    G, u, w = mus.noise_subspace_device(torch_cuda.from_numpy(R_o).cuda())
+    G_o, w_o = oracle.noise_projector(R_o, T, M, nthreads=nt)
+    G64, w64 = oracle.noise_projector_f64(R_o, T, M, nthreads=nt)
+    # eigenvalues ascending, as accurate as float32 LAPACK's against the float64 twin
+    assert np.abs(w.cpu().numpy() - w64).max() <= max(4.0 * np.abs(w_o - w64).max(), 1e-5 * np.abs(w64).max())
+    err_gpu = np.abs(G.cpu().numpy() - G64).max()
+    err_ref = np.abs(G_o - G64).max()
+    assert err_gpu <= max(4.0 * err_ref, 4e-6)                                           # projector as good as LAPACK's
+
+    spec_g = mus.work_device(torch_cuda.from_numpy(R_o).cuda()).cpu().numpy()
+    assert parity.spectrum_db_error(spec_g, spec_o, q64) <= parity.SPECTRUM_DB
+
+    ch = doa.DoaChain(M, N, 0, avg, 0.5, T, P, K, max_frames=B)
+    val, loc, bins = [t.cpu().numpy() for t in ch.run_device(x)]
+    ndiff, unexplained = parity.classify_bins(bins, bins_o, q64, q32)
+    assert unexplained == [], f"{len(unexplained)} of {ndiff} differing frames are not near-ties"
+    assert ndiff <= max(2, int(0.015 * B)), f"near-tie rate too high: {ndiff}/{B}"
+    same = (np.sort(bins, 1) == np.sort(bins_o, 1)).all(1)
+    assert np.array_equal(loc[same], loc_o[same])
+    assert np.all(np.abs(val[same] - val_o[same]) <= parity.peak_value_bound_db(q64, bins_o, q32)[same])
+    # and the estimates are right (grid step 180/P; jittered truths)
+    if T == K:
+        assert np.mean(np.abs(np.sort(loc, 1) - np.sort(truth, 1)).max(1) <= 1.0) > 0.995
+
+    rm = doa.rootMUSIC_linear_array(0.5, T, M, max_frames=B)
+    aoa = rm.work_device(torch_cuda.from_numpy(R_o).cuda()).cpu().numpy()
+    a64 = oracle.rootmusic_f64(R_o, 0.5, T, M, nthreads=nt)
+    a32 = oracle.rootmusic(R_o, 0.5, T, M, nthreads=nt)
+    assert np.abs(aoa - a64).max() <= parity.ROOT_DEG
+    assert np.abs(aoa - a32).max() <= max(parity.ROOT_DEG, 2.0 * np.abs(a32 - a64).max())
+
+
+def test_device_and_host_entry_points_agree_bit_for_bit(doa, torch_cuda):
+    from gr_doa_b200 import synth
+    fr, _ = synth.frames_numpy(96, 8, 512, [40.0, 90.0, 140.0], seed=5)
+    ch = doa.DoaChain(8, 512, 0, 0, 0.5, 3, 1024, 3, max_frames=96)
+    a = ch.run_host(fr)
+    b = [t.cpu().numpy() for t in ch.run_device(torch_cuda.from_numpy(fr).cuda())]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # the chain equals the three blocks run one after the other on the GPU (same kernels, spectrum never stored)
+    ac = doa.autocorrelate(8, 512, 0, 0, max_frames=96)
+    R = ac.work_device(torch_cuda.from_numpy(fr).cuda())
+    mus = doa.MUSIC_lin_array(0.5, 3, 8, 1024, max_frames=96)
+    spec = mus.work_device(R)
+    flm = doa.find_local_max(3, 1024, 0.0, 180.0, max_frames=96)
+    val, loc, bins = [t.cpu().numpy() for t in flm.work_device(spec)]
+    assert np.mean((np.sort(bins, 1) == np.sort(a[2], 1)).all(1)) > 0.95 and np.abs(np.sort(bins, 1) - np.sort(a[2], 1)).max() <= 1
+
+
+def test_tables_are_bit_identical_to_the_constructor_restatement(doa, oracle):
+    for d, M, P in ((0.5, 8, 4096), (0.4, 4, 1000), (0.5, 16, 2048), (0.37, 6, 777)):
+        mus = doa.MUSIC_lin_array(d, 1, M, P, max_frames=1)
+        loc, th, V = mus.tables()
+        lo, tho, Vo = oracle.music_tables(d, M, P)
+        assert np.array_equal(loc, lo) and np.array_equal(th, tho) and np.array_equal(V.view(np.float32), Vo.view(np.float32))
+
+
+# ---- ragged / odd shapes -----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,overlap,avg", [(4, 255, 31, 1), (8, 100, 7, 0), (6, 500, 123, 1), (3, 64, 0, 0), (12, 300, 45, 1),
+                                             (16, 1024, 256, 0), (32, 256, 0, 0), (64, 512, 64, 1), (2, 33, 32, 0)])
+def test_covariance_ragged_streams(doa, oracle, M, N, overlap, avg):
+    from gr_doa_b200 import synth
+    n = 9
+    x = synth.stream_numpy(n, M, N, overlap, [70.0], seed=M * 1000 + N)
+    ac = doa.autocorrelate(M, N, overlap, avg, max_frames=16)
+    got = ac.work(x)
+    exp = oracle.autocorrelate(x, N, overlap, avg)
+    assert got.shape == exp.shape == (n, M * M)
+    assert parity.rel_fro(got, exp) <= parity.COV_REL_FRO
+
+
+@pytest.mark.parametrize("M,T,P,K", [(6, 2, 1000, 2), (5, 1, 333, 1), (12, 4, 2048, 4), (8, 3, 4096, 5), (8, 2, 1024, 8),
+                                     (32, 4, 1024, 4), (3, 1, 100, 2)])
+def test_generic_sizes_chain(doa, oracle, M, T, P, K):
+    from gr_doa_b200 import synth
+    B, N = 48, 256
+    thetas = list(np.linspace(45.0, 135.0, T)) if T > 1 else [75.0]
+    fr, _ = synth.frames_numpy(B, M, N, thetas, snr_db=10.0, seed=M * 7 + P)
+    R = oracle.autocorrelate_frames(fr, 0)
+    spec = oracle.music(R, 0.5, T, M, P)
+    val_o, loc_o, bins_o = oracle.find_local_max(spec, K, 0.0, 180.0)
+    q32, q64 = oracle.music_q(R, 0.5, T, M, P), oracle.music_f64(R, 0.5, T, M, P)
+    ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
+    val, loc, bins = ch.run_host(fr)
+    if K <= T:   # with K > T the extra entries are rounding-noise peaks or the reference's fill-in: not comparable
+        ndiff, unexplained = parity.classify_bins(bins, bins_o, q64, q32)
+        assert unexplained == []
+    else:
+        strongest = np.sort(bins[:, :T], 1), np.sort(bins_o[:, :T], 1)
+        assert np.abs(strongest[0] - strongest[1]).max() <= 1
+    mus = doa.MUSIC_lin_array(0.5, T, M, P, max_frames=B)
+    assert parity.spectrum_db_error(mus.work(R), spec, q64) <= parity.SPECTRUM_DB
+    rm = doa.rootMUSIC_linear_array(0.5, T, M, max_frames=B)
+    assert np.nanmax(np.abs(rm.work(R) - oracle.rootmusic_f64(R, 0.5, T, M))) <= parity.ROOT_DEG
+
+
+# ---- find_local_max: bit-exact on anything ---------------------------------------------------------------------------------
+def unambiguous(vecs, K):
+    """Rows whose K highest local peaks are well defined.  The reference orders equal peak heights with an unstable
+    std::sort (sort_index, find_local_max_impl.cc:137), so WHICH of several equal-height peaks it reports is
+    implementation-defined [ext]; a row is unambiguous when its K+1 highest peak heights are pairwise different."""
+    out = []
+    for v in np.asarray(vecs):
+        pk = np.where((v[1:-1] >= v[:-2]) & (v[1:-1] >= v[2:]))[0] + 1      # superset of the reference's peaks
+        top = np.sort(v[pk])[::-1][: K + 1]
+        out.append(len(set(top.tolist())) == len(top))
+    return np.array(out)
+
+
+def test_find_local_max_golden_vectors(doa):
+    z = np.load(os.path.join(GOLDEN, "find_local_max.npz"))
+    for K in (1, 2, 3, 5, 8):
+        flm = doa.find_local_max(K, z["vecs"].shape[1], 0.0, 2 * np.pi, max_frames=16)
+        val, loc, bins = flm.work(z["vecs"], return_bins=True)
+        assert np.array_equal(val, z[f"val{K}"])                      # heights are always bit-exact
+        ok = unambiguous(z["vecs"], K)
+        assert ok.sum() >= 3
+        assert np.array_equal(bins[ok], z[f"bins{K}"][ok]) and np.array_equal(loc[ok], z[f"loc{K}"][ok])
+
+
+@pytest.mark.parametrize("length,K", [(37, 2), (64, 3), (1000, 3), (2048, 5), (4096, 3), (4096, 16), (5000, 1), (31, 4)])
+def test_find_local_max_random_and_plateaus(doa, oracle, length, K):
+    rng = np.random.default_rng(length * 31 + K)
+    n = 64
+    vecs = rng.standard_normal((n, length)).astype(np.float32)
+    vecs[n // 2:] = np.round(vecs[n // 2:] * 1.5) / 1.5                  # plateaus, flat tails, exact ties
+    vecs[0] = 0.0                                                          # all equal: no peak, arg-max = bin 0
+    vecs[1] = np.arange(length)                                            # monotone up
+    vecs[2] = -np.arange(length)                                           # monotone down
+    vecs[3] = 0.0; vecs[3, length // 2] = 1.0                              # exactly one peak -> fill-in rule
+    flm = doa.find_local_max(K, length, -3.0, 11.0, max_frames=n)
+    val, loc, bins = flm.work(vecs, return_bins=True)
+    val_o, loc_o, bins_o = oracle.find_local_max(vecs, K, -3.0, 11.0)
+    assert np.array_equal(val, val_o)                                      # heights are always bit-exact
+    ok = unambiguous(vecs, K)
+    assert ok.sum() >= n // 4
+    assert np.array_equal(bins[ok], bins_o[ok]) and np.array_equal(loc[ok], loc_o[ok])
+
+
+# ---- error behaviour -----------------------------------------------------------------------------------------------------
+def test_capacity_and_empty_batches(doa):
+    from gr_doa_b200 import _lib
+    ac = doa.autocorrelate(4, 64, 16, 0, max_frames=4)
+    x = np.zeros((4, 48 * 9 + 64), np.complex64)
+    with pytest.raises(_lib.DoaCudaError) as ei:
+        ac.general_work(5, list(x))
+    assert ei.value.code == _lib.ECAPACITY
+    out, consumed = ac.general_work(0, list(x))
+    assert out.shape == (0, 16) and consumed == 0
+    mus = doa.MUSIC_lin_array(0.5, 1, 4, 128, max_frames=4)
+    assert mus.work(np.zeros((0, 16), np.complex64)).shape == (0, 128)
+    ch = doa.DoaChain(4, 64, 0, 0, 0.5, 1, 128, 1, max_frames=4)
+    v, l, b = ch.run_host(np.zeros((0, 4, 64), np.complex64))
+    assert v.shape == (0, 1)
+    with pytest.raises(_lib.DoaCudaError):
+        ch.run_host(np.zeros((5, 4, 64), np.complex64))

@@ -1,0 +1,76 @@
+"""GPU (-m gpu): BASELINE.json's full single-GPU size (configs[2]: 65,536 x 8 x 2048, P 4096) checked through
+size-independent properties, plus an oracle spot check on a random subset of the very same device buffer."""
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+B, M, N, T, P, K = 65536, 8, 2048, 3, 4096, 3
+
+
+@pytest.fixture(scope="module")
+def full(doa):
+    import torch
+    from gr_doa_b200 import synth
+    x, truth = synth.frames_torch(B, M, N, [40.0, 90.0, 140.0], jitter_deg=5.0, snr_db=10.0, device="cuda")
+    ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
+    val, loc, bins = ch.run_device(x)
+    torch.cuda.synchronize()
+    return dict(x=x, truth=truth, ch=ch, val=val, loc=loc, bins=bins, torch=torch)
+
+
+def test_every_frame_finds_its_sources(full):
+    loc = np.sort(full["loc"].cpu().numpy(), 1)
+    truth = np.sort(full["truth"].cpu().numpy(), 1)
+    err = np.abs(loc - truth).max(1)
+    assert np.mean(err <= 1.0) >= 0.999 and np.median(err) < 0.25
+    val = full["val"].cpu().numpy()
+    assert np.all(val[:, 0] == 0.0) and np.all(val <= 0.0) and np.all(np.diff(val, axis=1) <= 0.0)
+    assert np.all(np.diff(full["loc"].cpu().numpy(), axis=1) <= 0.0)           # port 1 is sorted descending by x
+    bins = full["bins"].cpu().numpy()
+    assert bins.min() >= 1 and bins.max() <= P - 2                              # end points are never peaks
+
+
+def test_frames_are_independent(full):
+    """Any permutation / sub-batch of the frames gives the same per-frame answer, bit for bit (what sharding relies on)."""
+    torch = full["torch"]
+    perm = torch.randperm(4096, device="cuda")
+    sub = full["x"][:4096][perm].contiguous()
+    v, l, b = full["ch"].run_device(sub)
+    assert torch.equal(v, full["val"][:4096][perm]) and torch.equal(l, full["loc"][:4096][perm]) and torch.equal(b, full["bins"][:4096][perm])
+    v2, l2, b2 = full["ch"].run_device(full["x"][B // 2:])
+    assert torch.equal(b2, full["bins"][B // 2:]) and torch.equal(v2, full["val"][B // 2:])
+
+
+def test_power_of_two_scaling_is_exact(full):
+    """x -> 4x scales R by 16 exactly in float32, every Jacobi rotation and every ratio is unchanged: same bins, same dB."""
+    torch = full["torch"]
+    sub = (full["x"][:2048] * 4.0).contiguous()
+    v, l, b = full["ch"].run_device(sub)
+    assert torch.equal(b, full["bins"][:2048]) and torch.equal(v, full["val"][:2048])
+
+
+def test_array_reversal_mirrors_the_angles(full):
+    """Reversing the element order maps theta -> 180 - theta (a(theta) reversed = a(180-theta)): bins mirror to P - bin."""
+    torch = full["torch"]
+    sub = torch.flip(full["x"][:2048], dims=[1]).contiguous()
+    v, l, b = full["ch"].run_device(sub)
+    mirrored = np.sort(P - b.cpu().numpy(), 1)
+    ref = np.sort(full["bins"][:2048].cpu().numpy(), 1)
+    assert np.mean(np.abs(mirrored - ref).max(1) <= 1) > 0.99
+
+
+def test_oracle_spot_check_on_the_resident_buffer(full, oracle):
+    rng = np.random.default_rng(3)
+    pick = np.sort(rng.choice(B, 192, replace=False))
+    fr = full["x"][full["torch"].from_numpy(pick).cuda()].cpu().numpy()
+    nt = oracle.max_threads()
+    R = oracle.autocorrelate_frames(fr, 0, nthreads=nt)
+    spec = oracle.music(R, 0.5, T, M, P, nthreads=nt)
+    q32, q64 = oracle.music_q(R, 0.5, T, M, P, nthreads=nt), oracle.music_f64(R, 0.5, T, M, P, nthreads=nt)
+    val_o, loc_o, bins_o = oracle.find_local_max(spec, K, 0.0, 180.0, nthreads=nt)
+    bins = full["bins"].cpu().numpy()[pick]
+    ndiff, unexplained = parity.classify_bins(bins, bins_o, q64, q32)
+    assert unexplained == [] and ndiff <= 6
