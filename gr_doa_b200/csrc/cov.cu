@@ -274,7 +274,7 @@ int launch_small(const float2* in, long long fs, long long cs, int N, int nframe
                  float bscale, int avg, cudaStream_t st) {
   const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
   const int blocks = (nframes + COV_WARPS - 1) / COV_WARPS;
-  const int variant = dev_option("cov_groups", 2);
+  const int variant = dev_option("cov_groups", 1);   // 1: 128 regs, 2 CTAs/SM (6.4 TB/s at M=8); 2: 167 regs, 1 CTA/SM (5.9 TB/s)
   if (vec2) {
     if (variant == 1) cov_small_kernel<M, 2, 1><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg);
     else cov_small_kernel<M, 2, 2><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg);

@@ -23,19 +23,25 @@ namespace {
 
 struct Rot { float c; float sx, sy; };   // J_pp = J_qq = c, J_pq = sigma = (sx, sy), J_qp = -conj(sigma)
 
-// Rotation annihilating the (p,q) entry of a Hermitian 2x2 [[app, apq],[conj(apq), aqq]].
+// Rotation annihilating the (p,q) entry of a Hermitian 2x2 [[app, apq],[conj(apq), aqq]]:
+//   zeta = (aqq-app)/(2|apq|), t = sgn(zeta)/(|zeta|+sqrt(zeta^2+1)), c = 1/sqrt(1+t^2), s = t c, sigma = s apq/|apq|.
+// Built from MUFU rsqrt/rcp (4 special-function ops) instead of IEEE sqrt/div sequences (~100 instructions): c and s
+// share one relative error e, so J = (1+e) * (exact unitary) -- orthogonality of V is untouched, only its column norms
+// drift by O(1e-7) per rotation, and the columns are renormalised once at the end.  A t that is 1 ulp off just leaves
+// a pivot residue of 1e-7 |apq| for the next sweep.
 __device__ __forceinline__ Rot make_rotation(float app, float aqq, float2 apq) {
   Rot r; r.c = 1.0f; r.sx = 0.0f; r.sy = 0.0f;
-  const float b2 = apq.x * apq.x + apq.y * apq.y;
+  const float b2 = fmaf(apq.x, apq.x, apq.y * apq.y);
   if (b2 > 1e-36f) {
-    const float b = sqrtf(b2);
-    const float zeta = (aqq - app) / (2.0f * b);
+    const float inv_b = rsqrtf(b2);
+    float zeta = 0.5f * (aqq - app) * inv_b;
+    zeta = fminf(fmaxf(zeta, -1e18f), 1e18f);               // keep zeta^2 finite; |t| ~ 1/(2|zeta|) either way
     const float az = fabsf(zeta);
-    float t = 1.0f / (az + sqrtf(fmaf(zeta, zeta, 1.0f)));   // zeta^2 overflow -> t = 0, harmless
+    const float w = fmaf(zeta, zeta, 1.0f);
+    float t = __frcp_rn(az + w * rsqrtf(w));                 // sqrt(w) = w * rsqrt(w)
     t = (zeta < 0.0f) ? -t : t;
-    const float c = 1.0f / sqrtf(fmaf(t, t, 1.0f));
-    const float s = t * c;
-    const float sb = s / b;
+    const float c = rsqrtf(fmaf(t, t, 1.0f));
+    const float sb = t * c * inv_b;
     r.c = c; r.sx = sb * apq.x; r.sy = sb * apq.y;
   }
   return r;
@@ -169,6 +175,15 @@ jacobi_group_kernel(const float2* __restrict__ R, int T, int nframes, float2* __
     jacobi_sweep<M, 0>(a, v, j, done);
   }
 
+  // undo the accumulated norm drift of the fast rotations: unit eigenvectors
+  {
+    float n2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) n2 = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, n2));
+    const float sc = 1.0f / sqrtf(n2);
+#pragma unroll
+    for (int i = 0; i < M; ++i) { v[i].x *= sc; v[i].y *= sc; }
+  }
   // eigenvalue of this lane's column, its ascending rank (ties by column index)
   float lam = 0.0f;
 #pragma unroll

@@ -473,7 +473,9 @@ int oracle_rootmusic(const float* R, int nframes, float norm_spacing, int T, int
 }
 
 // float64 twin of stage 3 (zheevd + zgeev on the same fp32 R; same selection rule evaluated in double).
-int oracle_rootmusic_f64(const float* R, int nframes, float norm_spacing, int T, int M, double* out, int nthreads) {
+// dist (optional) [n][T]: 1-|z| of the selected roots, in selection order -- the conditioning of the frame: a selected root
+// closer to the circle than ~1e-3 is a nearly double root that float32 coefficients cannot place inside or outside reliably.
+int oracle_rootmusic_f64(const float* R, int nframes, float norm_spacing, int T, int M, double* out, double* dist, int nthreads) {
   const int n = 2 * M - 2;
 #pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
   {
@@ -510,6 +512,7 @@ int oracle_rootmusic_f64(const float* R, int nframes, float norm_spacing, int T,
         for (size_t k = 1; k < din.size(); ++k) if (din[k] < din[mi]) mi = k;
         if (std::isinf(din[mi])) break;
         aoa[ii] = 180.0 * std::acos(std::arg(rin[mi]) / (2 * kPi * (double)norm_spacing)) / kPi;
+        if (dist) dist[(size_t)i * T + ii] = din[mi];
         din[mi] = std::numeric_limits<double>::infinity();
       }
       std::sort(aoa.begin(), aoa.end(), [](double a, double b) { return a < b; });

@@ -137,11 +137,14 @@ def rootmusic(R, norm_spacing, num_targets, M, nthreads=1, return_roots=False):
     return (out, roots) if return_roots else out
 
 
-def rootmusic_f64(R, norm_spacing, num_targets, M, nthreads=1):
+def rootmusic_f64(R, norm_spacing, num_targets, M, nthreads=1, return_dist=False):
+    """float64 twin of Root-MUSIC.  return_dist: also 1-|z| of the selected roots (the frame's conditioning)."""
     R = _c64(R).reshape(-1, M * M)
     out = np.empty((R.shape[0], num_targets), np.float64)
-    lib().oracle_rootmusic_f64(_p(R), R.shape[0], C.c_float(norm_spacing), num_targets, M, _p(out, C.c_double), nthreads)
-    return out
+    dist = np.full((R.shape[0], num_targets), np.nan, np.float64)
+    lib().oracle_rootmusic_f64(_p(R), R.shape[0], C.c_float(norm_spacing), num_targets, M, _p(out, C.c_double),
+                               _p(dist, C.c_double), nthreads)
+    return (out, dist) if return_dist else out
 
 
 def x_axis(length, x_min, x_max):

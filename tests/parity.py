@@ -17,6 +17,19 @@ ROOT_DEG = 1e-4
 NEAR_TIE_SAFETY = 8.0
 
 
+ROOT_NEAR_CIRCLE = 4e-4      # ~ sqrt(float32 coefficient noise): closer than this, inside/outside is not decidable
+
+
+def root_angles_ok(aoa_gpu, aoa64, dist64):
+    """Root-MUSIC criterion: within ROOT_DEG of the float64 twin on every well-conditioned frame.  A frame whose selected
+    root sits within ROOT_NEAR_CIRCLE of the unit circle has a nearly double root (z, 1/conj z): coefficient noise of 1e-7
+    moves such roots by ~sqrt(1e-7) and decides which twin is "strictly inside" (lib/rootMUSIC_linear_array_impl.cc:125);
+    the reference's own float32 cgeev flips on those frames too.  Returns (worst error on good frames, #near-circle)."""
+    good = np.nanmin(dist64, axis=1) >= ROOT_NEAR_CIRCLE
+    worst = float(np.abs(aoa_gpu[good] - aoa64[good]).max()) if good.any() else 0.0
+    return worst, int((~good).sum())
+
+
 def rel_fro(a, b):
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
 

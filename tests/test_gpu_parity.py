@@ -130,10 +130,12 @@ def test_seeded_batch_against_oracle(doa, oracle, torch_cuda, M, T, N, P, K, the
 
     rm = doa.rootMUSIC_linear_array(0.5, T, M, max_frames=B)
     aoa = rm.work_device(torch_cuda.from_numpy(R_o).cuda()).cpu().numpy()
-    a64 = oracle.rootmusic_f64(R_o, 0.5, T, M, nthreads=nt)
+    a64, d64 = oracle.rootmusic_f64(R_o, 0.5, T, M, nthreads=nt, return_dist=True)
     a32 = oracle.rootmusic(R_o, 0.5, T, M, nthreads=nt)
-    assert np.abs(aoa - a64).max() <= parity.ROOT_DEG
-    assert np.abs(aoa - a32).max() <= max(parity.ROOT_DEG, 2.0 * np.abs(a32 - a64).max())
+    worst, near_circle = parity.root_angles_ok(aoa, a64, d64)
+    assert worst <= parity.ROOT_DEG and near_circle <= max(2, B // 50)
+    good = np.nanmin(d64, axis=1) >= parity.ROOT_NEAR_CIRCLE
+    assert np.abs(aoa[good] - a32[good]).max() <= max(parity.ROOT_DEG, 2.0 * np.abs(a32[good] - a64[good]).max())
 
 
 def test_device_and_host_entry_points_agree_bit_for_bit(doa, torch_cuda):
@@ -197,7 +199,9 @@ def test_generic_sizes_chain(doa, oracle, M, T, P, K):
     mus = doa.MUSIC_lin_array(0.5, T, M, P, max_frames=B)
     assert parity.spectrum_db_error(mus.work(R), spec, q64) <= parity.SPECTRUM_DB
     rm = doa.rootMUSIC_linear_array(0.5, T, M, max_frames=B)
-    assert np.nanmax(np.abs(rm.work(R) - oracle.rootmusic_f64(R, 0.5, T, M))) <= parity.ROOT_DEG
+    a64, d64 = oracle.rootmusic_f64(R, 0.5, T, M, return_dist=True)
+    worst, near_circle = parity.root_angles_ok(rm.work(R), a64, d64)
+    assert worst <= parity.ROOT_DEG and near_circle <= 2
 
 
 # ---- find_local_max: bit-exact on anything ---------------------------------------------------------------------------------

@@ -15,3 +15,12 @@ for it in range(5):
     out = ch.run_device(x)
 torch.cuda.synchronize()
 print("stage ms (cov, eig, scan):", ch.stage_ms(), "B", B)
+import subprocess
+print(subprocess.run("nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,temperature.gpu,clocks_event_reasons.active --format=csv,noheader", shell=True, capture_output=True, text=True).stdout.strip())
+for rep in range(3):
+    ch.set_profiling(True)
+    for it in range(20):
+        out = ch.run_device(x)
+    torch.cuda.synchronize()
+    print("stage ms (cov, eig, scan) mean of 20:", ch.stage_ms())
+print(subprocess.run("nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,temperature.gpu,clocks_event_reasons.active --format=csv,noheader", shell=True, capture_output=True, text=True).stdout.strip())
