@@ -1,0 +1,76 @@
+"""The GNU Radio block sources (gr_doa_b200/gnuradio/lib/*_impl.cc) compiled against the compile-only shim and driven by
+the fake scheduler (history / forecast / consume_each, scheduler-chosen noutput_items), like python/qa_*.py drive the
+reference blocks through a top_block.  CPU part: they compile and link.  GPU part: outputs against the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import parity
+from tests.conftest import ROOT
+
+
+def harness():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("build_harness", os.path.join(ROOT, "gr_doa_b200", "gnuradio", "build_harness.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build()
+
+
+def test_block_sources_compile_against_the_shim():
+    from gr_doa_b200 import build as lib_build
+    lib_build.build()
+    exe = harness()
+    assert os.access(exe, os.X_OK)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+
+
+def test_boundary_files_keep_the_reference_interface():
+    base = os.path.join(ROOT, "gr_doa_b200", "gnuradio")
+    want = {
+        "doa_autocorrelate.xml": "doa.autocorrelate($inputs, $snapshot_size, $overlap_size, $avg_method)",
+        "doa_MUSIC_lin_array.xml": "doa.MUSIC_lin_array($norm_spacing, $num_targets, $inputs, $pspectrum_len)",
+        "doa_rootMUSIC_linear_array.xml": "doa.rootMUSIC_linear_array($norm_spacing, $num_targets, $inputs)",
+        "doa_find_local_max.xml": "doa.find_local_max($num_max_vals, $vector_len, $x_min, $x_max)",
+    }
+    for fn, make in want.items():
+        assert "<make>" + make + "</make>" in open(os.path.join(base, "grc", fn)).read()
+    swig = open(os.path.join(base, "swig", "doa_swig.i")).read()
+    for blk in ("autocorrelate", "MUSIC_lin_array", "rootMUSIC_linear_array", "find_local_max"):
+        assert f"GR_SWIG_BLOCK_MAGIC2(doa, {blk});" in swig
+        hdr = open(os.path.join(base, "include", "doa", blk + ".h")).read()
+        assert "static sptr make(" in hdr and "boost::shared_ptr<" + blk + ">" in hdr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,overlap,avg,T,P,K", [(4, 2048, 512, 1, 1, 2048, 1), (8, 256, 32, 0, 2, 1024, 2)])
+def test_fake_scheduler_flowgraph_matches_oracle(oracle, tmp_path, M, N, overlap, avg, T, P, K):
+    from gr_doa_b200 import synth
+    exe = harness()
+    nframes = 300
+    thetas = [60.0] if T == 1 else [50.0, 110.0]
+    x = synth.stream_numpy(nframes, M, N, overlap, thetas, seed=77 + M)
+    inp = tmp_path / "in.c64"
+    x.astype(np.complex64).tofile(inp)
+    r = subprocess.run([exe, str(inp), str(M), str(N), str(overlap), str(avg), "0.5", str(T), str(P), str(K), str(tmp_path / "out")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert f"frames {nframes}" in r.stdout and "Total output items produced: %d" % nframes in r.stdout
+    R = np.fromfile(tmp_path / "out.R.c64", np.complex64).reshape(nframes, M * M)
+    spec = np.fromfile(tmp_path / "out.spec.f32", np.float32).reshape(nframes, P)
+    val = np.fromfile(tmp_path / "out.val.f32", np.float32).reshape(nframes, K)
+    loc = np.fromfile(tmp_path / "out.loc.f32", np.float32).reshape(nframes, K)
+    aoa = np.fromfile(tmp_path / "out.aoa.f32", np.float32).reshape(nframes, T)
+    R_o = oracle.autocorrelate(x, N, overlap, avg)
+    assert parity.rel_fro(R, R_o) <= parity.COV_REL_FRO
+    q64 = oracle.music_f64(R, 0.5, T, M, P)
+    assert parity.spectrum_db_error(spec, oracle.music(R, 0.5, T, M, P), q64) <= parity.SPECTRUM_DB
+    v_o, l_o, b_o = oracle.find_local_max(spec, K, 0.0, 180.0)
+    assert np.array_equal(val, v_o) and np.array_equal(loc, l_o)          # block-to-block: bit-exact on the GPU spectrum
+    a64, d64 = oracle.rootmusic_f64(R, 0.5, T, M, return_dist=True)
+    worst, near = parity.root_angles_ok(aoa, a64, d64)
+    assert worst <= parity.ROOT_DEG and near <= 6
+    assert np.abs(np.sort(loc, 1) - np.sort(np.array(thetas))[None, :]).max() < 2.0     # the reference QA's own bound
