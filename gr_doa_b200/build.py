@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libdoa_cuda.so")
-SOURCES = ["doa_cuda.cu", "cov.cu", "eig.cu", "scan.cu", "root.cu"]
+SOURCES = ["doa_cuda.cu", "cov.cu", "eig.cu", "scan.cu", "root.cu", "fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
 
@@ -40,8 +40,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_one(src):
         obj = os.path.join(BUILD, src.replace(".cu", ".o"))
         srcp = os.path.join(CSRC, src)
-        hdr_m = max(os.path.getmtime(os.path.join(CSRC, "doa_internal.h")),
-                    os.path.getmtime(os.path.join(HERE, "..", "include", "doa_cuda.h")))
+        hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+        hdr_m = max([os.path.getmtime(h) for h in hdrs] + [os.path.getmtime(os.path.join(HERE, "..", "include", "doa_cuda.h"))])
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(srcp), hdr_m):
             return obj, ""
         r = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", srcp, "-o", obj], capture_output=True, text=True)

@@ -12,64 +12,10 @@
 //
 // cov_tiled_kernel (any M <= 64): one CTA per frame, time tiles staged in shared memory, 4x4 complex register
 // blocks over the lower block triangle, slices of the tile's time axis per thread, shared-memory fold at the end.
-#include "doa_internal.h"
+#include "cov_device.cuh"
 
 namespace doa {
 namespace {
-
-__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float2 ldg_stream2(const float2* p) {
-  float2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-  return v;
-}
-
-// Reduce-scatter over the warp: on entry every lane holds CNT partial sums a[0..CNT); on exit lane L holds the
-// full sums of max(1, CNT/32) consecutive elements starting at rs_base<CNT>(L).
-template <int CNT, int OFF>
-__device__ __forceinline__ void warp_reduce_scatter(float* a, unsigned lane) {
-  if constexpr (OFF >= 1) {
-    if constexpr (CNT > 1) {
-      constexpr int H = CNT / 2;
-      const bool up = (lane & OFF) != 0;
-#pragma unroll
-      for (int i = 0; i < H; ++i) {
-        const float send = up ? a[i] : a[i + H];
-        const float keep = up ? a[i + H] : a[i];
-        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-      }
-      warp_reduce_scatter<H, OFF / 2>(a, lane);
-    } else {
-      a[0] += __shfl_xor_sync(0xffffffffu, a[0], OFF);
-      warp_reduce_scatter<1, OFF / 2>(a, lane);
-    }
-  }
-}
-template <int CNT>
-__device__ __forceinline__ int rs_base(unsigned lane) {
-  if constexpr (CNT >= 32) return (int)lane * (CNT / 32);
-  else if constexpr (CNT == 16) return (int)(lane >> 1);
-  else if constexpr (CNT == 8) return (int)(lane >> 2);
-  else if constexpr (CNT == 4) return (int)(lane >> 3);
-  else if constexpr (CNT == 2) return (int)(lane >> 4);
-  else return 0;
-}
-
-// Scale + optional forward-backward average + Hermitian expansion of the folded sums in `red`
-// (layout: offdiag pair p=(r>c): red[2p], red[2p+1] with p = r(r-1)/2 + c; diagonals at red[M*(M-1) + r]).
-template <int M>
-__device__ __forceinline__ float2 folded_entry(const float* red, int r, int c, float scale) {
-  constexpr int NP = M * (M - 1) / 2;
-  if (r == c) return make_float2(red[2 * NP + r] * scale, 0.0f);
-  if (r > c) { const int p = r * (r - 1) / 2 + c; return make_float2(red[2 * p] * scale, red[2 * p + 1] * scale); }
-  const int p = c * (c - 1) / 2 + r;
-  return make_float2(red[2 * p] * scale, -(red[2 * p + 1] * scale));
-}
 
 constexpr int COV_WARPS = 8;
 
@@ -77,92 +23,14 @@ template <int M, int VEC, int G>
 __global__ void __launch_bounds__(COV_WARPS * 32, (G == 1 && M >= 8) ? 2 : 1)
 cov_small_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
                  float2* __restrict__ out, float scale, float bscale, int avg_method) {
-  constexpr int NP = M * (M - 1) / 2;
   constexpr int CNT = M * M;
   __shared__ float red_s[COV_WARPS][CNT];
   const unsigned lane = threadIdx.x & 31u;
   const int warp = threadIdx.x >> 5;
   float* red = red_s[warp];
-
   for (int f = blockIdx.x * COV_WARPS + warp; f < nframes; f += gridDim.x * COV_WARPS) {
-    const float2* base = in + (long long)f * frame_stride;
-    float dg[M];
-    float ore[NP > 0 ? NP : 1], oim[NP > 0 ? NP : 1];
-#pragma unroll
-    for (int r = 0; r < M; ++r) dg[r] = 0.0f;
-#pragma unroll
-    for (int p = 0; p < NP; ++p) { ore[p] = 0.0f; oim[p] = 0.0f; }
-
-    // G independent load groups per iteration (G*M LDG.128 in flight per lane).
-    for (int t0 = (int)lane * VEC; t0 < N; t0 += G * 32 * VEC) {
-      float2 x[G][VEC][M];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int t = t0 + g * 32 * VEC;
-        const bool ok = t < N;   // N % VEC == 0 is guaranteed by the launcher
-#pragma unroll
-        for (int k = 0; k < M; ++k) {
-          const float2* p = base + (long long)k * chan_stride + t;
-          if constexpr (VEC == 2) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) v = ldg_stream4(reinterpret_cast<const float4*>(p));
-            x[g][0][k] = make_float2(v.x, v.y);
-            x[g][1][k] = make_float2(v.z, v.w);
-          } else {
-            float2 v = make_float2(0.f, 0.f);
-            if (ok) v = ldg_stream2(p);
-            x[g][0][k] = v;
-          }
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g)
-#pragma unroll
-        for (int s = 0; s < VEC; ++s) {
-#pragma unroll
-          for (int r = 0; r < M; ++r) {
-            const float2 xr = x[g][s][r];
-            dg[r] = fmaf(xr.x, xr.x, dg[r]);
-            dg[r] = fmaf(xr.y, xr.y, dg[r]);
-#pragma unroll
-            for (int c = 0; c < r; ++c) {
-              const float2 xc = x[g][s][c];
-              const int p = r * (r - 1) / 2 + c;
-              ore[p] = fmaf(xr.x, xc.x, ore[p]);   // x_r conj(x_c)
-              ore[p] = fmaf(xr.y, xc.y, ore[p]);
-              oim[p] = fmaf(xr.y, xc.x, oim[p]);
-              oim[p] = fmaf(-xr.x, xc.y, oim[p]);
-            }
-          }
-        }
-    }
-
-    float a[CNT];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) { a[2 * p] = ore[p]; a[2 * p + 1] = oim[p]; }
-#pragma unroll
-    for (int r = 0; r < M; ++r) a[2 * NP + r] = dg[r];
-    warp_reduce_scatter<CNT, 16>(a, lane);
-    {
-      const int b = rs_base<CNT>(lane);
-      constexpr int F = CNT >= 32 ? CNT / 32 : 1;
-#pragma unroll
-      for (int i = 0; i < F; ++i) red[b + i] = a[i];
-    }
-    __syncwarp();
-    float2* o = out + (long long)f * CNT;
-    for (int e = (int)lane; e < CNT; e += 32) {
-      const int r = e % M, c = e / M;
-      float2 v = folded_entry<M>(red, r, c, scale);
-      if (avg_method == 1) {
-        // 0.5*R + (0.5/N) * J conj(R) J : (J conj(R) J)(r,c) = conj(R(M-1-r, M-1-c))   lib/autocorrelate_impl.cc:108
-        const float2 w = folded_entry<M>(red, M - 1 - r, M - 1 - c, scale);
-        v.x = __fadd_rn(__fmul_rn(0.5f, v.x), __fmul_rn(bscale, w.x));
-        v.y = __fadd_rn(__fmul_rn(0.5f, v.y), __fmul_rn(bscale, -w.y));
-      }
-      o[e] = v;
-    }
-    __syncwarp();
+    cov_warp_frame<M, VEC, G>(in + (long long)f * frame_stride, chan_stride, N, lane, red);
+    cov_warp_emit<M>(red, scale, bscale, avg_method, lane, out + (long long)f * CNT);
   }
 }
 
