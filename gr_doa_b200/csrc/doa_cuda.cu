@@ -462,6 +462,19 @@ static int chain_on_lane(doa_cuda_handle* h, Lane& l, const float2* in_dev, long
   cudaEvent_t* ev = nullptr;
   if (prof) { ev = &h->ev[(size_t)(h->prof_calls % PROF_SETS) * 4]; ++h->prof_calls; }
   if (prof) CK(h, cudaEventRecord(ev[0], st));
+  if (dev_option("fused", 1)) {
+    // one persistent kernel for the whole chain when the shape allows it; stage events collapse to (0, 0, total)
+    if (prof) { CK(h, cudaEventRecord(ev[1], st)); CK(h, cudaEventRecord(ev[2], st)); }
+    int f = launch_chain_fused(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, h->T, tables_of(h), h->K, val,
+                               loc, bin, st);
+    if (f < 0) return fail(h, f, "fused chain launch rejected");
+    if (f > 0) {
+      if (prof) CK(h, cudaEventRecord(ev[3], st));
+      h->launches += f;
+      CK(h, cudaGetLastError());
+      return DOA_CUDA_OK;
+    }
+  }
   int a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st);
   if (a < 0) return fail(h, a, "covariance launch rejected");
   if (prof) CK(h, cudaEventRecord(ev[1], st));

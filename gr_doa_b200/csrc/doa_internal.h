@@ -34,6 +34,12 @@ struct ScanTables {
 int launch_scan_peaks(const float2* u, const float2* G, const ScanTables& tb, int nframes, int K, float* out_val,
                       float* out_loc, int* out_bin, cudaStream_t st);
 
+// The whole chain in one persistent kernel (fused.cu).  Returns 1 if launched, 0 if the shape is not covered (the caller
+// then runs the three stage kernels), <0 on error.  Bit-identical to the three-kernel path.
+int launch_chain_fused(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
+                       int avg_method, int T, const ScanTables& tb, int K, float* out_val, float* out_loc, int* out_bin,
+                       cudaStream_t st);
+
 // Stage 2b standalone: the full dB pseudo-spectrum [nframes][P].
 int launch_scan_spectrum(const float2* u, const float2* G, const ScanTables& tb, int nframes, float* out,
                          cudaStream_t st);

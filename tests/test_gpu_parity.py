@@ -74,7 +74,7 @@ def test_golden_chain(doa, name):
     assert np.all(val[:, 0] == 0.0)                                       # highest peak is the 0 dB reference
     bound = parity.peak_value_bound_db(z["q64"], z["bins"], z["q32"])
     assert np.all(np.abs(val[same] - z["val"][same]) <= bound[same])
-    assert ch.launches() == 3
+    assert ch.launches() in (1, 3)            # 1 = fused persistent kernel, 3 = covariance, Jacobi, scan
 
 
 # ---------------------------------------------------------------------------------------------------------------------
