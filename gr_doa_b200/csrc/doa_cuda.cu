@@ -81,7 +81,7 @@ struct doa_cuda_handle {
   float d = 0.f, x_min = 0.f, x_max = 0.f;
   Lane lane[2];
   int nlanes = 1;
-  float2* d_z = nullptr; float2* d_V = nullptr; float* d_x = nullptr;
+  float2* d_z = nullptr; float2* d_V = nullptr; float* d_x = nullptr; float* d_zpair = nullptr;
   std::vector<float> h_loc, h_theta, h_x; std::vector<float2> h_V, h_z;
   std::string err;
   int launches = 0;
@@ -115,7 +115,7 @@ extern "C" void doa_cuda_destroy(doa_cuda_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (int i = 0; i < 2; ++i) free_lane(h->lane[i]);
-  cudaFree(h->d_z); cudaFree(h->d_V); cudaFree(h->d_x);
+  cudaFree(h->d_z); cudaFree(h->d_V); cudaFree(h->d_x); cudaFree(h->d_zpair);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
 }
@@ -151,7 +151,10 @@ static bool upload_scan_tables(doa_cuda_handle* h, bool need_steering, bool need
   bool ok = true;
   if (need_steering) {
     build_music_tables(h->d, h->M, h->P, h->h_loc, h->h_theta, h->h_V, h->h_z);
-    ok = ok && dalloc(&h->d_z, (size_t)h->P) && dalloc(&h->d_V, (size_t)h->P * h->M);
+    std::vector<float> zpair;
+    build_zpair_table(h->h_z, zpair);
+    ok = ok && dalloc(&h->d_z, (size_t)h->P) && dalloc(&h->d_V, (size_t)h->P * h->M) && dalloc(&h->d_zpair, zpair.size());
+    if (ok) ok = cudaMemcpy(h->d_zpair, zpair.data(), sizeof(float) * zpair.size(), cudaMemcpyHostToDevice) == cudaSuccess;
     if (ok) {
       ok = cudaMemcpy(h->d_z, h->h_z.data(), sizeof(float2) * h->P, cudaMemcpyHostToDevice) == cudaSuccess &&
            cudaMemcpy(h->d_V, h->h_V.data(), sizeof(float2) * (size_t)h->P * h->M, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -167,7 +170,7 @@ static bool upload_scan_tables(doa_cuda_handle* h, bool need_steering, bool need
 }
 
 static ScanTables tables_of(const doa_cuda_handle* h) {
-  ScanTables t; t.M = h->M; t.P = h->P; t.z = h->d_z; t.V = h->d_V; t.xaxis = h->d_x; return t;
+  ScanTables t; t.M = h->M; t.P = h->P; t.z = h->d_z; t.zpair = h->d_zpair; t.V = h->d_V; t.xaxis = h->d_x; return t;
 }
 
 extern "C" {

@@ -25,6 +25,7 @@ int launch_noise_subspace(const float2* R, int M, int T, int nframes, float2* G,
 struct ScanTables {
   int M = 0, P = 0;
   const float2* z = nullptr;      // [P]   e^{j*psi_i}, psi_i = 2*pi*d*cos(theta_i): the ULA phase step per element
+  const float* zpair = nullptr;   // the same z in the scan kernels' per-lane pair layout (scan_device.cuh: ZTab)
   const float2* V = nullptr;      // [P][M] steering table exactly as the reference constructor builds it
   const float* xaxis = nullptr;   // [P]   find_local_max x-axis (float-accumulated)
 };
@@ -60,5 +61,6 @@ int dev_option(const char* key, int dflt);
 void build_music_tables(float norm_spacing, int M, int P, std::vector<float>& array_loc, std::vector<float>& theta,
                         std::vector<float2>& V, std::vector<float2>& z);
 void build_x_axis(int len, float x_min, float x_max, std::vector<float>& x);
+void build_zpair_table(const std::vector<float2>& z, std::vector<float>& out);   // scan.cu
 
 }  // namespace doa

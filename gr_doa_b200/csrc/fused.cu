@@ -24,14 +24,14 @@ constexpr int FU_WARPS = 8;
 template <int M, int KL>
 __global__ void __launch_bounds__(FU_WARPS * 32, 2)
 chain_fused_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
-                   int avg_method, float scale, float bscale, int T, int max_sweeps, const float2* __restrict__ ztab,
+                   int avg_method, float scale, float bscale, int T, int max_sweeps, const float* __restrict__ zpair,
                    const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int P, int K,
                    float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin, int stagger) {
   constexpr int TILE = FU_WARPS * 32 / M;      // frames per tile = matrices the CTA's threads cover in phase 2
   constexpr int MM = M * M;
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
-  const ZTab zt = ztab_fill(smem, ztab, P);
+  const ZTab zt = ztab_fill(smem, zpair, P);
   float2* Rs = reinterpret_cast<float2*>(smem + ztab_floats(P));   // [TILE][M*M] covariance, then eigenvector staging
   float2* Gs = Rs + TILE * MM;                                     // [TILE][M*M] noise projector
   float2* us = Gs + TILE * MM;                                     // [TILE][M]   diagonal sums
@@ -89,7 +89,7 @@ int launch_fused_m(const float2* in, long long fs, long long cs, int N, int nfra
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::max(1, std::min(2 * sms, (nframes + TILE - 1) / TILE));
   const float scale = (float)(1.0 / N), bscale = (float)(0.5 / N);
-  kern<<<grid, FU_WARPS * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.z, tb.V, tb.xaxis, tb.P, K,
+  kern<<<grid, FU_WARPS * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.V, tb.xaxis, tb.P, K,
                                           out_val, out_loc, out_bin, dev_option("fused_stagger", 1));
   return 1;
 }

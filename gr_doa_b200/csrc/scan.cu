@@ -25,13 +25,14 @@ constexpr int SCAN_WARPS = 8;
 
 template <int MT, int KL>
 __global__ void __launch_bounds__(SCAN_WARPS * 32)
-scan_peaks_kernel(const float2* __restrict__ u, const float2* __restrict__ G, const float2* __restrict__ ztab,
+scan_peaks_kernel(const float2* __restrict__ u, const float2* __restrict__ G, const float* __restrict__ zpair,
                   const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int M, int P, int nframes, int K,
-                  float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin) {
+                  float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin, int z_in_smem) {
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
-  const ZTab zt = ztab_fill(smem, ztab, P);
-  float2* us_all = reinterpret_cast<float2*>(smem + ztab_floats(P));   // [SCAN_WARPS][M] (runtime-M path only)
+  // z table: staged in shared memory when it fits (conflict-free LDS.128), read in place from global memory otherwise
+  const ZTab zt = z_in_smem ? ztab_fill(smem, zpair, P) : ztab_view(zpair, P);
+  float2* us_all = reinterpret_cast<float2*>(smem + (z_in_smem ? ztab_floats(P) : 0));   // [SCAN_WARPS][M] (runtime-M path only)
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2* us = us_all + warp * (MT > 0 ? 0 : M);
@@ -139,10 +140,10 @@ find_local_max_kernel(const float* __restrict__ in, int len, int nframes, int K,
                       float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin) {
   extern __shared__ float fsm[];
   const int S = (len + 31) / 32, SP = S | 1;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   float* vs = fsm + (size_t)warp * 32 * SP;
   const int s0 = lane * S, s1 = min(len, s0 + S);
-  for (int f = blockIdx.x * FLM_WARPS + warp; f < nframes; f += gridDim.x * FLM_WARPS) {
+  for (int f = blockIdx.x * nwarps + warp; f < nframes; f += gridDim.x * nwarps) {
     const float* src = in + (size_t)f * len;
     __syncwarp();
     for (int i = lane; i < len; i += 32) vs[(i / S) * SP + (i % S)] = src[i];
@@ -207,18 +208,19 @@ int launch_peaks_mt(const float2* u, const float2* G, const ScanTables& tb, int 
                                                                   out_loc, out_bin);
     return 1;
   }
-  const size_t smem = ztab_floats(P) * sizeof(float) + (MT > 0 ? 0 : (size_t)SCAN_WARPS * M) * sizeof(float2);
-  if (smem > 200 * 1024) return DOA_CUDA_EINVAL;
+  const size_t us_bytes = (MT > 0 ? 0 : (size_t)SCAN_WARPS * M) * sizeof(float2);
+  const bool z_in_smem = ztab_floats(P) * sizeof(float) + us_bytes <= 200 * 1024;
+  const size_t smem = (z_in_smem ? ztab_floats(P) * sizeof(float) : 0) + us_bytes;
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1)));
   const int blocks = min(blocks_needed, sm_count() * per_sm);
   if (K <= 4) {
     auto kern = scan_peaks_kernel<MT, 4>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<blocks, SCAN_WARPS * 32, smem, st>>>(u, G, tb.z, tb.V, tb.xaxis, M, P, nframes, K, out_val, out_loc, out_bin);
+    kern<<<blocks, SCAN_WARPS * 32, smem, st>>>(u, G, tb.zpair, tb.V, tb.xaxis, M, P, nframes, K, out_val, out_loc, out_bin, (int)z_in_smem);
   } else {
     auto kern = scan_peaks_kernel<MT, 16>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<blocks, SCAN_WARPS * 32, smem, st>>>(u, G, tb.z, tb.V, tb.xaxis, M, P, nframes, K, out_val, out_loc, out_bin);
+    kern<<<blocks, SCAN_WARPS * 32, smem, st>>>(u, G, tb.zpair, tb.V, tb.xaxis, M, P, nframes, K, out_val, out_loc, out_bin, (int)z_in_smem);
   }
   return 1;
 }
@@ -232,6 +234,20 @@ int launch_spectrum_mt(const float2* u, const ScanTables& tb, int nframes, float
 }
 
 }  // namespace
+
+void build_zpair_table(const std::vector<float2>& z, std::vector<float>& out) {
+  const int P = (int)z.size();
+  out.assign(ztab_floats(P), 0.0f);
+  const ZTab zt = ztab_view(out.data(), P);
+  float* za = out.data(); float* zb = out.data() + 32 * zt.LA;
+  for (int i = 0; i < 32 * zt.S; ++i) {
+    const float2 v = z[std::min(i, P - 1)];
+    const int L = i / zt.S, k = i - L * zt.S;
+    za[L * zt.LA + (k >> 1) * 4 + (k & 1)] = v.x;
+    za[L * zt.LA + (k >> 1) * 4 + 2 + (k & 1)] = v.y;
+    zb[L * zt.LB + (k >> 1) * 2 + (k & 1)] = -v.y;
+  }
+}
 
 int launch_scan_peaks(const float2* u, const float2* G, const ScanTables& tb, int nframes, int K, float* out_val,
                       float* out_loc, int* out_bin, cudaStream_t st) {
@@ -264,18 +280,20 @@ int launch_find_local_max(const float* in, int len, int nframes, int K, const fl
   if (nframes <= 0) return 0;
   if (K < 1 || K > 16 || len < 1) return DOA_CUDA_EINVAL;
   const int S = (len + 31) / 32, SP = S | 1;
-  const size_t smem = (size_t)FLM_WARPS * 32 * SP * sizeof(float);
-  if (smem > 200 * 1024) return DOA_CUDA_EINVAL;
+  int warps = FLM_WARPS;                                        // fewer warps per CTA for very long vectors
+  while (warps > 1 && (size_t)warps * 32 * SP * sizeof(float) > 200 * 1024) warps >>= 1;
+  const size_t smem = (size_t)warps * 32 * SP * sizeof(float);
+  if (smem > 200 * 1024) return DOA_CUDA_EINVAL;                // vector_len beyond ~51k
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
-  const int blocks = min((nframes + FLM_WARPS - 1) / FLM_WARPS, sm_count() * per_sm);
+  const int blocks = min((nframes + warps - 1) / warps, sm_count() * per_sm);
   if (K <= 4) {
     auto kern = find_local_max_kernel<4>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<blocks, FLM_WARPS * 32, smem, st>>>(in, len, nframes, K, xaxis, out_val, out_loc, out_bin);
+    kern<<<blocks, warps * 32, smem, st>>>(in, len, nframes, K, xaxis, out_val, out_loc, out_bin);
   } else {
     auto kern = find_local_max_kernel<16>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<blocks, FLM_WARPS * 32, smem, st>>>(in, len, nframes, K, xaxis, out_val, out_loc, out_bin);
+    kern<<<blocks, warps * 32, smem, st>>>(in, len, nframes, K, xaxis, out_val, out_loc, out_bin);
   }
   return 1;
 }

@@ -215,22 +215,21 @@ struct ZTab {
 };
 
 
-// Fill the shared-memory z table (layout: ZTab) from the plan's global table; all threads of the CTA, then __syncthreads.
-__device__ __forceinline__ ZTab ztab_fill(float* smem, const float2* __restrict__ ztab, int P) {
+// The z table in ZTab layout is built once per plan on the host (build_zpair_table) and lives in global memory; kernels
+// copy it linearly into shared memory when it fits and otherwise read it in place (any P, just slower).
+__host__ __device__ inline size_t ztab_floats(int P) { const int S = 2 * ((P + 63) / 64); return (size_t)32 * ((2 * S + 4) + (S + 2)); }
+__host__ __device__ inline ZTab ztab_view(const float* base, int P) {
   const int S = 2 * ((P + 63) / 64);                        // bins per lane, even
   ZTab zt; zt.S = S; zt.LA = 2 * S + 4; zt.LB = S + 2;
-  float* za = smem; float* zb = smem + 32 * zt.LA;
-  zt.za = za; zt.zb = zb;
-  for (int i = threadIdx.x; i < 32 * S; i += blockDim.x) {
-    const float2 z = ztab[min(i, P - 1)];
-    const int L = i / S, k = i - L * S;
-    za[L * zt.LA + (k >> 1) * 4 + (k & 1)] = z.x;
-    za[L * zt.LA + (k >> 1) * 4 + 2 + (k & 1)] = z.y;
-    zb[L * zt.LB + (k >> 1) * 2 + (k & 1)] = -z.y;
-  }
+  zt.za = base; zt.zb = base + 32 * zt.LA;
   return zt;
 }
-__host__ __device__ inline size_t ztab_floats(int P) { const int S = 2 * ((P + 63) / 64); return (size_t)32 * ((2 * S + 4) + (S + 2)); }
+// All threads of the CTA; caller issues __syncthreads() afterwards.
+__device__ __forceinline__ ZTab ztab_fill(float* smem, const float* __restrict__ zpair, int P) {
+  const int n = (int)ztab_floats(P);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = zpair[i];
+  return ztab_view(smem, P);
+}
 
 // One frame by one warp: coarse scan over all P bins, peak picking, refinement with the reference arithmetic, dB
 // conversion, sorted outputs.  uf: the frame's M diagonal sums, Gf: its M x M projector (global or shared memory);

@@ -204,6 +204,33 @@ def test_generic_sizes_chain(doa, oracle, M, T, P, K):
     assert worst <= parity.ROOT_DEG and near_circle <= 2
 
 
+def test_large_array_shape_cfg4(doa, oracle, torch_cuda):
+    """BASELINE configs[3] shape on a handful of frames: 64 elements, 16,384 snapshots, 8 sources, 16,384-point scan, K = 8
+    (generic-M kernels: tiled covariance, CTA-per-matrix Jacobi, scan with the z table read from global memory)."""
+    from gr_doa_b200 import synth
+    B, M, N, T, P, K = 4, 64, 16384, 8, 16384, 8
+    thetas = list(np.linspace(30.0, 150.0, T))
+    fr, truth = synth.frames_numpy(B, M, N, thetas, snr_db=10.0, seed=64)
+    nt = oracle.max_threads()
+    R_o = oracle.autocorrelate_frames(fr, 0, nthreads=nt)
+    x = torch_cuda.from_numpy(fr).cuda()
+    ac = doa.autocorrelate(M, N, 0, 0, max_frames=B)
+    assert parity.rel_fro(ac.work_device(x).cpu().numpy(), R_o) <= parity.COV_REL_FRO
+    spec_o = oracle.music(R_o, 0.5, T, M, P, nthreads=nt)
+    q32, q64 = oracle.music_q(R_o, 0.5, T, M, P, nthreads=nt), oracle.music_f64(R_o, 0.5, T, M, P, nthreads=nt)
+    val_o, loc_o, bins_o = oracle.find_local_max(spec_o, K, 0.0, 180.0, nthreads=nt)
+    mus = doa.MUSIC_lin_array(0.5, T, M, P, max_frames=B)
+    assert parity.spectrum_db_error(mus.work(R_o), spec_o, q64) <= parity.SPECTRUM_DB
+    ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
+    val, loc, bins = [t.cpu().numpy() for t in ch.run_device(x)]
+    ndiff, unexplained = parity.classify_bins(bins, bins_o, q64, q32)
+    assert unexplained == []
+    assert np.abs(np.sort(loc, 1) - np.sort(truth, 1)).max() < 0.1
+    flm = doa.find_local_max(K, P, 0.0, 180.0, max_frames=B)
+    v2, l2, b2 = flm.work(spec_o, return_bins=True)
+    assert np.array_equal(v2, val_o) and np.array_equal(b2, bins_o) and np.array_equal(l2, loc_o)
+
+
 # ---- find_local_max: bit-exact on anything ---------------------------------------------------------------------------------
 def unambiguous(vecs, K):
     """Rows whose K highest local peaks are well defined.  The reference orders equal peak heights with an unstable
