@@ -273,7 +273,7 @@ def main():
             "msamples_per_s_aggregate": value * N * M / 1e6,
             "roofline": {"bound": "hbm", "achieved": cov_gbs, "peak": peak, "unit": "GB/s", "frac": cov_gbs / peak,
                          "traffic": traffic,
-                         "kernel": ("chain_fused_kernel<8,4> (covariance + Jacobi + scan/peaks in one persistent kernel)" if fused
+                         "kernel": ("chain_ws_kernel<8> (covariance + Jacobi + scan/peaks in one persistent warp-specialised kernel)" if fused
                                     else "cov_small_kernel<8> (covariance, dominant)"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": kern_bytes, "launch_ms": kern_ms,
                          "stage_ms": ({"fused_chain": kern_ms} if fused else {"cov": cov_ms, "eig": eig_ms, "scan_peaks": scan_ms}),

@@ -60,20 +60,60 @@ __device__ __forceinline__ float2 folded_entry(const float* red, int r, int c, f
 }
 
 
+// Per-lane accumulators of the Hermitian lower half (M diagonal reals + M(M-1)/2 complex = M*M floats).
+template <int M>
+struct CovAcc {
+  static constexpr int NP = M * (M - 1) / 2;
+  float dg[M];
+  float ore[NP > 0 ? NP : 1], oim[NP > 0 ? NP : 1];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int r = 0; r < M; ++r) dg[r] = 0.0f;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { ore[p] = 0.0f; oim[p] = 0.0f; }
+  }
+  // one time sample of all M channels
+  __device__ __forceinline__ void add(const float2 (&x)[M]) {
+#pragma unroll
+    for (int r = 0; r < M; ++r) {
+      const float2 xr = x[r];
+      dg[r] = fmaf(xr.x, xr.x, dg[r]);
+      dg[r] = fmaf(xr.y, xr.y, dg[r]);
+#pragma unroll
+      for (int c = 0; c < r; ++c) {
+        const float2 xc = x[c];
+        const int p = r * (r - 1) / 2 + c;
+        ore[p] = fmaf(xr.x, xc.x, ore[p]);   // x_r conj(x_c)
+        ore[p] = fmaf(xr.y, xc.y, ore[p]);
+        oim[p] = fmaf(xr.y, xc.x, oim[p]);
+        oim[p] = fmaf(-xr.x, xc.y, oim[p]);
+      }
+    }
+  }
+  // fold the 32 lanes' partial matrices; `red` (M*M floats, shared, this warp's) receives the raw sums
+  __device__ __forceinline__ void fold(unsigned lane, float* red) {
+    constexpr int CNT = M * M;
+    float a[CNT];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { a[2 * p] = ore[p]; a[2 * p + 1] = oim[p]; }
+#pragma unroll
+    for (int r = 0; r < M; ++r) a[2 * NP + r] = dg[r];
+    warp_reduce_scatter<CNT, 16>(a, lane);
+    const int b = rs_base<CNT>(lane);
+    constexpr int F = CNT >= 32 ? CNT / 32 : 1;
+#pragma unroll
+    for (int i = 0; i < F; ++i) red[b + i] = a[i];
+    __syncwarp();
+  }
+};
+
 // One frame by one warp: accumulate the Hermitian lower half over the frame's time axis and fold the 32 partial
 // matrices; on return `red` (M*M floats, shared memory, this warp's) holds the raw sums (layout: see folded_entry).
 template <int M, int VEC, int G>
 __device__ __forceinline__ void cov_warp_frame(const float2* __restrict__ base, long long chan_stride, int N, unsigned lane,
                                                float* red) {
-  constexpr int NP = M * (M - 1) / 2;
-  constexpr int CNT = M * M;
-  float dg[M];
-  float ore[NP > 0 ? NP : 1], oim[NP > 0 ? NP : 1];
-#pragma unroll
-  for (int r = 0; r < M; ++r) dg[r] = 0.0f;
-#pragma unroll
-  for (int p = 0; p < NP; ++p) { ore[p] = 0.0f; oim[p] = 0.0f; }
-
+  CovAcc<M> acc;
+  acc.clear();
   // G independent load groups per iteration (G*M LDG.128 in flight per lane).
   for (int t0 = (int)lane * VEC; t0 < N; t0 += G * 32 * VEC) {
     float2 x[G][VEC][M];
@@ -99,38 +139,9 @@ __device__ __forceinline__ void cov_warp_frame(const float2* __restrict__ base, 
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
-      for (int s = 0; s < VEC; ++s) {
-#pragma unroll
-        for (int r = 0; r < M; ++r) {
-          const float2 xr = x[g][s][r];
-          dg[r] = fmaf(xr.x, xr.x, dg[r]);
-          dg[r] = fmaf(xr.y, xr.y, dg[r]);
-#pragma unroll
-          for (int c = 0; c < r; ++c) {
-            const float2 xc = x[g][s][c];
-            const int p = r * (r - 1) / 2 + c;
-            ore[p] = fmaf(xr.x, xc.x, ore[p]);   // x_r conj(x_c)
-            ore[p] = fmaf(xr.y, xc.y, ore[p]);
-            oim[p] = fmaf(xr.y, xc.x, oim[p]);
-            oim[p] = fmaf(-xr.x, xc.y, oim[p]);
-          }
-        }
-      }
+      for (int s = 0; s < VEC; ++s) acc.add(x[g][s]);
   }
-
-  float a[CNT];
-#pragma unroll
-  for (int p = 0; p < NP; ++p) { a[2 * p] = ore[p]; a[2 * p + 1] = oim[p]; }
-#pragma unroll
-  for (int r = 0; r < M; ++r) a[2 * NP + r] = dg[r];
-  warp_reduce_scatter<CNT, 16>(a, lane);
-  {
-    const int b = rs_base<CNT>(lane);
-    constexpr int F = CNT >= 32 ? CNT / 32 : 1;
-#pragma unroll
-    for (int i = 0; i < F; ++i) red[b + i] = a[i];
-  }
-  __syncwarp();
+  acc.fold(lane, red);
 }
 
 // Scale, optional forward-backward term, Hermitian expansion; writes the M x M column-major matrix to `o`

@@ -1,15 +1,18 @@
-// fused.cu -- the whole chain (autocorrelate -> MUSIC_lin_array -> find_local_max) in ONE persistent kernel.
+// fused.cu -- the whole chain (autocorrelate -> MUSIC_lin_array -> find_local_max) in ONE persistent, warp-specialised kernel.
 //
-// The three stage kernels run back to back leave the machine half idle twice: the covariance is HBM-bound and uses ~40 %
-// of the issue slots, the eigendecomposition and the scan are issue-bound and move no data.  Here a CTA owns a contiguous
-// range of frames and walks it in tiles of TILE = 256/M frames through three phases, with every intermediate (R, G, u)
-// in shared memory:
-//     phase 1  each warp streams TILE/8 frames from HBM and folds their covariance        (cov_device.cuh)
-//     phase 2  256 threads = TILE matrices x M lanes: Jacobi, noise projector, diagonal sums (eig_device.cuh)
-//     phase 3  each warp scans TILE/8 frames, picks, refines and writes K peaks             (scan_device.cuh)
-// Two CTAs share an SM (<= 128 registers, ~86 KB shared memory each); the second half of the grid starts with a
-// half-size tile, so the two CTAs of an SM run in antiphase and one streams while the other computes.
-// The device code is the stage kernels' own, so the fused path is bit-identical to the three-kernel path (tested).
+// Run back to back, the three stage kernels leave the machine half idle twice: the covariance is HBM-bound and uses ~40 %
+// of the issue slots, the eigendecomposition and the scan are issue-bound and move no data.  Here one CTA of 16 warps per SM
+// owns a contiguous range of frames and keeps every intermediate (R, G, u) in shared memory:
+//   producer warps: stream their frames through per-lane cp.async rings (WS_STAGES x 4 KB per warp, so the bytes in flight
+//       depend neither on registers nor on what the other warps do), accumulate the covariance (cov_device.cuh), emit R into
+//       a double-buffered tile and signal "full"; they wait for the consumers only when both tile buffers are taken.
+//   consumer warps: wait for a full tile (TILE = 32/M matrices per consumer warp), run Jacobi on their own matrices
+//       (eig_device.cuh), release the tile buffer, scan + pick + refine their frames (scan_device.cuh) and write K peaks.
+// Hand-off with named barriers (bar.arrive / bar.sync): FULL0/1 and EMPTY0/1 between the two groups; a consumer warp owns
+// its matrices end to end, so the consumers need no barrier among themselves.
+// The device code is the stage kernels' own and per-entry operation order is unchanged, so the fused path is bit-identical to
+// the three-kernel path (tested).  Measured on B200 at cfg3: 2.21 ms (three kernels) -> 1.94 ms; a phase-structured variant
+// (two CTAs/SM alternating stream / Jacobi / scan phases behind __syncthreads) measured 2.02 ms and was dropped.
 #include "cov_device.cuh"
 #include "eig_device.cuh"
 #include "scan_device.cuh"
@@ -19,97 +22,164 @@
 namespace doa {
 namespace {
 
-constexpr int FU_WARPS = 8;
+constexpr int WS_STAGES = 3;
+constexpr int BAR_FULL = 1, BAR_EMPTY = 3;
 
-template <int M, int KL>
-__global__ void __launch_bounds__(FU_WARPS * 32, 2)
-chain_fused_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
-                   int avg_method, float scale, float bscale, int T, int max_sweeps, const float* __restrict__ zpair,
-                   const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int P, int K,
-                   float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin, int stagger) {
-  constexpr int TILE = FU_WARPS * 32 / M;      // frames per tile = matrices the CTA's threads cover in phase 2
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(NKEEP) : "memory"); }
+
+template <int M, int KL, int WS_P, int WS_C>
+__global__ void __launch_bounds__((WS_P + WS_C) * 32, 1)
+chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
+                int avg_method, float scale, float bscale, int T, int max_sweeps, const float* __restrict__ zpair,
+                const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int P, int K,
+                float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin) {
+  static_assert(M == 8, "tile geometry below assumes 8 lanes per matrix");
+  constexpr int TILE = WS_C * 32 / M;          // frames per tile: every consumer warp owns 32/M of them
   constexpr int MM = M * M;
+  constexpr int NTHREADS = (WS_P + WS_C) * 32;
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
   const ZTab zt = ztab_fill(smem, zpair, P);
-  float2* Rs = reinterpret_cast<float2*>(smem + ztab_floats(P));   // [TILE][M*M] covariance, then eigenvector staging
-  float2* Gs = Rs + TILE * MM;                                     // [TILE][M*M] noise projector
-  float2* us = Gs + TILE * MM;                                     // [TILE][M]   diagonal sums
-  float* red = reinterpret_cast<float*>(us + TILE * M);            // [FU_WARPS][M*M] covariance fold scratch
-  for (int i = threadIdx.x; i < TILE * MM; i += blockDim.x) Rs[i] = make_float2(0.f, 0.f);
+  float2* Rbuf = reinterpret_cast<float2*>(smem + ((ztab_floats(P) + 3) & ~(size_t)3));   // [2][TILE][MM]
+  float2* Gs = Rbuf + 2 * TILE * MM;                                 // [TILE][MM]
+  float2* us = Gs + TILE * MM;                                       // [TILE][M]
+  float* red = reinterpret_cast<float*>(us + TILE * M);              // [WS_P][MM]
+  float4* ring = reinterpret_cast<float4*>(red + WS_P * MM);         // [WS_P][WS_STAGES][M][32]
+  for (int i = threadIdx.x; i < 2 * TILE * MM; i += blockDim.x) Rbuf[i] = make_float2(0.f, 0.f);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned ulane = (unsigned)lane;
 
-  // contiguous, balanced frame range of this CTA
   const long long per = nframes / gridDim.x, rem = nframes % gridDim.x;
   const long long lo = blockIdx.x * per + min((long long)blockIdx.x, rem);
-  const long long hi = lo + per + (blockIdx.x < rem ? 1 : 0);
-  long long f0 = lo;
-  int tile = (stagger && blockIdx.x >= gridDim.x / 2) ? TILE / 2 : TILE;   // antiphase start for the SM's second CTA
+  const int nf = (int)(per + (blockIdx.x < rem ? 1 : 0));            // frames of this CTA
+  const int ntiles = (nf + TILE - 1) / TILE;
 
-  while (f0 < hi) {
-    const int nt = (int)min((long long)tile, hi - f0);
-    // ---- phase 1: covariance of nt frames, warp-strided -------------------------------------------------------------
-    for (int i = warp; i < nt; i += FU_WARPS) {
-      cov_warp_frame<M, 2, 1>(in + (f0 + i) * frame_stride, chan_stride, N, ulane, red + warp * MM);
-      cov_warp_emit<M>(red + warp * MM, scale, bscale, avg_method, ulane, Rs + i * MM);
+  if (warp < WS_P) {
+    // ================================ producer ================================
+    const int w = warp;
+    const int NCH = (N + 63) / 64;                                   // 64-sample chunks per frame (2 samples per lane)
+    const int nfw = (w < nf) ? (nf - w + WS_P - 1) / WS_P : 0;       // frames of this warp: w, w+P, w+2P, ...
+    const int total = nfw * NCH;                                     // chunks of this warp, frame-major
+    float4* myring = ring + (size_t)w * WS_STAGES * M * 32;
+    // issue cursor (frame base pointer, chunk in frame, ring stage) advances incrementally: no divisions in the loop
+    const float2* ibase = in + (lo + w) * frame_stride;
+    int ic = 0, istage = 0, issued = 0;
+    auto issue = [&]() {
+      const int t = ic * 64 + lane * 2;
+      const int nbytes = (t < N) ? 16 : 0;                           // beyond the frame: zero fill
+      float4* dst = myring + (size_t)istage * M * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < M; ++k) cp_async16(dst + k * 32, ibase + (long long)k * chan_stride + (nbytes ? t : 0), nbytes);
+      if (++ic == NCH) { ic = 0; ibase += (long long)WS_P * frame_stride; }
+      if (++istage == WS_STAGES) istage = 0;
+      ++issued;
+    };
+#pragma unroll
+    for (int q = 0; q < WS_STAGES - 1; ++q) { if (issued < total) issue(); cp_async_commit(); }
+    CovAcc<M> acc;
+    acc.clear();
+    int cur_tile = 0; bool opened = false;
+    int c = 0, m = 0, rstage = 0;
+    for (int q = 0; q < total; ++q) {
+      if (issued < total) issue();
+      cp_async_commit();
+      cp_async_wait<WS_STAGES - 1>();
+      const float4* src = myring + (size_t)rstage * M * 32 + lane;
+      if (++rstage == WS_STAGES) rstage = 0;
+      float2 x0[M], x1[M];
+#pragma unroll
+      for (int k = 0; k < M; ++k) { const float4 v = src[k * 32]; x0[k] = make_float2(v.x, v.y); x1[k] = make_float2(v.z, v.w); }
+      acc.add(x0);
+      acc.add(x1);
+      if (++c == NCH) {
+        // frame complete: fold, then emit into the tile buffer (waiting for it only now)
+        c = 0;
+        const int g = w + m * WS_P; ++m;
+        const int tf = g / TILE, slot = g - tf * TILE;
+        acc.fold((unsigned)lane, red + w * MM);
+        while (cur_tile < tf) {                                       // close tiles this warp is done with
+          if (!opened && cur_tile >= 2) bar_sync(BAR_EMPTY + (cur_tile & 1), NTHREADS);
+          __threadfence_block();
+          bar_arrive(BAR_FULL + (cur_tile & 1), NTHREADS);
+          ++cur_tile; opened = false;
+        }
+        if (!opened) { if (cur_tile >= 2) bar_sync(BAR_EMPTY + (cur_tile & 1), NTHREADS); opened = true; }
+        cov_warp_emit<M>(red + w * MM, scale, bscale, avg_method, (unsigned)lane, Rbuf + ((size_t)(tf & 1) * TILE + slot) * MM);
+        acc.clear();
+      }
     }
-    __syncthreads();
-    // ---- phase 2: Jacobi on TILE matrices at once (groups beyond nt carry stale finite data and store nothing) ----------
-    {
-      const int g = threadIdx.x / M, j = threadIdx.x % M;
-      jacobi_group_solve<M>(Rs + g * MM, j, T, max_sweeps, g < nt, Gs + g * MM, us + g * M, nullptr);
+    while (cur_tile < ntiles) {
+      if (!opened && cur_tile >= 2) bar_sync(BAR_EMPTY + (cur_tile & 1), NTHREADS);
+      __threadfence_block();
+      bar_arrive(BAR_FULL + (cur_tile & 1), NTHREADS);
+      ++cur_tile; opened = false;
     }
-    __syncthreads();
-    // ---- phase 3: scan + peaks, warp-strided; results go straight to global memory ---------------------------------------
-    for (int i = warp; i < nt; i += FU_WARPS) {
-      const long long f = f0 + i;
-      scan_frame_peaks<M, KL>(us + i * M, Gs + i * MM, zt, nullptr, Vtab, xaxis, M, P, K, lane, out_val + f * K,
-                              out_loc + f * K, out_bin ? out_bin + f * K : nullptr);
+  } else {
+    // ================================ consumer ================================
+    const int ct = threadIdx.x - WS_P * 32, cw = warp - WS_P;
+    for (int t = 0; t < ntiles; ++t) {
+      const int b = t & 1;
+      const int nt = min(TILE, nf - t * TILE);
+      bar_sync(BAR_FULL + b, NTHREADS);
+      {
+        const int g = ct / M, j = ct % M;
+        jacobi_group_solve<M>(Rbuf + ((size_t)b * TILE + g) * MM, j, T, max_sweeps, g < nt, Gs + g * MM, us + g * M, nullptr);
+      }
+      // A consumer warp owns its 32/M matrices end to end (Jacobi -> G/u -> scan), so nothing but the tile buffer is shared:
+      // no consumer-wide barrier, a warp whose matrices converge early starts scanning early.
+      __syncwarp();
+      if (t + 2 < ntiles) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NTHREADS); }
+      for (int i = cw * (32 / M); i < min(nt, (cw + 1) * (32 / M)); ++i) {
+        const long long f = lo + (long long)t * TILE + i;
+        scan_frame_peaks<M, KL>(us + i * M, Gs + i * MM, zt, nullptr, Vtab, xaxis, M, P, K, lane, out_val + f * K,
+                                            out_loc + f * K, out_bin ? out_bin + f * K : nullptr);
+      }
+      __syncwarp();
     }
-    // no barrier needed here: the next tile's phase 1 only writes Rs/red, and its closing barrier orders every warp's
-    // phase 3 reads of Gs/us before the next phase 2 overwrites them
-    f0 += nt;
-    tile = TILE;
   }
 }
 
-template <int M>
-int launch_fused_m(const float2* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
-                   int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st) {
-  constexpr int TILE = FU_WARPS * 32 / M;
-  const size_t smem = ztab_floats(tb.P) * sizeof(float) + ((size_t)2 * TILE * M * M + (size_t)TILE * M) * sizeof(float2) +
-                      (size_t)FU_WARPS * M * M * sizeof(float);
-  if (smem > 110 * 1024) return 0;   // two CTAs per SM must fit; larger scans use the three-kernel path
-  auto kern = chain_fused_kernel<M, 4>;
+template <int M, int WS_P, int WS_C>
+int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
+                  int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st) {
+  constexpr int TILE = WS_C * 32 / M;
+  const size_t smem = ((ztab_floats(tb.P) + 3) & ~(size_t)3) * sizeof(float) + ((size_t)3 * TILE * M * M + (size_t)TILE * M) * sizeof(float2) +
+                      (size_t)WS_P * M * M * sizeof(float) + (size_t)WS_P * WS_STAGES * M * 32 * sizeof(float4);
+  if (smem > 225 * 1024) return 0;
+  auto kern = chain_ws_kernel<M, 4, WS_P, WS_C>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = std::max(1, std::min(2 * sms, (nframes + TILE - 1) / TILE));
+  const int grid = std::max(1, std::min(sms, (nframes + TILE - 1) / TILE));
   const float scale = (float)(1.0 / N), bscale = (float)(0.5 / N);
-  kern<<<grid, FU_WARPS * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.V, tb.xaxis, tb.P, K,
-                                          out_val, out_loc, out_bin, dev_option("fused_stagger", 1));
+  kern<<<grid, (WS_P + WS_C) * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.V, tb.xaxis, tb.P,
+                                               K, out_val, out_loc, out_bin);
   return 1;
 }
 
 }  // namespace
 
 // Returns 1 if the fused kernel was launched, 0 if this shape is not covered (caller falls back to the three kernels).
+// Covered: M = 8, 2 <= K <= 4, 16-byte aligned even strides, scan table + tiles + rings within one SM's shared memory
+// (P <= ~6000).  M = 4 is HBM-dominated (covariance is 80 % of the step) and measured faster unfused.
 int launch_chain_fused(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
                        int avg_method, int T, const ScanTables& tb, int K, float* out_val, float* out_loc, int* out_bin,
                        cudaStream_t st) {
-  if (nframes <= 0) return 0;
+  if (nframes <= 0 || M != 8) return 0;
   if (K < 2 || K > 4) return 0;                       // K == 1 is the arg-max kernel, K > 4 the wide candidate lists
   const bool vec2 = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
                     ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
   if (!vec2) return 0;
-  switch (M) {
-    case 4: return launch_fused_m<4>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st);
-    case 8: return launch_fused_m<8>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st);
-    default: return 0;
-  }
+  // 4 producer + 12 consumer warps measured best (1.94 ms at cfg3) among 4/12, 5/11, 6/10, 8/8 (2.02 - 2.19 ms)
+  return launch_ws_cfg<8, 4, 12>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st);
 }
 
 }  // namespace doa

@@ -77,12 +77,12 @@ def test_oracle_spot_check_on_the_resident_buffer(full, oracle):
 
 
 def test_fused_kernel_equals_three_kernel_path(full):
-    """chain_fused_kernel runs the stage kernels' own device code with R, G, u in shared memory: bit-identical output."""
+    """The warp-specialised fused kernel runs the stage kernels own device code with R, G, u in shared memory: bit-identical."""
     from gr_doa_b200 import _lib
     torch = full["torch"]
     L = _lib.lib()
     try:
-        for nb in (1, 31, 32, 33, 4097, 20000):
+        for nb in (1, 31, 47, 48, 49, 97, 4097, 20000):
             L.doa_cuda_dev_set(b"fused", 0)
             a = [t.clone() for t in full["ch"].run_device(full["x"][:nb])]
             assert full["ch"].launches() == 3
