@@ -46,18 +46,21 @@ jacobi_group_kernel(const float2* __restrict__ R, int T, int nframes, float2* __
 }
 
 // ---- generic M: one CTA per matrix ----------------------------------------------------------------------------
+// A and V live in shared memory with an odd leading dimension (M+1 float2) so that both the column phase (threads walk a
+// column) and the row phase (threads walk a row, stride LD) are bank-conflict free.
 constexpr int JB_THREADS = 256;
 
 __global__ void __launch_bounds__(JB_THREADS)
 jacobi_block_kernel(const float2* __restrict__ R, int M, int T, int nframes, float2* __restrict__ G,
                     float2* __restrict__ u, float* __restrict__ w, int max_sweeps) {
   extern __shared__ float2 sm[];
-  float2* A = sm;                    // [M][M] column-major: A[i + j*M]
-  float2* V = A + M * M;             // [M][M]
-  float* rc = reinterpret_cast<float*>(V + M * M);   // rotation params: c[Mp/2], sx[Mp/2], sy[Mp/2]
-  int* pp = reinterpret_cast<int*>(rc + 3 * 32);     // p[Mp/2], q[Mp/2]
-  float* lam = reinterpret_cast<float*>(pp + 2 * 32);   // [M]
-  int* rk = reinterpret_cast<int*>(lam + 64);           // [M]
+  const int LD = M | 1;              // odd leading dimension
+  float2* A = sm;                    // element (i, j) at A[i + j*LD]
+  float2* V = A + (size_t)M * LD;
+  float* rc = reinterpret_cast<float*>(V + (size_t)M * LD);   // rotation params: c[32], sx[32], sy[32]
+  int* pp = reinterpret_cast<int*>(rc + 3 * 32);              // p[32], q[32]
+  float* lam = reinterpret_cast<float*>(pp + 2 * 32);         // [64]
+  int* rk = reinterpret_cast<int*>(lam + 64);                 // [64]
   __shared__ float red[2];
   const int tid = threadIdx.x;
   const int Mp = (M + 1) & ~1, HP = Mp / 2;
@@ -67,11 +70,11 @@ jacobi_block_kernel(const float2* __restrict__ R, int M, int T, int nframes, flo
     for (int e = tid; e < M * M; e += JB_THREADS) {
       const int i = e % M, j = e / M;
       float2 x;
-      if (i < j) x = src[i + j * M];
+      if (i < j) x = src[i + j * M];                      // upper triangle only, like cheevd 'U'
       else if (i == j) x = make_float2(src[e].x, 0.f);
       else { const float2 t = src[j + i * M]; x = make_float2(t.x, -t.y); }
-      A[e] = x;
-      V[e] = make_float2(i == j ? 1.f : 0.f, 0.f);
+      A[i + j * LD] = x;
+      V[i + j * LD] = make_float2(i == j ? 1.f : 0.f, 0.f);
     }
     __syncthreads();
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
@@ -79,8 +82,10 @@ jacobi_block_kernel(const float2* __restrict__ R, int M, int T, int nframes, flo
       __syncthreads();
       float off = 0.f, dg = 0.f;
       for (int e = tid; e < M * M; e += JB_THREADS) {
-        const float m2 = A[e].x * A[e].x + A[e].y * A[e].y;
-        if (e % M == e / M) dg += m2; else off += m2;
+        const int i = e % M, j = e / M;
+        const float2 a = A[i + j * LD];
+        const float m2 = a.x * a.x + a.y * a.y;
+        if (i == j) dg += m2; else off += m2;
       }
       for (int o = 16; o >= 1; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dg += __shfl_xor_sync(0xffffffffu, dg, o); }
       if ((tid & 31) == 0) { atomicAdd(&red[0], off); atomicAdd(&red[1], dg); }
@@ -94,42 +99,48 @@ jacobi_block_kernel(const float2* __restrict__ R, int M, int T, int nframes, flo
           int b_ = (tid == 0) ? (Mp - 1) : (s - tid + (Mp - 1)) % (Mp - 1);
           int p = min(a_, b_), q = max(a_, b_);
           Rot r; r.c = 1.f; r.sx = 0.f; r.sy = 0.f;
-          if (q < M) r = make_rotation(A[p + p * M].x, A[q + q * M].x, A[p + q * M]);
+          if (q < M) r = make_rotation(A[p + p * LD].x, A[q + q * LD].x, A[p + q * LD]);
           else { p = -1; }   // pair with the padding index: skip
           rc[tid] = r.c; rc[32 + tid] = r.sx; rc[64 + tid] = r.sy; pp[tid] = p; pp[32 + tid] = q;
         }
         __syncthreads();
-        for (int it = tid; it < HP * M; it += JB_THREADS) {   // columns of A and V
+        for (int it = tid; it < HP * M; it += JB_THREADS) {   // columns of A and V: A <- A J, V <- V J
           const int k = it / M, i = it % M;
           const int p = pp[k], q = pp[32 + k];
           if (p < 0) continue;
           const float c = rc[k], sx = rc[32 + k], sy = rc[64 + k];
           {
-            const float2 x = A[i + p * M], y = A[i + q * M];
-            A[i + p * M] = make_float2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
-            A[i + q * M] = make_float2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
+            const float2 x = A[i + p * LD], y = A[i + q * LD];
+            A[i + p * LD] = make_float2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
+            A[i + q * LD] = make_float2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
           }
           {
-            const float2 x = V[i + p * M], y = V[i + q * M];
-            V[i + p * M] = make_float2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
-            V[i + q * M] = make_float2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
+            const float2 x = V[i + p * LD], y = V[i + q * LD];
+            V[i + p * LD] = make_float2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
+            V[i + q * LD] = make_float2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
           }
         }
         __syncthreads();
-        for (int it = tid; it < HP * M; it += JB_THREADS) {   // rows of A
+        for (int it = tid; it < HP * M; it += JB_THREADS) {   // rows of A: A <- J^H A
           const int k = it / M, i = it % M;
           const int p = pp[k], q = pp[32 + k];
           if (p < 0) continue;
           const float c = rc[k], sx = rc[32 + k], sy = rc[64 + k];
-          const float2 x = A[p + i * M], y = A[q + i * M];
-          A[p + i * M] = make_float2(c * x.x - (sx * y.x - sy * y.y), c * x.y - (sx * y.y + sy * y.x));
-          A[q + i * M] = make_float2(sx * x.x + sy * x.y + c * y.x, sx * x.y - sy * x.x + c * y.y);
+          const float2 x = A[p + i * LD], y = A[q + i * LD];
+          A[p + i * LD] = make_float2(c * x.x - (sx * y.x - sy * y.y), c * x.y - (sx * y.y + sy * y.x));
+          A[q + i * LD] = make_float2(sx * x.x + sy * x.y + c * y.x, sx * x.y - sy * x.x + c * y.y);
         }
         __syncthreads();
       }
     }
-    // ranks
-    for (int j = tid; j < M; j += JB_THREADS) lam[j] = A[j + j * M].x;
+    // unit eigenvectors (the MUFU rotations let column norms drift by O(1e-7) per rotation), eigenvalues, ranks
+    for (int j = tid; j < M; j += JB_THREADS) {
+      float n2 = 0.f;
+      for (int i = 0; i < M; ++i) { const float2 v = V[i + j * LD]; n2 = fmaf(v.x, v.x, fmaf(v.y, v.y, n2)); }
+      const float sc = 1.0f / sqrtf(n2);
+      for (int i = 0; i < M; ++i) { V[i + j * LD].x *= sc; V[i + j * LD].y *= sc; }
+      lam[j] = A[j + j * LD].x;
+    }
     __syncthreads();
     for (int j = tid; j < M; j += JB_THREADS) {
       int r = 0;
@@ -144,18 +155,18 @@ jacobi_block_kernel(const float2* __restrict__ R, int M, int T, int nframes, flo
       const int i = e % M, j = e / M;
       float gx = 0.f, gy = 0.f;
       for (int n = 0; n < nn; ++n) {
-        const float2 ei = V[i + rk[n] * M], ej = V[j + rk[n] * M];
+        const float2 ei = V[i + rk[n] * LD], ej = V[j + rk[n] * LD];
         gx = fmaf(ei.x, ej.x, gx); gx = fmaf(ei.y, ej.y, gx);
         gy = fmaf(ei.y, ej.x, gy); gy = fmaf(-ei.x, ej.y, gy);
       }
-      A[e] = make_float2(gx, gy);
+      A[i + j * LD] = make_float2(gx, gy);
       if (G) G[(long long)f * M * M + e] = make_float2(gx, gy);
     }
     __syncthreads();
     if (u) {
       for (int l = tid; l < M; l += JB_THREADS) {
         float sx = 0.f, sy = 0.f;
-        for (int r = 0; r + l < M; ++r) { sx += A[r + (r + l) * M].x; sy += A[r + (r + l) * M].y; }
+        for (int r = 0; r + l < M; ++r) { sx += A[r + (r + l) * LD].x; sy += A[r + (r + l) * LD].y; }
         u[(long long)f * M + l] = make_float2(sx, l == 0 ? 0.f : sy);
       }
     }
@@ -183,7 +194,7 @@ int launch_noise_subspace(const float2* R, int M, int T, int nframes, float2* G,
     default: break;
   }
   if (M > 64 || M < 2) return DOA_CUDA_EINVAL;
-  const size_t smem = (size_t)2 * M * M * sizeof(float2) + (3 * 32) * sizeof(float) + (2 * 32) * sizeof(int) +
+  const size_t smem = (size_t)2 * M * (M | 1) * sizeof(float2) + (3 * 32) * sizeof(float) + (2 * 32) * sizeof(int) +
                       64 * sizeof(float) + 64 * sizeof(int);
   cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   int dev = 0, sms = 148;
