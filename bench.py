@@ -160,14 +160,14 @@ def main():
     x, _ = synth.frames_torch(B, M, N, w["thetas"], d=w["d"], snr_db=w["snr_db"], jitter_deg=w["jitter"],
                               seed=synth.SEED_BASE + 3 + 1000 * rank, device=dev)
     chain = doa.DoaChain(M, N, 0, 0, w["d"], T, P, K, device=local, max_frames=B)
-    out = (torch.empty((B, K), dtype=torch.float32, device=dev), torch.empty((B, K), dtype=torch.float32, device=dev),
-           torch.empty((B, K), dtype=torch.int32, device=dev))
+    peaks = sharding.PeakBuffers(B, K, dev, world=world, is_dst=(rank == 0))
+    out = peaks.outputs()
     total = B * world
 
     def step():
         chain.run_device(x, out=out)
         if world > 1:
-            return sharding.gather_peaks(out[0], out[1], out[2], total, dst=0)
+            return peaks.gather(dst=0)      # the one collective of the path: packed peaks of every shard to rank 0
         return out
 
     def fence():

@@ -63,6 +63,38 @@ def gather_peaks(val, loc, bins, nframes_total: int, dst: int = 0, group=None):
     return None
 
 
+class PeakBuffers:
+    """Peaks of one shard in ONE packed int32 buffer [3][n][K] (values | locations | bins; float32 words bit-cast), so that
+    the per-step exchange is a single collective on a preallocated buffer with no packing kernels around it:
+    `val`, `loc`, `bins` are views the chain writes into; on the destination rank `gathered` is [world][3][n][K]."""
+
+    def __init__(self, n: int, K: int, device, world: int = 1, is_dst: bool = False):
+        self.n, self.K, self.world = n, K, world
+        self.buf = torch.empty((3, n, K), dtype=torch.int32, device=device)
+        self.val = self.buf[0].view(torch.float32)
+        self.loc = self.buf[1].view(torch.float32)
+        self.bins = self.buf[2]
+        self.gathered = torch.empty((world, 3, n, K), dtype=torch.int32, device=device) if (is_dst and world > 1) else None
+        self._views = [self.gathered[r] for r in range(world)] if self.gathered is not None else None
+
+    def outputs(self):
+        return self.val, self.loc, self.bins
+
+    def gather(self, dst: int = 0, group=None):
+        """Equal-size shards only (bench / streaming slabs); returns the [world][3][n][K] buffer on dst, None elsewhere."""
+        if self.world == 1:
+            return self.buf[None]
+        dist.gather(self.buf, self._views, dst=dst, group=group)
+        return self.gathered
+
+    @staticmethod
+    def split(gathered):
+        """[world][3][n][K] int32 -> (val, loc, bins) as [world*n][K] in frame order (rank-major)."""
+        w, _, n, K = gathered.shape
+        return (gathered[:, 0].reshape(w * n, K).view(torch.float32), gathered[:, 1].reshape(w * n, K).view(torch.float32),
+                gathered[:, 2].reshape(w * n, K))
+
+
 def run_sharded(chain_fn, frames_local, nframes_total: int, dst: int = 0, group=None):
     """chain_fn(frames_local) -> (val, loc, bins) for this rank's frames; returns the gathered result on dst."""
     val, loc, bins = chain_fn(frames_local)

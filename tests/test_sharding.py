@@ -38,6 +38,43 @@ def test_pack_roundtrip_is_bit_exact():
     assert torch.equal(v, val) and torch.equal(l, loc) and torch.equal(b, bins)
 
 
+def _worker_packed(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, K = 6, 3
+    pb = sharding.PeakBuffers(n, K, "cpu", world=world, is_dst=(rank == 0))
+    g = torch.Generator().manual_seed(100 + rank)
+    pb.val.copy_(torch.randn((n, K), generator=g)); pb.loc.copy_(torch.randn((n, K), generator=g))
+    pb.bins.copy_(torch.randint(0, 4096, (n, K), generator=g, dtype=torch.int32))
+    got = pb.gather(dst=0)
+    if rank == 0:
+        val, loc, bins = sharding.PeakBuffers.split(got)
+        ok = True
+        for r in range(world):
+            g = torch.Generator().manual_seed(100 + r)
+            ok &= torch.equal(val[r * n:(r + 1) * n], torch.randn((n, K), generator=g))
+            ok &= torch.equal(loc[r * n:(r + 1) * n], torch.randn((n, K), generator=g))
+            ok &= torch.equal(bins[r * n:(r + 1) * n], torch.randint(0, 4096, (n, K), generator=g, dtype=torch.int32))
+        q.put(bool(ok))
+    else:
+        assert got is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_packed_peak_buffers_gather():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_packed, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
 def _worker(rank, world, port, nframes, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
