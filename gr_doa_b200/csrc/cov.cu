@@ -166,6 +166,10 @@ int launch_covariance(const float2* in, long long frame_stride, long long chan_s
     default: break;
   }
   if (M > 64) return DOA_CUDA_EINVAL;
+  if (M == 64 && dev_option("herk_tc", 1)) {   // tensor-core complex HERK (3xTF32) when alignment allows
+    const int r = launch_covariance_tc(in, frame_stride, chan_stride, M, N, nframes, avg_method, out, st);
+    if (r != 0) return r;
+  }
   const int Mp = ((M + 3) / 4) * 4;
   const size_t smem = (size_t)Mp * (CT_TT + 1) * sizeof(float2) + (size_t)Mp * Mp * 2 * sizeof(float);
   cudaFuncSetAttribute(cov_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

@@ -15,6 +15,10 @@ namespace doa {
 int launch_covariance(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
                       int avg_method, float2* out, cudaStream_t st);
 
+// Tensor-core path of stage 1 for M = 64 (herk_tc.cu): 1 if launched, 0 if the shape is not covered.
+int launch_covariance_tc(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
+                         int avg_method, float2* out, cudaStream_t st);
+
 // Stage 2a.  Hermitian EVD (batched Jacobi) of R (upper triangle read, like cheevd 'U') and the noise subspace:
 //   G[f][r + c*M] = sum_{n < M-T} e_n[r] conj(e_n[c])   (may be null)
 //   u[f][l]       = sum_r G[r][r+l], l = 0..M-1          (complex, u[0] real; may be null)

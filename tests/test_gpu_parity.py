@@ -231,6 +231,34 @@ def test_large_array_shape_cfg4(doa, oracle, torch_cuda):
     assert np.array_equal(v2, val_o) and np.array_equal(b2, bins_o) and np.array_equal(l2, loc_o)
 
 
+@pytest.mark.parametrize("N,overlap,avg,B", [(64, 0, 0, 5), (1000, 0, 1, 3), (2048, 512, 0, 9), (4096, 0, 1, 150), (16384, 0, 0, 3),
+                                             (34, 32, 1, 40), (1001, 0, 0, 3)])
+def test_large_array_covariance_tensor_core(doa, oracle, torch_cuda, N, overlap, avg, B):
+    """M = 64: the tcgen05 3xTF32 HERK (herk_tc.cu) and the CUDA-core tiled kernel both meet the covariance tolerance and
+    agree with one another; an odd snapshot size is outside the tensor-core kernel's 16-byte pieces and takes the CUDA-core
+    kernel on both settings (whose time slices meet in shared-memory atomics: reproducible to rounding, not bit for bit).  Long snapshots are the case that exposes a truncating accumulator (error grows with N)."""
+    from gr_doa_b200 import synth, _lib
+    L = _lib.lib()
+    x = synth.stream_numpy(B, 64, N, overlap, [40.0, 75.0, 120.0], seed=N + B)
+    exp = oracle.autocorrelate(x, N, overlap, avg, nthreads=oracle.max_threads())
+    ac = doa.autocorrelate(64, N, overlap, avg, max_frames=B)
+    got = {}
+    try:
+        for tc in (0, 1):
+            L.doa_cuda_dev_set(b"herk_tc", tc)
+            got[tc] = ac.work(x)
+    finally:
+        L.doa_cuda_dev_set(b"herk_tc", 1)
+    for tc in (0, 1):
+        assert got[tc].shape == exp.shape
+        assert parity.rel_fro(got[tc], exp) <= 2e-6 <= parity.COV_REL_FRO, (tc, parity.rel_fro(got[tc], exp))
+    assert parity.rel_fro(got[1], got[0]) <= 2e-6
+    # Hermitian to rounding (the two triangles come from different accumulator rows), exactly real-positive diagonal is not
+    # promised by either implementation; check the symmetry the consumers rely on
+    Rm = got[1].reshape(-1, 64, 64)
+    assert np.abs(Rm - np.conj(np.transpose(Rm, (0, 2, 1)))).max() <= 4e-6 * np.abs(Rm).max()
+
+
 # ---- find_local_max: bit-exact on anything ---------------------------------------------------------------------------------
 def unambiguous(vecs, K):
     """Rows whose K highest local peaks are well defined.  The reference orders equal peak heights with an unstable
