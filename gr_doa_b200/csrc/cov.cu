@@ -34,6 +34,137 @@ cov_small_kernel(const float2* __restrict__ in, long long frame_stride, long lon
   }
 }
 
+// ---- M = 16 ----------------------------------------------------------------------------------------------------
+// The Hermitian lower half of a 16 x 16 matrix is 256 floats: too many accumulators for one lane.  Two warps share a frame:
+// role A keeps the two diagonal 8 x 8 blocks (two CovAcc<8> = 128 accumulators), role B the off-diagonal block R[8..15][0..7]
+// (64 complex = 128 accumulators).  Both walk the frame's time axis the same way as the one-warp kernels (lanes split the
+// time axis, LDG.128 = two samples per channel), fold with the reduce-scatter butterfly and scatter their sums into the
+// frame's shared 256-float area in the layout folded_entry<16> reads; the pair then emits half of R each.
+constexpr int C16_FRAMES = 4;   // frames in flight per CTA (8 warps)
+
+__device__ const unsigned char kTri8Row[28] = {1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7};
+__device__ const unsigned char kTri8Col[28] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 6};
+
+template <int VEC>
+__device__ __forceinline__ void cov16_load(const float2* __restrict__ base, long long chan_stride, int t, bool ok,
+                                           float2 (&x)[VEC][16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float2* p = base + (long long)k * chan_stride + t;
+    if constexpr (VEC == 2) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) v = ldg_stream4(reinterpret_cast<const float4*>(p));
+      x[0][k] = make_float2(v.x, v.y);
+      x[1][k] = make_float2(v.z, v.w);
+    } else {
+      float2 v = make_float2(0.f, 0.f);
+      if (ok) v = ldg_stream2(p);
+      x[0][k] = v;
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(C16_FRAMES * 64, 1)
+cov16_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
+             float2* __restrict__ out, float scale, float bscale, int avg_method) {
+  constexpr int M = 16, CNT = 256, NP16 = 120;
+  __shared__ float red_s[C16_FRAMES][CNT];
+  const unsigned lane = threadIdx.x & 31u;
+  const int warp = threadIdx.x >> 5, slot = warp >> 1, role = warp & 1;
+  float* red = red_s[slot];
+  const int nslots = gridDim.x * C16_FRAMES;
+  // every warp of a pair runs the same number of iterations (the pair barrier needs both)
+  for (int f = blockIdx.x * C16_FRAMES + slot; f < nframes; f += nslots) {
+    const float2* base = in + (long long)f * frame_stride;
+    float a[128];
+    if (role == 0) {
+      CovAcc<8> d0, d1;
+      d0.clear(); d1.clear();
+      for (int t = (int)lane * VEC; t < N; t += 32 * VEC) {
+        float2 x[VEC][16];
+        cov16_load<VEC>(base, chan_stride, t, true, x);
+#pragma unroll
+        for (int s = 0; s < VEC; ++s) {
+          float2 lo8[8], hi8[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { lo8[k] = x[s][k]; hi8[k] = x[s][8 + k]; }
+          d0.add(lo8);
+          d1.add(hi8);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 28; ++p) { a[2 * p] = d0.ore[p]; a[2 * p + 1] = d0.oim[p]; a[64 + 2 * p] = d1.ore[p]; a[64 + 2 * p + 1] = d1.oim[p]; }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { a[56 + r] = d0.dg[r]; a[120 + r] = d1.dg[r]; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 128; ++i) a[i] = 0.0f;
+      for (int t = (int)lane * VEC; t < N; t += 32 * VEC) {
+        float2 x[VEC][16];
+        cov16_load<VEC>(base, chan_stride, t, true, x);
+#pragma unroll
+        for (int s = 0; s < VEC; ++s)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 xr = x[s][8 + i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 xc = x[s][j];
+              float& re = a[2 * (i * 8 + j)];
+              float& im = a[2 * (i * 8 + j) + 1];
+              re = fmaf(xr.x, xc.x, re);   // x_r conj(x_c)
+              re = fmaf(xr.y, xc.y, re);
+              im = fmaf(xr.y, xc.x, im);
+              im = fmaf(-xr.x, xc.y, im);
+            }
+          }
+      }
+    }
+    warp_reduce_scatter<128, 16>(a, lane);          // lane L now holds the full sums of elements 4L .. 4L+3
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = (int)lane * 4 + i;
+      int pos;
+      if (role == 0) {
+        const int blk = k >> 6, kk = k & 63;
+        if (kk < 56) {
+          const int r = 8 * blk + kTri8Row[kk >> 1], c = 8 * blk + kTri8Col[kk >> 1];
+          pos = 2 * (r * (r - 1) / 2 + c) + (kk & 1);
+        } else {
+          pos = 2 * NP16 + 8 * blk + (kk - 56);
+        }
+      } else {
+        const int r = 8 + (k >> 4), c = (k >> 1) & 7;
+        pos = 2 * (r * (r - 1) / 2 + c) + (k & 1);
+      }
+      red[pos] = a[i];
+    }
+    asm volatile("bar.sync %0, 64;" :: "r"(1 + slot) : "memory");   // both roles' sums are in red
+    float2* o = out + (long long)f * CNT;
+    for (int e = role * 32 + (int)lane; e < CNT; e += 64) {
+      const int r = e % M, c = e / M;
+      float2 v = folded_entry<M>(red, r, c, scale);
+      if (avg_method == 1) {   // 0.5*R + (0.5/N) * J conj(R) J, lib/autocorrelate_impl.cc:108
+        const float2 w = folded_entry<M>(red, M - 1 - r, M - 1 - c, scale);
+        v.x = __fadd_rn(__fmul_rn(0.5f, v.x), __fmul_rn(bscale, w.x));
+        v.y = __fadd_rn(__fmul_rn(0.5f, v.y), __fmul_rn(bscale, -w.y));
+      }
+      o[e] = v;
+    }
+    asm volatile("bar.sync %0, 64;" :: "r"(1 + slot) : "memory");   // red may be overwritten
+  }
+}
+
+int launch_cov16(const float2* in, long long fs, long long cs, int N, int nframes, float2* out, float scale, float bscale,
+                 int avg, cudaStream_t st) {
+  const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
+  const int blocks = (nframes + C16_FRAMES - 1) / C16_FRAMES;
+  if (vec2) cov16_kernel<2><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg);
+  else cov16_kernel<1><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg);
+  return 1;
+}
+
 // ---- generic M ---------------------------------------------------------------------------------------------
 constexpr int CT_THREADS = 512;
 constexpr int CT_TT = 64;   // time samples per shared-memory tile
@@ -163,6 +294,7 @@ int launch_covariance(const float2* in, long long frame_stride, long long chan_s
     case 2: return launch_small<2>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st);
     case 4: return launch_small<4>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st);
     case 8: return launch_small<8>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st);
+    case 16: return launch_cov16(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st);
     default: break;
   }
   if (M > 64) return DOA_CUDA_EINVAL;

@@ -6,27 +6,38 @@
 // Formulation.  Read channel m's interleaved samples (re0, im0, re1, im1, ...) as a REAL row Z_m of length 2N, and let W_m
 // be the same row with every (re, im) pair replaced by (im, -re).  Then
 //     Re R[r][c] = sum_t re_r re_c + im_r im_c = (Z Z^T)[r][c]        Im R[r][c] = sum_t im_r re_c - re_r im_c = (W Z^T)[r][c]
-// so ONE real product  D (128 x 64) = [Z; W] (128 x 2N) * Z^T  gives the whole covariance: a tcgen05 kind::tf32 UMMA with
-// M = 128, N = 64, K = 8, accumulator = 128 TMEM lanes x 64 columns, both operands K-major in 128-byte-swizzled shared
-// memory, the B operand aliasing rows 0..63 of A.  fp32 accuracy comes from the 3xTF32 split x = hi + lo
-// (hi = tf32(x), lo = tf32(x - hi)):  D += A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T  (the dropped lo*lo term is 2^-22 relative).
+// so ONE real product  D (128 x 64) = A (128 x 2N) * Z^T  with  A = [Z; W]  gives the whole covariance.  fp32 accuracy comes
+// from the 3xTF32 split x = hi + lo (hi = x rounded to tf32, lo = x - hi, which the tensor core truncates to tf32):
+//     D += A_hi Z_hi^T + A_hi Z_lo^T + A_lo Z_hi^T          (the dropped lo*lo term is 2^-22 relative)
+// issued per K-step of 8 as TWO tcgen05 kind::tf32 UMMAs: M = 128, N = 128 for A_hi [Z_hi; Z_lo]^T (hi*hi into accumulator
+// columns 0..63, hi*lo into 64..127; the Z_hi and Z_lo tiles are adjacent in shared memory, i.e. one 128-row K-major operand)
+// and M = 128, N = 64 for A_lo Z_hi^T into columns 64..127.  A is written straight into TMEM (tcgen05.st; lane = row,
+// column = k) and only the B operand Z lives in 128-byte-swizzled shared memory: with A in shared memory as well the
+// tensor core's operand reads plus the converters' stores saturate the 128 B/clk shared-memory port (measured: 48 clk per
+// M128 N64 K8 UMMA from shared memory, against 32 for the math).
 //
-// Accumulation.  The tensor core truncates the fp32 accumulator on every MMA (measured: relative error of the diagonal
-// grows as #MMAs * 2^-24: 3e-5 at N = 2048, 2e-4 at N = 16384 with a single accumulator).  So the big terms A_hi B_hi^T go
-// into a ping-pong pair of TMEM accumulators that is folded into fp32 REGISTERS (properly rounded adds) every TC_CHUNK
-// stages = 16 MMAs, and the two cross terms, 2^-11 smaller, into a third accumulator folded once per frame.
+// Accumulation.  The tensor core TRUNCATES the fp32 accumulator on every MMA (measured: the relative error of the diagonal
+// grows as #MMAs * 2^-24 -- 3e-5 at N = 2048, 7e-5 at N = 4096 with one accumulator per frame).  So the 128-column
+// accumulator is a ping-pong pair, and every TC_CHUNK stages (16 MMAs per column block) the finished one is folded into fp32
+// REGISTERS with properly rounded adds: rel. Frobenius error 4e-7 at every N (tests/test_gpu_parity.py).
 //
-// One persistent CTA per SM, 13 warps:
-//   warp 0, one lane : MMA issuer.  Per 128-byte stage: wait full[s]; 4 K-steps x (hi*hi -> D_big[b], hi*lo and lo*hi ->
-//                      D_small); tcgen05.commit -> empty[s]; every TC_CHUNK stages commit -> chunk_full[b] and switch b;
-//                      after a frame's last stage commit -> small_full.
-//   warps 1..8       : converters.  Thread t owns 4 complex samples of channel t/4 per stage: cp.async them into a private raw
-//                      ring (RAW_STAGES deep: HBM bytes in flight do not depend on registers), split hi/lo with integer
-//                      round-to-nearest on the tf32 boundary, store the four operand rows (Z_hi, Z_lo, W_hi, W_lo) with the
-//                      swizzle applied, fence.proxy.async, arrive on full[s].  They run ahead across frame boundaries.
+// One persistent CTA per SM, 13 warps; a "stage" is 16 complex samples = 32 K-values = 128 bytes per row:
+//   warp 0           : MMA issuer.  The whole warp runs the loop (warp-uniform operands, so ptxas emits bare UTCHMMA) and one
+//                      elected lane issues: wait full[s]; 4 K-steps x 2 MMAs; tcgen05.commit -> empty[s]; every TC_CHUNK
+//                      stages and at the end of a frame commit -> chunk_full[b] and switch accumulators.
+//   warps 1..8       : converters, two independent groups of 4 warps on alternate stages.  Loader role: cp.async 64 B of one
+//                      channel into the group's raw ring (HBM bytes in flight do not depend on registers).  Converter role:
+//                      a thread IS one row of A (TMEM lanes belong to warp % 4): read the row's 32 raw values, split hi/lo
+//                      (integer round-to-nearest on the tf32 boundary), (im, -re) for W rows, tcgen05.st into the A ring;
+//                      Z rows also store the swizzled B tiles; fences, arrive on full[s].  They run ahead across frames.
 //   warps 9..12      : adders + epilogue.  Thread = one TMEM lane (row of [Re R; Im R]), 64 fp32 register accumulators:
-//                      wait chunk_full[b], tcgen05.ld, add, arrive chunk_empty[b]; at the frame end add D_small, stage the
-//                      128 x 64 result in shared memory, combine Re/Im, scale, forward-backward term, store R.
+//                      wait chunk_full[b], tcgen05.ld both column blocks, add, arrive chunk_empty[b]; at the frame end stage
+//                      the 128 x 64 result in shared memory, combine Re/Im, scale, forward-backward term, store R.
+// TMEM (512 columns): accumulators @0 and @128, A ring @256 + 64 s (32 hi | 32 lo columns per stage, 4 stages).
+//
+// Measured (B200, 592 frames of 64 x 16384): 2.2 ms = 2.2 TB/s of input = 0.34 of HBM, against 5.30 ms for the CUDA-core
+// tiled kernel.  Both sides of the pipeline now cost 700-900 clk per stage of dependent latency (converter iteration; MMA
+// issue + commit), against a 384 clk tensor-pipe floor: the next step is software-pipelining the converter's fences.
 #include "doa_internal.h"
 
 #include <algorithm>
@@ -36,14 +47,15 @@ namespace {
 
 constexpr int TC_M = 64;                 // channels
 constexpr int TC_ROWS = 128;             // rows of [Z; W]
-constexpr int TC_OP_STAGES = 4;          // operand ring depth (32 KB per stage: hi + lo tiles of 128 x 128 B)
-constexpr int TC_RAW_STAGES = 6;         // raw fp32 ring depth (8 KB per stage)
+constexpr int TC_OP_STAGES = 4;          // operand ring depth: A = 64 TMEM columns (hi | lo), B = 16 KB smem (hi | lo tiles of 64 x 128 B)
+constexpr int TC_RAW_STAGES = 5;         // raw fp32 ring depth PER converter group (8 KB per stage)
 constexpr int TC_CHUNK = 4;              // stages (= 16 hi*hi MMAs) per big-accumulator chunk
-constexpr int TC_TILE_BYTES = TC_ROWS * 128;
+constexpr int TC_TILE_BYTES = TC_M * 128; // one B tile (Z_hi or Z_lo): 64 rows x 128 B
 constexpr int TC_CONV_WARPS = 8, TC_ADD_WARPS = 4;
 constexpr int TC_CONV_THREADS = TC_CONV_WARPS * 32;
 constexpr int TC_THREADS = (1 + TC_CONV_WARPS + TC_ADD_WARPS) * 32;
-constexpr int TC_TMEM_COLS = 256;        // D_big[0] @0, D_big[1] @64, D_small[0] @128, D_small[1] @192
+constexpr int TC_TMEM_COLS = 512;        // D[0] @0, D[1] @128 (64 hi*hi columns | 64 cross-term columns), A ring @256 + 64 s (hi | lo)
+constexpr uint32_t TC_A_COL = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count)); }
@@ -62,44 +74,51 @@ __device__ __forceinline__ void umma_commit(uint64_t* b) {
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-               :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+// A operand from TMEM (lane = row, column = k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                  "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                  "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                  "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])) : "memory");
 }
 // round to nearest (ties away) on the tf32 boundary: add half an ulp of the 10-bit mantissa, clear the low 13 bits
 __device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void cp_async16z(void* smem_dst, const void* gsrc, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
 }
-// byte offset of the 16-byte chunk `chunk` (0..7) of row r inside a [128][128 B] SWIZZLE_128B tile
-__device__ __forceinline__ uint32_t sw128_chunk(int r, int chunk) {
-  return ((uint32_t)r >> 3) * 1024u + ((uint32_t)r & 7u) * 128u + (((uint32_t)chunk ^ ((uint32_t)r & 7u)) << 4);
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+// 16 consecutive columns of this thread's TMEM lane; no wait (the caller batches loads, then tmem_ld_wait())
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                 "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
 }
-
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __global__ void __launch_bounds__(TC_THREADS, 1)
 herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
                  float2* __restrict__ out, float scale, float bscale, int avg_method) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* op = smem;                                                                  // [OP_STAGES][hi tile | lo tile]
-  float4* raw = reinterpret_cast<float4*>(smem + TC_OP_STAGES * 2 * TC_TILE_BYTES);      // [RAW_STAGES][256 threads][2]
-  float* stg = reinterpret_cast<float*>(smem + TC_OP_STAGES * 2 * TC_TILE_BYTES + TC_RAW_STAGES * TC_CONV_THREADS * 2 * 16);   // [128][65]
-  __shared__ uint64_t full_bar[TC_OP_STAGES], empty_bar[TC_OP_STAGES], chunk_full[2], chunk_empty[2], small_full[2], small_empty[2];
+  // 1024-byte alignment by OFFSETTING the shared array (an integer round trip would turn every access into a generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* op = smem;                                                                  // B ring [OP_STAGES][Z_hi tile | Z_lo tile]
+  float4* raw = reinterpret_cast<float4*>(smem + TC_OP_STAGES * 2 * TC_TILE_BYTES);      // [2 groups][RAW_STAGES][8 pieces][64 channels]
+  float* stg = reinterpret_cast<float*>(smem + TC_OP_STAGES * 2 * TC_TILE_BYTES + 2 * TC_RAW_STAGES * TC_CONV_THREADS * 2 * 16);   // [128][65]
+  __shared__ uint64_t full_bar[TC_OP_STAGES], empty_bar[TC_OP_STAGES], chunk_full[2], chunk_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < TC_OP_STAGES; ++s) { mbar_init(&full_bar[s], TC_CONV_THREADS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < TC_OP_STAGES; ++s) { mbar_init(&full_bar[s], TC_CONV_THREADS / 2); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&chunk_full[b], 1); mbar_init(&chunk_empty[b], TC_ADD_WARPS * 32); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&small_full[b], 1); mbar_init(&small_empty[b], TC_ADD_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -117,89 +136,141 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
 
   if (warp == 0) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_M >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+    // The whole warp runs the loop (warp-uniform control flow and operands: ptxas emits bare UTCHMMA with uniform registers);
+    // one elected lane issues.  A descriptor differs from the ring's base descriptor only in its low word (start address).
+    {
+      const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_M >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+      const uint32_t idesc128 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * TC_M >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+      const uint64_t desc0 = umma_desc(smem_u32(op));
+      const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
       int s = 0; uint32_t ph = 0; int sf = 0;
       int cb = 0, in_chunk = 0; uint32_t ce_ph = 0u;   // parity bits, one per buffer (bit b)
       long long chunks = 0;
-      uint32_t se_ph = 0u; int frames_done = 0;
       for (long long q = 0; q < total; ++q) {
-        if (in_chunk == 0) {                                        // first stage of a chunk: D_big[cb] must have been folded
+        if (in_chunk == 0) {                                        // first stage of a chunk: D[cb] must have been folded
           if (chunks >= 2) { mbar_wait(&chunk_empty[cb], (ce_ph >> cb) & 1u); ce_ph ^= 1u << cb; }
           ++chunks;
         }
-        const int fb = frames_done & 1;                             // D_small buffer of this frame
-        if (sf == 0 && frames_done >= 2) { mbar_wait(&small_empty[fb], (se_ph >> fb) & 1u); se_ph ^= 1u << fb; }   // folded by the epilogue
         mbar_wait(&full_bar[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t hi = smem_u32(op + (size_t)s * 2 * TC_TILE_BYTES), lo = hi + TC_TILE_BYTES;
-        const uint32_t dbig = tmem_d + (uint32_t)cb * 64u, dsmall = tmem_d + 128u + (uint32_t)fb * 64u;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t dhi = umma_desc(hi + k * 32), dlo = umma_desc(lo + k * 32);
-          umma_tf32(dbig, dhi, dhi, idesc, (in_chunk | k) != 0);   // A_hi B_hi^T   (B = rows 0..63 of the same tile)
-          umma_tf32(dsmall, dhi, dlo, idesc, (sf | k) != 0);       // A_hi B_lo^T
-          umma_tf32(dsmall, dlo, dhi, idesc, 1u);                  // A_lo B_hi^T
-        }
-        umma_commit(&empty_bar[s]);                                 // stage s reusable once these MMAs retire
+        const uint32_t b32 = desc_lo0 + (uint32_t)s * (2u * TC_TILE_BYTES >> 4);
+        const uint32_t ahi = tmem_d + TC_A_COL + (uint32_t)s * 64u, alo = ahi + 32u;
+        const uint32_t dacc = tmem_d + (uint32_t)cb * 128u;
         ++sf; ++in_chunk;
         const bool frame_end = (sf == spf);
-        if (in_chunk == TC_CHUNK || frame_end) { umma_commit(&chunk_full[cb]); cb ^= 1; in_chunk = 0; }
-        if (frame_end) { sf = 0; ++frames_done; umma_commit(&small_full[fb]); }
+        const bool chunk_end = (in_chunk == TC_CHUNK) || frame_end;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // the Z_hi and Z_lo tiles are contiguous: one 128-row B operand
+            const uint64_t db = ((uint64_t)desc_hi << 32) | (b32 + (uint32_t)k * 2u);
+            umma_tf32_ts(dacc, ahi + k * 8, db, idesc128, k == 0 ? (uint32_t)(in_chunk != 1) : 1u);   // A_hi [Z_hi; Z_lo]^T
+            umma_tf32_ts(dacc + 64u, alo + k * 8, db, idesc64, 1u);                                   // A_lo Z_hi^T
+          }
+          umma_commit(&empty_bar[s]);                               // stage s reusable once these MMAs retire
+          if (chunk_end) umma_commit(&chunk_full[cb]);
+        }
+        __syncwarp();
+        if (chunk_end) { cb ^= 1; in_chunk = 0; }
+        if (frame_end) sf = 0;
         if (++s == TC_OP_STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp <= TC_CONV_WARPS) {
     // ================================ converters ================================
-    const int ct = tid - 32;                       // 0..255
-    const int ch = ct >> 2, qt = ct & 3;           // channel, which 4 of the stage's 16 complex samples
-    float4* myraw = raw + ct;                      // raw ring laid out [stage][piece j][thread]: conflict-free LDS.128
-    long long fi = blockIdx.x;
-    const float2* ibase = in + fi * frame_stride + (long long)ch * chan_stride;
-    int isf = 0, irs = 0; long long issued = 0;
+    // Two independent groups of 4 warps take alternate stages (group g: stages q = g, g + 2, ...), each with its own raw ring
+    // and named barrier, so one group's latencies (barrier, ring waits, TMEM store drain) hide behind the other's work.
+    const int g = (warp - 1) >> 2;
+    const int gt = ((warp - 1) & 3) * 32 + lane;   // 0..127 within the group
+    // loader role: channel gt >> 1, pieces 4 (gt & 1) + {0..3} of the stage's 8 (a piece = 2 complex samples = 16 B): 2 lanes
+    // cover one 128-byte line.  Raw ring layout [stage][piece][channel]: conflict-free for both roles.
+    const int lch = gt >> 1, lh = gt & 1;
+    float4* graw = raw + (size_t)g * TC_RAW_STAGES * (8 * TC_M);
+    float4* lraw = graw + (lh * 4) * TC_M + lch;
+    // converter role: this thread IS row (warp & 3) * 32 + lane of A = [Z; W] (TMEM lanes are per-warp quarters)
+    const int row = (warp & 3) * 32 + lane, cch = row & (TC_M - 1);
+    const bool is_w = row >= TC_M;
+    const float4* craw = graw + cch;
+    const uint32_t a_lane = tmem_d + TC_A_COL + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t row_off = ((uint32_t)cch >> 3) * 1024u + ((uint32_t)cch & 7u) * 128u, row_x = (uint32_t)cch & 7u;
+    int isf = g % spf;
+    long long fi = (long long)blockIdx.x + (long long)(g / spf) * gridDim.x;
+    const float2* ibase = in + fi * frame_stride + (long long)lch * chan_stride;
+    int irs = 0; long long qi = g;
     auto issue = [&]() {
-      const int t = isf * 16 + qt * 4;             // first complex sample of this thread's 4
-      float4* dst = myraw + (size_t)irs * TC_CONV_THREADS * 2;
+      const int t = isf * 16 + lh * 8;             // first complex sample of this thread's 8
+      float4* dst = lraw + (size_t)irs * (8 * TC_M);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < 4; ++j) {
         const int tj = t + 2 * j;
         const int nb = (tj < N) ? 16 : 0;          // N is even (launcher): a 16-byte piece is all in or all out
-        cp_async16z(dst + j * TC_CONV_THREADS, ibase + (nb ? tj : 0), nb);
+        cp_async16z(dst + j * TC_M, ibase + (nb ? tj : 0), nb);
       }
-      if (++isf == spf) { isf = 0; fi += gridDim.x; ibase = in + fi * frame_stride + (long long)ch * chan_stride; }
+      isf += 2;
+      if (isf >= spf) {
+        do { isf -= spf; fi += gridDim.x; } while (isf >= spf);
+        ibase = in + fi * frame_stride + (long long)lch * chan_stride;
+      }
       if (++irs == TC_RAW_STAGES) irs = 0;
-      ++issued;
+      qi += 2;
     };
 #pragma unroll
-    for (int p = 0; p < TC_RAW_STAGES - 1; ++p) { if (issued < total) issue(); asm volatile("cp.async.commit_group;" ::: "memory"); }
-    int s = 0; uint32_t ph = 0; int rs = 0;
-    for (long long q = 0; q < total; ++q) {
-      if (issued < total) issue();
+    for (int p = 0; p < TC_RAW_STAGES - 2; ++p) { if (qi < total) issue(); asm volatile("cp.async.commit_group;" ::: "memory"); }
+    int rs = 0;
+    for (long long q = g; q < total; q += 2) {
+      // the slot refilled here was read two iterations ago at the latest, before the barrier every thread passed last time
+      if (qi < total) issue();
       asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group %0;" :: "n"(TC_RAW_STAGES - 1) : "memory");
-      if (q >= TC_OP_STAGES) mbar_wait(&empty_bar[s], ph ^ 1u);     // MMAs of the previous use of this stage have retired
-      const float4* src = myraw + (size_t)rs * TC_CONV_THREADS * 2;
-      uint8_t* thi = op + (size_t)s * 2 * TC_TILE_BYTES;
-      uint8_t* tlo = thi + TC_TILE_BYTES;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const float4 v = src[j * TC_CONV_THREADS];   // (re0, im0, re1, im1)
-        float4 zh, zl;
-        zh.x = to_tf32(v.x); zh.y = to_tf32(v.y); zh.z = to_tf32(v.z); zh.w = to_tf32(v.w);
-        zl.x = to_tf32(v.x - zh.x); zl.y = to_tf32(v.y - zh.y); zl.z = to_tf32(v.z - zh.z); zl.w = to_tf32(v.w - zh.w);
-        const float4 wh = make_float4(zh.y, -zh.x, zh.w, -zh.z);     // (im, -re)
-        const float4 wl = make_float4(zl.y, -zl.x, zl.w, -zl.z);
-        const int chunk = qt * 2 + j;              // 16-byte chunk within the 128-byte row
-        const uint32_t oz = sw128_chunk(ch, chunk), ow = sw128_chunk(TC_M + ch, chunk);
-        *reinterpret_cast<float4*>(thi + oz) = zh;
-        *reinterpret_cast<float4*>(tlo + oz) = zl;
-        *reinterpret_cast<float4*>(thi + ow) = wh;
-        *reinterpret_cast<float4*>(tlo + ow) = wl;
+      asm volatile("cp.async.wait_group %0;" :: "n"(TC_RAW_STAGES - 2) : "memory");
+      asm volatile("bar.sync %0, 128;" :: "r"(2 + g) : "memory");   // every loader's pieces of this raw stage have landed
+      const int s = (int)(q & (TC_OP_STAGES - 1));
+      if (q >= TC_OP_STAGES) {                                      // MMAs of the previous use of this stage have retired
+        mbar_wait(&empty_bar[s], (uint32_t)((q >> 2) + 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      const float4* src = craw + (size_t)rs * (8 * TC_M);
+      uint8_t* thi = op + (size_t)s * 2 * TC_TILE_BYTES + row_off;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                 // 16 K-values (4 pieces) at a time
+        float hi[16], lo[16];
+        float4 v[4];                                // (re0, im0, re1, im1) each
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = src[(4 * h + j) * TC_M];
+        if (!is_w) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { hi[4 * j + e] = to_tf32(x[e]); lo[4 * j + e] = x[e] - hi[4 * j + e]; }
+          }
+        } else {                                    // W row: every (re, im) pair becomes (im, -re)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+              const float hre = to_tf32(x[e]), him = to_tf32(x[e + 1]);
+              hi[4 * j + e] = him;                 lo[4 * j + e] = x[e + 1] - him;
+              hi[4 * j + e + 1] = __uint_as_float(__float_as_uint(hre) ^ 0x80000000u);   lo[4 * j + e + 1] = hre - x[e];
+            }
+          }
+        }
+        if (!is_w) {             // Z rows are also the B operand: swizzled K-major tiles in shared memory
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t o = (((uint32_t)(4 * h + j)) ^ row_x) << 4;
+            *reinterpret_cast<float4*>(thi + o) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            *reinterpret_cast<float4*>(thi + TC_TILE_BYTES + o) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+        }
+        tmem_st16(a_lane + (uint32_t)s * 64u + (uint32_t)h * 16u, hi);
+        tmem_st16(a_lane + (uint32_t)s * 64u + 32u + (uint32_t)h * 16u, lo);
+      }
+      if (!is_w) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&full_bar[s]);
       if (++rs == TC_RAW_STAGES) rs = 0;
-      if (++s == TC_OP_STAGES) { s = 0; ph ^= 1u; }
     }
   } else {
     // ============================ adders + epilogue ============================
@@ -207,7 +278,7 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
     const int q4 = warp & 3;                                       // TMEM lane quarter this warp may read
     const int row = q4 * 32 + lane;                                // row of [Re R; Im R]
     const uint32_t lane_addr = tmem_d + ((uint32_t)(q4 * 32) << 16);
-    uint32_t cf_ph = 0u, sf_ph = 0u;                               // parity bits, one per buffer
+    uint32_t cf_ph = 0u;                                           // parity bits, one per buffer
     int cb = 0;
     long long fcur = blockIdx.x;
     for (int fr = 0; fr < my_frames; ++fr) {
@@ -219,28 +290,20 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
         mbar_wait(&chunk_full[cb], (cf_ph >> cb) & 1u); cf_ph ^= 1u << cb;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int c0 = 0; c0 < TC_M; c0 += 8) {
-          float v[8];
-          tmem_ld8(lane_addr + (uint32_t)cb * 64u + (uint32_t)c0, v);
+        for (int h = 0; h < 4; ++h) {               // columns 16h.. of the hi*hi block and of the cross-term block
+          uint32_t v0[16], v1[16];
+          tmem_ld16(lane_addr + (uint32_t)cb * 128u + (uint32_t)h * 16u, v0);
+          tmem_ld16(lane_addr + (uint32_t)cb * 128u + 64u + (uint32_t)h * 16u, v1);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[c0 + j] += v[j];
+          for (int j = 0; j < 16; ++j) acc[16 * h + j] += __uint_as_float(v0[j]) + __uint_as_float(v1[j]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(&chunk_empty[cb]);
         cb ^= 1;
       }
-      const int fb = fr & 1;
-      mbar_wait(&small_full[fb], (sf_ph >> fb) & 1u); sf_ph ^= 1u << fb;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int c0 = 0; c0 < TC_M; c0 += 8) {
-        float v[8];
-        tmem_ld8(lane_addr + 128u + (uint32_t)fb * 64u + (uint32_t)c0, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) stg[row * 65 + c0 + j] = acc[c0 + j] + v[j];
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&small_empty[fb]);
+      for (int c = 0; c < TC_M; ++c) stg[row * 65 + c] = acc[c];
       asm volatile("bar.sync 1, 128;" ::: "memory");
       float2* o = out + fcur * (long long)(TC_M * TC_M);
       for (int e = at; e < TC_M * TC_M; e += 128) {
@@ -272,7 +335,7 @@ int launch_covariance_tc(const float2* in, long long frame_stride, long long cha
   const bool aligned = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
                        ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
   if (!aligned) return 0;
-  const size_t smem = (size_t)TC_OP_STAGES * 2 * TC_TILE_BYTES + (size_t)TC_RAW_STAGES * TC_CONV_THREADS * 2 * sizeof(float4) +
+  const size_t smem = (size_t)TC_OP_STAGES * 2 * TC_TILE_BYTES + (size_t)2 * TC_RAW_STAGES * TC_CONV_THREADS * 2 * sizeof(float4) +
                       (size_t)128 * 65 * sizeof(float) + 1024;
   cudaFuncSetAttribute(herk_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
