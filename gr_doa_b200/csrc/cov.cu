@@ -94,12 +94,13 @@ cov16_kernel(const float2* __restrict__ in, long long frame_stride, long long ch
         }
       }
 #pragma unroll
-      for (int p = 0; p < 28; ++p) { a[2 * p] = d0.ore[p]; a[2 * p + 1] = d0.oim[p]; a[64 + 2 * p] = d1.ore[p]; a[64 + 2 * p + 1] = d1.oim[p]; }
+      for (int p = 0; p < 28; ++p) { d0.get(p, a[2 * p], a[2 * p + 1]); d1.get(p, a[64 + 2 * p], a[64 + 2 * p + 1]); }
 #pragma unroll
       for (int r = 0; r < 8; ++r) { a[56 + r] = d0.dg[r]; a[120 + r] = d1.dg[r]; }
     } else {
+      f32x2 od[64];                                 // (re, im) of R[8 + i][j] at od[i * 8 + j]
 #pragma unroll
-      for (int i = 0; i < 128; ++i) a[i] = 0.0f;
+      for (int i = 0; i < 64; ++i) od[i] = 0ull;
       for (int t = (int)lane * VEC; t < N; t += 32 * VEC) {
         float2 x[VEC][16];
         cov16_load<VEC>(base, chan_stride, t, true, x);
@@ -108,18 +109,17 @@ cov16_kernel(const float2* __restrict__ in, long long frame_stride, long long ch
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float2 xr = x[s][8 + i];
+            const f32x2 xp = pk2(xr.x, xr.y), xs = pk2(xr.y, -xr.x);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float2 xc = x[s][j];
-              float& re = a[2 * (i * 8 + j)];
-              float& im = a[2 * (i * 8 + j) + 1];
-              re = fmaf(xr.x, xc.x, re);   // x_r conj(x_c)
-              re = fmaf(xr.y, xc.y, re);
-              im = fmaf(xr.y, xc.x, im);
-              im = fmaf(-xr.x, xc.y, im);
+              od[i * 8 + j] = fma2(xp, pk2(xc.x, xc.x), od[i * 8 + j]);   // x_r conj(x_c), see CovAcc
+              od[i * 8 + j] = fma2(xs, pk2(xc.y, xc.y), od[i * 8 + j]);
             }
           }
       }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) upk2(od[i], a[2 * i], a[2 * i + 1]);
     }
     warp_reduce_scatter<128, 16>(a, lane);          // lane L now holds the full sums of elements 4L .. 4L+3
 #pragma unroll

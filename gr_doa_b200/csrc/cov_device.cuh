@@ -1,6 +1,7 @@
 // cov_device.cuh -- device code of the covariance stage shared by cov.cu and fused.cu.
 #pragma once
 #include "doa_internal.h"
+#include "f32x2.cuh"
 
 namespace doa {
 namespace {
@@ -60,17 +61,22 @@ __device__ __forceinline__ float2 folded_entry(const float* red, int r, int c, f
 }
 
 
-// Per-lane accumulators of the Hermitian lower half (M diagonal reals + M(M-1)/2 complex = M*M floats).
+// Per-lane accumulators of the Hermitian lower half (M diagonal reals + M(M-1)/2 complex = M*M floats).  An off-diagonal
+// entry is one packed pair (re, im) updated by two fma.rn.f32x2 per sample:
+//     (re, im) += (x_r.re, x_r.im) * x_c.re          (re, im) += (x_r.im, -x_r.re) * x_c.im
+// which is, per component and in this order, the scalar form  re = fma(xr.re, xc.re, re); re = fma(xr.im, xc.im, re);
+// im = fma(xr.im, xc.re, im); im = fma(-xr.re, xc.im, im)  -- same bits, half the issue slots (M = 8: 56 FFMA2 + 16 FFMA
+// per sample instead of 128 FFMA; the broadcast and the swapped/negated pair are operand modifiers in SASS).
 template <int M>
 struct CovAcc {
   static constexpr int NP = M * (M - 1) / 2;
   float dg[M];
-  float ore[NP > 0 ? NP : 1], oim[NP > 0 ? NP : 1];
+  f32x2 od[NP > 0 ? NP : 1];
   __device__ __forceinline__ void clear() {
 #pragma unroll
     for (int r = 0; r < M; ++r) dg[r] = 0.0f;
 #pragma unroll
-    for (int p = 0; p < NP; ++p) { ore[p] = 0.0f; oim[p] = 0.0f; }
+    for (int p = 0; p < NP; ++p) od[p] = 0ull;
   }
   // one time sample of all M channels
   __device__ __forceinline__ void add(const float2 (&x)[M]) {
@@ -79,23 +85,23 @@ struct CovAcc {
       const float2 xr = x[r];
       dg[r] = fmaf(xr.x, xr.x, dg[r]);
       dg[r] = fmaf(xr.y, xr.y, dg[r]);
+      const f32x2 xp = pk2(xr.x, xr.y), xs = pk2(xr.y, -xr.x);
 #pragma unroll
       for (int c = 0; c < r; ++c) {
         const float2 xc = x[c];
         const int p = r * (r - 1) / 2 + c;
-        ore[p] = fmaf(xr.x, xc.x, ore[p]);   // x_r conj(x_c)
-        ore[p] = fmaf(xr.y, xc.y, ore[p]);
-        oim[p] = fmaf(xr.y, xc.x, oim[p]);
-        oim[p] = fmaf(-xr.x, xc.y, oim[p]);
+        od[p] = fma2(xp, pk2(xc.x, xc.x), od[p]);   // x_r conj(x_c)
+        od[p] = fma2(xs, pk2(xc.y, xc.y), od[p]);
       }
     }
   }
+  __device__ __forceinline__ void get(int p, float& re, float& im) const { upk2(od[p], re, im); }
   // fold the 32 lanes' partial matrices; `red` (M*M floats, shared, this warp's) receives the raw sums
   __device__ __forceinline__ void fold(unsigned lane, float* red) {
     constexpr int CNT = M * M;
     float a[CNT];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) { a[2 * p] = ore[p]; a[2 * p + 1] = oim[p]; }
+    for (int p = 0; p < NP; ++p) upk2(od[p], a[2 * p], a[2 * p + 1]);
 #pragma unroll
     for (int r = 0; r < M; ++r) a[2 * NP + r] = dg[r];
     warp_reduce_scatter<CNT, 16>(a, lane);

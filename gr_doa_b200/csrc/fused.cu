@@ -11,7 +11,7 @@
 // Hand-off with named barriers (bar.arrive / bar.sync): FULL0/1 and EMPTY0/1 between the two groups; a consumer warp owns
 // its matrices end to end, so the consumers need no barrier among themselves.
 // The device code is the stage kernels' own and per-entry operation order is unchanged, so the fused path is bit-identical to
-// the three-kernel path (tested).  Measured on B200 at cfg3: 2.21 ms (three kernels) -> 1.94 ms; a phase-structured variant
+// the three-kernel path (tested).  Measured on B200 at cfg3: 2.21 ms (three kernels) -> 1.66 ms; a phase-structured variant
 // (two CTAs/SM alternating stream / Jacobi / scan phases behind __syncthreads) measured 2.02 ms and was dropped.
 #include "cov_device.cuh"
 #include "eig_device.cuh"
@@ -22,7 +22,6 @@
 namespace doa {
 namespace {
 
-constexpr int WS_STAGES = 3;
 constexpr int BAR_FULL = 1, BAR_EMPTY = 3;
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
@@ -34,7 +33,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(NKEEP) : "memory"); }
 
-template <int M, int KL, int WS_P, int WS_C>
+template <int M, int KL, int WS_P, int WS_C, int WS_STAGES>
 __global__ void __launch_bounds__((WS_P + WS_C) * 32, 1)
 chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
                 int avg_method, float scale, float bscale, int T, int max_sweeps, const float* __restrict__ zpair,
@@ -61,8 +60,15 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
   const int nf = (int)(per + (blockIdx.x < rem ? 1 : 0));            // frames of this CTA
   const int ntiles = (nf + TILE - 1) / TILE;
 
+  // More than 16 warps do not fit at the producers' 128 registers: the kernel is then compiled for (and launched with) 96
+  // per thread, the consumer warpgroups hand registers back and the producer warpgroup takes them (setmaxnreg works on
+  // aligned groups of 4 warps, hence WS_P == 4).
+  constexpr bool REALLOC = (WS_P + WS_C) > 16;
+  static_assert(!REALLOC || (WS_P == 4 && WS_C % 4 == 0 && (WS_P * 128 + WS_C * 88) * 32 <= 65536 / NTHREADS / 8 * 8 * NTHREADS),
+                "register budget of the re-allocated configuration");
   if (warp < WS_P) {
     // ================================ producer ================================
+    if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     const int w = warp;
     const int NCH = (N + 63) / 64;                                   // 64-sample chunks per frame (2 samples per lane)
     const int nfw = (w < nf) ? (nf - w + WS_P - 1) / WS_P : 0;       // frames of this warp: w, w+P, w+2P, ...
@@ -123,6 +129,7 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
     }
   } else {
     // ================================ consumer ================================
+    if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     const int ct = threadIdx.x - WS_P * 32, cw = warp - WS_P;
     for (int t = 0; t < ntiles; ++t) {
       const int b = t & 1;
@@ -146,14 +153,14 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
   }
 }
 
-template <int M, int WS_P, int WS_C>
+template <int M, int WS_P, int WS_C, int WS_STAGES>
 int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
                   int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st) {
   constexpr int TILE = WS_C * 32 / M;
   const size_t smem = ((ztab_floats(tb.P) + 3) & ~(size_t)3) * sizeof(float) + ((size_t)3 * TILE * M * M + (size_t)TILE * M) * sizeof(float2) +
                       (size_t)WS_P * M * M * sizeof(float) + (size_t)WS_P * WS_STAGES * M * 32 * sizeof(float4);
   if (smem > 225 * 1024) return 0;
-  auto kern = chain_ws_kernel<M, 4, WS_P, WS_C>;
+  auto kern = chain_ws_kernel<M, 4, WS_P, WS_C, WS_STAGES>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -178,8 +185,30 @@ int launch_chain_fused(const float2* in, long long frame_stride, long long chan_
   const bool vec2 = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
                     ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
   if (!vec2) return 0;
-  // 4 producer + 12 consumer warps measured best (1.94 ms at cfg3) among 4/12, 5/11, 6/10, 8/8 (2.02 - 2.19 ms)
-  return launch_ws_cfg<8, 4, 12>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st);
+  // Producer/consumer split and ring depth, measured at cfg3 with the packed (FFMA2) covariance: 8+8 warps x 3 stages 1.66 ms;
+  // 4+12: 1.88-1.99, 5+11: 1.91, 6+10: 1.85, 7+9: 1.84, 9+7: 1.94, 10+6: 2.03, 12+4: 2.39; 4+16 (setmaxnreg re-allocation,
+  // 96-register launch): 1.97.  Warp-stall sampling (profiles/) shows why: with 4 producers the consumers idle at the FULL
+  // barrier 41 % of the time while each producer warp, alone on its scheduler, issues at 0.25 IPC.
+#define WS_ARGS in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st
+  switch (dev_option("ws_split", 808) * 10 + dev_option("ws_stages", 3)) {   // producers * 100 + consumers, ring stages
+    case 4163: case 4164: return launch_ws_cfg<8, 4, 16, 4>(WS_ARGS);
+    case 4124: return launch_ws_cfg<8, 4, 12, 4>(WS_ARGS);
+    case 4125: return launch_ws_cfg<8, 4, 12, 5>(WS_ARGS);
+    case 5113: return launch_ws_cfg<8, 5, 11, 3>(WS_ARGS);
+    case 5114: return launch_ws_cfg<8, 5, 11, 4>(WS_ARGS);
+    case 6103: return launch_ws_cfg<8, 6, 10, 3>(WS_ARGS);
+    case 6104: return launch_ws_cfg<8, 6, 10, 4>(WS_ARGS);
+    case 7093: return launch_ws_cfg<8, 7, 9, 3>(WS_ARGS);
+    case 8083: return launch_ws_cfg<8, 8, 8, 3>(WS_ARGS);
+    case 8082: return launch_ws_cfg<8, 8, 8, 2>(WS_ARGS);
+    case 9073: return launch_ws_cfg<8, 9, 7, 3>(WS_ARGS);
+    case 10063: return launch_ws_cfg<8, 10, 6, 3>(WS_ARGS);
+    case 10062: return launch_ws_cfg<8, 10, 6, 2>(WS_ARGS);
+    case 12043: return launch_ws_cfg<8, 12, 4, 3>(WS_ARGS);
+    case 4123: return launch_ws_cfg<8, 4, 12, 3>(WS_ARGS);
+    default: return launch_ws_cfg<8, 8, 8, 3>(WS_ARGS);
+  }
+#undef WS_ARGS
 }
 
 }  // namespace doa

@@ -1,6 +1,7 @@
 // scan_device.cuh -- device code of the pseudo-spectrum scan + peak picking shared by scan.cu and fused.cu.
 #pragma once
 #include "doa_internal.h"
+#include "f32x2.cuh"
 #include <cfloat>
 
 namespace doa {
@@ -176,14 +177,7 @@ __device__ __forceinline__ int rank_desc(float v, int K, int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Packed pair arithmetic: Blackwell's fma.rn.f32x2 does two FMAs per lane per instruction (same FMA-pipe rate as FFMA,
-// half the issue slots; measured, tools/microbench/ffma2.cu).
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-
+// Packed pair arithmetic (f32x2.cuh).
 // Two adjacent bins at once.  State (A, B) = (Re acc, -Im acc); with the table holding zx, zy and -zy no negation is needed:
 //   A' = A zx + (B zy + ux)        B' = A (-zy) + (B zx - uy)
 // Operation for operation this is the scalar Horner of q_coarse (negations are exact), so both give identical bits.
