@@ -64,11 +64,12 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
   // per thread, the consumer warpgroups hand registers back and the producer warpgroup takes them (setmaxnreg works on
   // aligned groups of 4 warps, hence WS_P == 4).
   constexpr bool REALLOC = (WS_P + WS_C) > 16;
-  static_assert(!REALLOC || (WS_P == 4 && WS_C % 4 == 0 && (WS_P * 128 + WS_C * 88) * 32 <= 65536 / NTHREADS / 8 * 8 * NTHREADS),
+  constexpr int REG_P = (WS_P == 4) ? 128 : 120, REG_C = (WS_P == 4) ? 88 : 80;
+  static_assert(!REALLOC || (WS_P % 4 == 0 && WS_C % 4 == 0 && (WS_P * REG_P + WS_C * REG_C) * 32 <= 65536 / NTHREADS / 8 * 8 * NTHREADS),
                 "register budget of the re-allocated configuration");
   if (warp < WS_P) {
     // ================================ producer ================================
-    if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(REG_P));
     const int w = warp;
     const int NCH = (N + 63) / 64;                                   // 64-sample chunks per frame (2 samples per lane)
     const int nfw = (w < nf) ? (nf - w + WS_P - 1) / WS_P : 0;       // frames of this warp: w, w+P, w+2P, ...
@@ -129,7 +130,7 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
     }
   } else {
     // ================================ consumer ================================
-    if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(REG_C));
     const int ct = threadIdx.x - WS_P * 32, cw = warp - WS_P;
     for (int t = 0; t < ntiles; ++t) {
       const int b = t & 1;
@@ -202,6 +203,8 @@ int launch_chain_fused(const float2* in, long long frame_stride, long long chan_
     case 8083: return launch_ws_cfg<8, 8, 8, 3>(WS_ARGS);
     case 8082: return launch_ws_cfg<8, 8, 8, 2>(WS_ARGS);
     case 9073: return launch_ws_cfg<8, 9, 7, 3>(WS_ARGS);
+    case 8123: return launch_ws_cfg<8, 8, 12, 3>(WS_ARGS);
+    case 8122: return launch_ws_cfg<8, 8, 12, 2>(WS_ARGS);
     case 10063: return launch_ws_cfg<8, 10, 6, 3>(WS_ARGS);
     case 10062: return launch_ws_cfg<8, 10, 6, 2>(WS_ARGS);
     case 12043: return launch_ws_cfg<8, 12, 4, 3>(WS_ARGS);
