@@ -166,6 +166,9 @@ int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nfram
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // Multi-GPU runs leave a few SMs to the peak gather's NCCL kernel so that it overlaps the next step's chain kernel
+  // (a persistent CTA owns a whole SM's registers and shared memory: nothing else can co-reside).
+  sms = std::max(1, sms - std::max(0, dev_option("chain_sms_reserve", 0)));
   const int grid = std::max(1, std::min(sms, (nframes + TILE - 1) / TILE));
   const float scale = (float)(1.0 / N), bscale = (float)(0.5 / N);
   kern<<<grid, (WS_P + WS_C) * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.V, tb.xaxis, tb.P,

@@ -95,6 +95,63 @@ class PeakBuffers:
                 gathered[:, 2].reshape(w * n, K))
 
 
+class PeakExchange:
+    """The per-step exchange, pipelined: `depth` PeakBuffers used round-robin and a side stream, so that the gather of step i
+    runs under the chain kernel of step i+1 (the chain kernel must leave the collective's kernel a few SMs:
+    dev knob chain_sms_reserve).  Per step:  out = ex.begin();  chain.run_device(x, out=out);  ex.submit().
+    `drain()` makes the current stream wait for every gather submitted so far.  On CPU tensors (gloo tests) the same calls run
+    synchronously."""
+
+    def __init__(self, n: int, K: int, device, world: int = 1, is_dst: bool = False, depth: int = 2, dst: int = 0, group=None,
+                 pipelined: bool = True):
+        self.bufs = [PeakBuffers(n, K, device, world=world, is_dst=is_dst) for _ in range(depth)]
+        self.world, self.dst, self.group, self.i = world, dst, group, 0
+        self.cuda = torch.device(device).type == "cuda" and pipelined   # otherwise: the gather runs in stream order
+        if self.cuda and world > 1:
+            self.comm = torch.cuda.Stream(device=device)
+            self.ready = [torch.cuda.Event() for _ in range(depth)]      # chain kernel of this slot finished
+            self.done = [None] * depth                                   # gather of this slot finished
+        self.last = None
+
+    def begin(self):
+        """Outputs for the next step; the current stream first waits until this slot's previous gather has read them."""
+        k = self.i % len(self.bufs)
+        if self.cuda and self.world > 1 and self.done[k] is not None:
+            torch.cuda.current_stream().wait_event(self.done[k])
+        return self.bufs[k].outputs()
+
+    def submit(self):
+        """Queue the gather of the slot filled since begin(); returns that slot's PeakBuffers."""
+        k = self.i % len(self.bufs)
+        pb = self.bufs[k]
+        self.i += 1
+        self.last = pb
+        if self.world == 1:
+            return pb
+        if not self.cuda:
+            pb.gather(dst=self.dst, group=self.group)
+            return pb
+        self.ready[k].record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ready[k])
+            pb.gather(dst=self.dst, group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.comm)
+            self.done[k] = ev
+        return pb
+
+    def drain(self):
+        if self.cuda and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm)
+
+    def result(self):
+        """(val, loc, bins) of the last submitted step in frame order on dst (after drain()), None elsewhere."""
+        pb = self.last
+        if self.world == 1:
+            return pb.outputs()
+        return PeakBuffers.split(pb.gathered) if pb.gathered is not None else None
+
+
 def run_sharded(chain_fn, frames_local, nframes_total: int, dst: int = 0, group=None):
     """chain_fn(frames_local) -> (val, loc, bins) for this rank's frames; returns the gathered result on dst."""
     val, loc, bins = chain_fn(frames_local)

@@ -75,6 +75,51 @@ def test_packed_peak_buffers_gather():
     assert q.get(timeout=5) is True
 
 
+def _worker_exchange(rank, world, port, q):
+    """Three pipelined steps through PeakExchange (two slots): every step's gather delivers that step's data."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, K = 5, 2
+    ex = sharding.PeakExchange(n, K, "cpu", world=world, is_dst=(rank == 0))
+    ok = True
+    for step in range(3):
+        val, loc, bins = ex.begin()
+        g = torch.Generator().manual_seed(1000 * step + rank)
+        val.copy_(torch.randn((n, K), generator=g)); loc.copy_(torch.randn((n, K), generator=g))
+        bins.copy_(torch.randint(0, 4096, (n, K), generator=g, dtype=torch.int32))
+        ex.submit()
+        ex.drain()
+        res = ex.result()
+        if rank == 0:
+            v, l, b = res
+            for r in range(world):
+                g = torch.Generator().manual_seed(1000 * step + r)
+                ok &= torch.equal(v[r * n:(r + 1) * n], torch.randn((n, K), generator=g))
+                ok &= torch.equal(l[r * n:(r + 1) * n], torch.randn((n, K), generator=g))
+                ok &= torch.equal(b[r * n:(r + 1) * n], torch.randint(0, 4096, (n, K), generator=g, dtype=torch.int32))
+        else:
+            ok &= res is None
+    if rank == 0:
+        q.put(bool(ok))
+    else:
+        assert ok
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_peak_exchange():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_exchange, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
 def _worker(rank, world, port, nframes, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
