@@ -146,7 +146,7 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
       if (t + 2 < ntiles) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NTHREADS); }
       for (int i = cw * (32 / M); i < min(nt, (cw + 1) * (32 / M)); ++i) {
         const long long f = lo + (long long)t * TILE + i;
-        scan_frame_peaks<M, KL>(us + i * M, Gs + i * MM, zt, nullptr, Vtab, xaxis, M, P, K, lane, out_val + f * K,
+        scan_frame_peaks<M, KL, true>(us + i * M, Gs + i * MM, zt, nullptr, Vtab, xaxis, M, P, K, lane, out_val + f * K,
                                             out_loc + f * K, out_bin ? out_bin + f * K : nullptr);
       }
       __syncwarp();

@@ -228,7 +228,8 @@ __device__ __forceinline__ ZTab ztab_fill(float* smem, const float* __restrict__
 // One frame by one warp: coarse scan over all P bins, peak picking, refinement with the reference arithmetic, dB
 // conversion, sorted outputs.  uf: the frame's M diagonal sums, Gf: its M x M projector (global or shared memory);
 // us: M float2 of per-warp shared scratch (runtime-M path only); o_*: this frame's K output slots.
-template <int MT, int KL>
+// ZS: the z table is known to live in shared memory (fused kernel): the hot loop then uses LDS instead of generic loads.
+template <int MT, int KL, bool ZS = false>
 __device__ __forceinline__ void scan_frame_peaks(const float2* __restrict__ uf, const float2* __restrict__ Gf, const ZTab& zt,
                                                  float2* us, const float2* __restrict__ Vtab,
                                                  const float* __restrict__ xaxis, int M, int P, int K, int lane,
@@ -271,18 +272,40 @@ __device__ __forceinline__ void scan_frame_peaks(const float2* __restrict__ uf, 
         cand = down ? bin : cand;
         p1 = q;
       };
+      // Four bins at a time.  Inside [s0, s1) an armed candidate is always a bin of this lane (cand < s1), so an emission in
+      // the group is  up_i && d1_i  for some i; Q is a degree-(M-1) trigonometric polynomial with at most M-1 minima per
+      // frame, so that is rare: the common path only advances the detector state, the rare one replays the four steps.
+      auto feed4 = [&](float q0, float q1, float q2, float q3, int bin0) {
+        const bool up0 = q0 > p1, dn0 = q0 < p1, up1 = q1 > q0, dn1 = q1 < q0, up2 = q2 > q1, dn2 = q2 < q1, up3 = q3 > q2, dn3 = q3 < q2;
+        const bool da = dn0 || (d1 && !up0), db = dn1 || (da && !up1), dc = dn2 || (db && !up2), dd = dn3 || (dc && !up3);
+        if ((up0 && d1) || (up1 && da) || (up2 && db) || (up3 && dc)) {
+          feed(q0, bin0); feed(q1, bin0 + 1); feed(q2, bin0 + 2); feed(q3, bin0 + 3);
+        } else {
+          cand = dn3 ? bin0 + 3 : dn2 ? bin0 + 2 : dn1 ? bin0 + 1 : dn0 ? bin0 : cand;
+          d1 = dd; p1 = q3;
+        }
+      };
       const int len = s1 - s0;
       if (k == 1) { feed(q_at(1), 1); k = 2; }          // lane 0: bins 0,1 handled, continue pair-aligned
       const float4* pa = reinterpret_cast<const float4*>(za + lane * zt.LA);
       const float2* pb = reinterpret_cast<const float2*>(zb + lane * zt.LB);
+      const unsigned pa_s = ZS ? (unsigned)__cvta_generic_to_shared(pa) : 0u, pb_s = ZS ? (unsigned)__cvta_generic_to_shared(pb) : 0u;
       for (; k + 4 <= len; k += 4) {
-        const float4 a0 = pa[k >> 1], a1 = pa[(k >> 1) + 1];
-        const float2 b0 = pb[k >> 1], b1 = pb[(k >> 1) + 1];
+        float4 a0, a1; float2 b0, b1;
+        if constexpr (ZS) {
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a0.x), "=f"(a0.y), "=f"(a0.z), "=f"(a0.w) : "r"(pa_s + (unsigned)(k >> 1) * 16u));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(a1.x), "=f"(a1.y), "=f"(a1.z), "=f"(a1.w) : "r"(pa_s + (unsigned)(k >> 1) * 16u));
+          asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(b0.x), "=f"(b0.y) : "r"(pb_s + (unsigned)(k >> 1) * 8u));
+          asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+8];" : "=f"(b1.x), "=f"(b1.y) : "r"(pb_s + (unsigned)(k >> 1) * 8u));
+        } else {
+          a0 = pa[k >> 1]; a1 = pa[(k >> 1) + 1];
+          b0 = pb[k >> 1]; b1 = pb[(k >> 1) + 1];
+        }
         const f32x2 Q0 = q_coarse_pair<MT>(ux2, muy2, u0_2, two2, pk2(a0.x, a0.y), pk2(a0.z, a0.w), pk2(b0.x, b0.y));
         const f32x2 Q1 = q_coarse_pair<MT>(ux2, muy2, u0_2, two2, pk2(a1.x, a1.y), pk2(a1.z, a1.w), pk2(b1.x, b1.y));
         float q0, q1, q2, q3;
         upk2(Q0, q0, q1); upk2(Q1, q2, q3);
-        feed(q0, s0 + k); feed(q1, s0 + k + 1); feed(q2, s0 + k + 2); feed(q3, s0 + k + 3);
+        feed4(q0, q1, q2, q3, s0 + k);
       }
       for (; k < len; ++k) feed(q_at(s0 + k), s0 + k);
       if (s1 < P) {
