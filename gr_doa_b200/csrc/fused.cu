@@ -5,13 +5,13 @@
 // owns a contiguous range of frames and keeps every intermediate (R, G, u) in shared memory:
 //   producer warps: stream their frames through per-lane cp.async rings (WS_STAGES x 4 KB per warp, so the bytes in flight
 //       depend neither on registers nor on what the other warps do), accumulate the covariance (cov_device.cuh), emit R into
-//       a double-buffered tile and signal "full"; they wait for the consumers only when both tile buffers are taken.
+//       one of WS_NBUF tile buffers and signal "full"; they wait for the consumers only when every tile buffer is taken.
 //   consumer warps: wait for a full tile (TILE = 32/M matrices per consumer warp), run Jacobi on their own matrices
 //       (eig_device.cuh), release the tile buffer, scan + pick + refine their frames (scan_device.cuh) and write K peaks.
 // Hand-off with named barriers (bar.arrive / bar.sync): FULL0/1 and EMPTY0/1 between the two groups; a consumer warp owns
 // its matrices end to end, so the consumers need no barrier among themselves.
 // The device code is the stage kernels' own and per-entry operation order is unchanged, so the fused path is bit-identical to
-// the three-kernel path (tested).  Measured on B200 at cfg3: 2.21 ms (three kernels) -> 1.66 ms; a phase-structured variant
+// the three-kernel path (tested).  Measured on B200 at cfg3: 2.21 ms (three kernels) -> 1.64 ms; a phase-structured variant
 // (two CTAs/SM alternating stream / Jacobi / scan phases behind __syncthreads) measured 2.02 ms and was dropped.
 #include "cov_device.cuh"
 #include "eig_device.cuh"
@@ -22,7 +22,7 @@
 namespace doa {
 namespace {
 
-constexpr int BAR_FULL = 1, BAR_EMPTY = 3;
+constexpr int BAR_FULL = 1;                     // named barriers: FULL b = 1 + b, EMPTY b = 1 + WS_NBUF + b
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
@@ -33,7 +33,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(NKEEP) : "memory"); }
 
-template <int M, int KL, int WS_P, int WS_C, int WS_STAGES>
+template <int M, int KL, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF>
 __global__ void __launch_bounds__((WS_P + WS_C) * 32, 1)
 chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
                 int avg_method, float scale, float bscale, int T, int max_sweeps, const float* __restrict__ zpair,
@@ -41,17 +41,19 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
                 float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin) {
   static_assert(M == 8, "tile geometry below assumes 8 lanes per matrix");
   constexpr int TILE = WS_C * 32 / M;          // frames per tile: every consumer warp owns 32/M of them
+  constexpr int BAR_EMPTY = BAR_FULL + WS_NBUF; // WS_NBUF tile buffers between producers and consumers
+  static_assert(BAR_EMPTY + WS_NBUF <= 16, "named barriers");
   constexpr int MM = M * M;
   constexpr int NTHREADS = (WS_P + WS_C) * 32;
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
   const ZTab zt = ztab_fill(smem, zpair, P);
-  float2* Rbuf = reinterpret_cast<float2*>(smem + ((ztab_floats(P) + 3) & ~(size_t)3));   // [2][TILE][MM]
-  float2* Gs = Rbuf + 2 * TILE * MM;                                 // [TILE][MM]
+  float2* Rbuf = reinterpret_cast<float2*>(smem + ((ztab_floats(P) + 3) & ~(size_t)3));   // [WS_NBUF][TILE][MM]
+  float2* Gs = Rbuf + WS_NBUF * TILE * MM;                                 // [TILE][MM]
   float2* us = Gs + TILE * MM;                                       // [TILE][M]
   float* red = reinterpret_cast<float*>(us + TILE * M);              // [WS_P][MM]
   float4* ring = reinterpret_cast<float4*>(red + WS_P * MM);         // [WS_P][WS_STAGES][M][32]
-  for (int i = threadIdx.x; i < 2 * TILE * MM; i += blockDim.x) Rbuf[i] = make_float2(0.f, 0.f);
+  for (int i = threadIdx.x; i < WS_NBUF * TILE * MM; i += blockDim.x) Rbuf[i] = make_float2(0.f, 0.f);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -112,20 +114,20 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
         const int tf = g / TILE, slot = g - tf * TILE;
         acc.fold((unsigned)lane, red + w * MM);
         while (cur_tile < tf) {                                       // close tiles this warp is done with
-          if (!opened && cur_tile >= 2) bar_sync(BAR_EMPTY + (cur_tile & 1), NTHREADS);
+          if (!opened && cur_tile >= WS_NBUF) bar_sync(BAR_EMPTY + (cur_tile % WS_NBUF), NTHREADS);
           __threadfence_block();
-          bar_arrive(BAR_FULL + (cur_tile & 1), NTHREADS);
+          bar_arrive(BAR_FULL + (cur_tile % WS_NBUF), NTHREADS);
           ++cur_tile; opened = false;
         }
-        if (!opened) { if (cur_tile >= 2) bar_sync(BAR_EMPTY + (cur_tile & 1), NTHREADS); opened = true; }
-        cov_warp_emit<M>(red + w * MM, scale, bscale, avg_method, (unsigned)lane, Rbuf + ((size_t)(tf & 1) * TILE + slot) * MM);
+        if (!opened) { if (cur_tile >= WS_NBUF) bar_sync(BAR_EMPTY + (cur_tile % WS_NBUF), NTHREADS); opened = true; }
+        cov_warp_emit<M>(red + w * MM, scale, bscale, avg_method, (unsigned)lane, Rbuf + ((size_t)(tf % WS_NBUF) * TILE + slot) * MM);
         acc.clear();
       }
     }
     while (cur_tile < ntiles) {
-      if (!opened && cur_tile >= 2) bar_sync(BAR_EMPTY + (cur_tile & 1), NTHREADS);
+      if (!opened && cur_tile >= WS_NBUF) bar_sync(BAR_EMPTY + (cur_tile % WS_NBUF), NTHREADS);
       __threadfence_block();
-      bar_arrive(BAR_FULL + (cur_tile & 1), NTHREADS);
+      bar_arrive(BAR_FULL + (cur_tile % WS_NBUF), NTHREADS);
       ++cur_tile; opened = false;
     }
   } else {
@@ -133,7 +135,7 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
     if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(REG_C));
     const int ct = threadIdx.x - WS_P * 32, cw = warp - WS_P;
     for (int t = 0; t < ntiles; ++t) {
-      const int b = t & 1;
+      const int b = t % WS_NBUF;
       const int nt = min(TILE, nf - t * TILE);
       bar_sync(BAR_FULL + b, NTHREADS);
       {
@@ -143,7 +145,7 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
       // A consumer warp owns its 32/M matrices end to end (Jacobi -> G/u -> scan), so nothing but the tile buffer is shared:
       // no consumer-wide barrier, a warp whose matrices converge early starts scanning early.
       __syncwarp();
-      if (t + 2 < ntiles) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NTHREADS); }
+      if (t + WS_NBUF < ntiles) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NTHREADS); }
       for (int i = cw * (32 / M); i < min(nt, (cw + 1) * (32 / M)); ++i) {
         const long long f = lo + (long long)t * TILE + i;
         scan_frame_peaks<M, KL, true>(us + i * M, Gs + i * MM, zt, nullptr, Vtab, xaxis, M, P, K, lane, out_val + f * K,
@@ -154,14 +156,14 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
   }
 }
 
-template <int M, int WS_P, int WS_C, int WS_STAGES>
+template <int M, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF = 3>
 int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
                   int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st) {
   constexpr int TILE = WS_C * 32 / M;
-  const size_t smem = ((ztab_floats(tb.P) + 3) & ~(size_t)3) * sizeof(float) + ((size_t)3 * TILE * M * M + (size_t)TILE * M) * sizeof(float2) +
+  const size_t smem = ((ztab_floats(tb.P) + 3) & ~(size_t)3) * sizeof(float) + ((size_t)(WS_NBUF + 1) * TILE * M * M + (size_t)TILE * M) * sizeof(float2) +
                       (size_t)WS_P * M * M * sizeof(float) + (size_t)WS_P * WS_STAGES * M * 32 * sizeof(float4);
   if (smem > 225 * 1024) return 0;
-  auto kern = chain_ws_kernel<M, 4, WS_P, WS_C, WS_STAGES>;
+  auto kern = chain_ws_kernel<M, 4, WS_P, WS_C, WS_STAGES, WS_NBUF>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -189,30 +191,25 @@ int launch_chain_fused(const float2* in, long long frame_stride, long long chan_
   const bool vec2 = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
                     ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
   if (!vec2) return 0;
-  // Producer/consumer split and ring depth, measured at cfg3 with the packed (FFMA2) covariance: 8+8 warps x 3 stages 1.66 ms;
+  // Producer/consumer split, ring depth and tile buffers, measured at cfg3 with the packed (FFMA2) covariance: 8+8 warps,
+  // 2 stages x 4 tile buffers or 3 x 3: 1.59-1.64 ms (equal within box-to-box noise; 2 x 4 needs 201 KB of shared memory);
   // 4+12: 1.88-1.99, 5+11: 1.91, 6+10: 1.85, 7+9: 1.84, 9+7: 1.94, 10+6: 2.03, 12+4: 2.39; 4+16 (setmaxnreg re-allocation,
   // 96-register launch): 1.97.  Warp-stall sampling (profiles/) shows why: with 4 producers the consumers idle at the FULL
   // barrier 41 % of the time while each producer warp, alone on its scheduler, issues at 0.25 IPC.
 #define WS_ARGS in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st
-  switch (dev_option("ws_split", 808) * 10 + dev_option("ws_stages", 3)) {   // producers * 100 + consumers, ring stages
-    case 4163: case 4164: return launch_ws_cfg<8, 4, 16, 4>(WS_ARGS);
-    case 4124: return launch_ws_cfg<8, 4, 12, 4>(WS_ARGS);
-    case 4125: return launch_ws_cfg<8, 4, 12, 5>(WS_ARGS);
-    case 5113: return launch_ws_cfg<8, 5, 11, 3>(WS_ARGS);
-    case 5114: return launch_ws_cfg<8, 5, 11, 4>(WS_ARGS);
-    case 6103: return launch_ws_cfg<8, 6, 10, 3>(WS_ARGS);
-    case 6104: return launch_ws_cfg<8, 6, 10, 4>(WS_ARGS);
-    case 7093: return launch_ws_cfg<8, 7, 9, 3>(WS_ARGS);
-    case 8083: return launch_ws_cfg<8, 8, 8, 3>(WS_ARGS);
-    case 8082: return launch_ws_cfg<8, 8, 8, 2>(WS_ARGS);
-    case 9073: return launch_ws_cfg<8, 9, 7, 3>(WS_ARGS);
-    case 8123: return launch_ws_cfg<8, 8, 12, 3>(WS_ARGS);
-    case 8122: return launch_ws_cfg<8, 8, 12, 2>(WS_ARGS);
-    case 10063: return launch_ws_cfg<8, 10, 6, 3>(WS_ARGS);
-    case 10062: return launch_ws_cfg<8, 10, 6, 2>(WS_ARGS);
-    case 12043: return launch_ws_cfg<8, 12, 4, 3>(WS_ARGS);
-    case 4123: return launch_ws_cfg<8, 4, 12, 3>(WS_ARGS);
-    default: return launch_ws_cfg<8, 8, 8, 3>(WS_ARGS);
+  // dev knobs (tools/ws_exp.py): ws_split = producers * 100 + consumers, ws_stages = cp.async ring depth, ws_nbuf = tile buffers
+  switch ((dev_option("ws_split", 808) * 10 + dev_option("ws_stages", 2)) * 10 + dev_option("ws_nbuf", 4)) {
+    case 41232: return launch_ws_cfg<8, 4, 12, 3, 2>(WS_ARGS);      // the first fused configuration (1.91 ms)
+    case 41252: return launch_ws_cfg<8, 4, 12, 5, 2>(WS_ARGS);
+    case 41642: return launch_ws_cfg<8, 4, 16, 4, 2>(WS_ARGS);      // setmaxnreg re-allocated
+    case 61032: return launch_ws_cfg<8, 6, 10, 3, 2>(WS_ARGS);
+    case 81232: return launch_ws_cfg<8, 8, 12, 3, 2>(WS_ARGS);      // setmaxnreg re-allocated
+    case 80832: return launch_ws_cfg<8, 8, 8, 3, 2>(WS_ARGS);
+    case 80833: return launch_ws_cfg<8, 8, 8, 3, 3>(WS_ARGS);
+    case 80823: return launch_ws_cfg<8, 8, 8, 2, 3>(WS_ARGS);
+    case 80825: return launch_ws_cfg<8, 8, 8, 2, 5>(WS_ARGS);
+    case 80826: return launch_ws_cfg<8, 8, 8, 2, 6>(WS_ARGS);
+    default: return launch_ws_cfg<8, 8, 8, 2, 4>(WS_ARGS);
   }
 #undef WS_ARGS
 }

@@ -1,4 +1,4 @@
-"""Fused-kernel configuration sweep at cfg3 (dev knobs ws_split = producers*100 + consumers, ws_stages), interleaved
+"""Fused-kernel configuration sweep at cfg3 (dev knobs ws_split = producers*100 + consumers, ws_stages, ws_nbuf; a configuration is written split|stages|nbuf, e.g. 80824), interleaved
 round-robin so that clock/thermal drift hits every configuration alike.  usage: ws_exp.py 8083 4123 ..."""
 import os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,9 +9,9 @@ L = _lib.lib()
 B, M, N, T, P, K = 65536, 8, 2048, 3, 4096, 3
 x, _ = synth.frames_torch(B, M, N, [40.0, 90.0, 140.0], jitter_deg=2.0, device="cuda", chunk=2048)
 ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
-cfgs = [int(a) for a in sys.argv[1:]] or [8083]
+cfgs = [int(a) for a in sys.argv[1:]] or [80824]
 def select(c):
-    L.doa_cuda_dev_set(b"ws_split", c // 10); L.doa_cuda_dev_set(b"ws_stages", c % 10)
+    L.doa_cuda_dev_set(b"ws_split", c // 100); L.doa_cuda_dev_set(b"ws_stages", (c // 10) % 10); L.doa_cuda_dev_set(b"ws_nbuf", c % 10)
 ref, same, times, launches = None, {}, {c: [] for c in cfgs}, {}
 for c in cfgs:
     select(c)
@@ -32,4 +32,4 @@ for rnd in range(6):
         times[c].append(e0.elapsed_time(e1) / 8)
 for c in cfgs:
     ms, med = min(times[c]), statistics.median(times[c])
-    print(f"split/stages={c}: min {ms:.4f} ms  median {med:.4f} ms  {B/med/1e3:.2f} M frames/s  frac {B*131096/med/1e6/6542.7:.3f}  launches {launches[c]}  bit-identical to first: {same[c]}", flush=True)
+    print(f"split|stages|nbuf={c}: min {ms:.4f} ms  median {med:.4f} ms  {B/med/1e3:.2f} M frames/s  frac {B*131096/med/1e6/6542.7:.3f}  launches {launches[c]}  bit-identical to first: {same[c]}", flush=True)
