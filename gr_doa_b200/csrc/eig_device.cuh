@@ -31,46 +31,58 @@ __device__ __forceinline__ Rot make_rotation(float app, float aqq, float2 apq) {
   return r;
 }
 
-template <int M> __host__ __device__ constexpr int pair_a(int s, int k) { return k == 0 ? s : (s + k) % (M - 1); }
-template <int M> __host__ __device__ constexpr int pair_b(int s, int k) { return k == 0 ? (M - 1) : (s - k + (M - 1)) % (M - 1); }
-template <int M> __host__ __device__ constexpr int pair_p(int s, int k) { return pair_a<M>(s, k) < pair_b<M>(s, k) ? pair_a<M>(s, k) : pair_b<M>(s, k); }
-template <int M> __host__ __device__ constexpr int pair_q(int s, int k) { return pair_a<M>(s, k) < pair_b<M>(s, k) ? pair_b<M>(s, k) : pair_a<M>(s, k); }
-
-template <int M, int S>
-__device__ __forceinline__ void jacobi_step(float2 (&a)[M], float2 (&v)[M], const int j, const bool frozen) {
-  constexpr int HP = M / 2;
+// One step of the round-robin tournament on the ring Z_R, R = M - 1 (index R sits out): in step S ring index r meets
+// (2S - r) mod R and S itself meets R.  Pair k of step S is (a_k, b_k) = ((S + k) mod R, (S - k) mod R), pair 0 is (S, R).
+// To keep ONE step body for all S (a fully unrolled tournament is 48 KB of code at M = 8 and 166 KB at M = 16, and the
+// eigensolver was instruction-fetch bound: `no_instruction` was its second largest stall), every lane stores the rows of
+// its column in a frame that rotates with S: original row i < R lives in register position (i - S) mod R, row R in
+// position R.  In that frame the row pairs are always (0, R) and (k, R - k), compile-time register indices; partners,
+// roles and source lanes are run-time arithmetic on (j, S); after each step the R ring rows move down one position
+// (register moves), and after a whole sweep (R steps) the frame is back where it started.  Columns never move between
+// lanes, so the shuffle count is unchanged.
+template <int M>
+__device__ __forceinline__ void jacobi_step(float2 (&a)[M], float2 (&v)[M], const int j, const int S, const bool frozen) {
+  constexpr int HP = M / 2, R = M - 1;
   constexpr unsigned FULL = 0xffffffffu;
-  // my diagonal entry, my partner, my role and my copy of the pivot
-  float dj = 0.0f;
-#pragma unroll
-  for (int i = 0; i < M; ++i) dj = (i == j) ? a[i].x : dj;
-  int partner = 0; bool is_p = false; float2 piv = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < HP; ++k) {
-    constexpr int dummy = 0; (void)dummy;
-    const int p = pair_p<M>(S, k), q = pair_q<M>(S, k);
-    if (j == p) { partner = q; is_p = true; piv = make_float2(a[q].x, -a[q].y); }   // A[p][q] = conj(A[q][p])
-    if (j == q) { partner = p; is_p = false; piv = a[p]; }
+  // my diagonal's position, my partner (lane = original column index), my role (a-role = the "p" of the rotation formulas)
+  // and the position of the pivot A[p][q] or its conjugate in my column
+  int jr, partner, pp; bool is_a;
+  if (j == R) { jr = R; partner = S; pp = 0; is_a = false; }
+  else {
+    jr = j - S; jr += (jr < 0) ? R : 0;
+    if (jr == 0) { partner = R; pp = R; is_a = true; }
+    else {
+      pp = R - jr;
+      is_a = jr < HP;
+      partner = is_a ? (S - jr) : (S + pp);                 // b_k = S - k (k = jr)   |   a_k = S + k (k = R - jr)
+      partner += (partner < 0) ? R : 0;
+      partner -= (partner >= R) ? R : 0;
+    }
   }
+  float dj = 0.0f; float2 piv = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    dj = (i == jr) ? a[i].x : dj;
+    piv = (i == pp) ? a[i] : piv;
+  }
+  if (is_a) piv.y = -piv.y;                                  // column p holds A[q][p] = conj(A[p][q])
   const float dpart = __shfl_sync(FULL, dj, partner, M);
-  Rot mine = make_rotation(is_p ? dj : dpart, is_p ? dpart : dj, piv);
+  Rot mine = make_rotation(is_a ? dj : dpart, is_a ? dpart : dj, piv);
   if (frozen) { mine.c = 1.0f; mine.sx = 0.0f; mine.sy = 0.0f; }
-  // the M/2 rotations of this step, as lane p_k computed them
+  // the M/2 rotations of this step, as the a-role lane of each pair computed them
   float ck[HP], sxk[HP], syk[HP];
 #pragma unroll
   for (int k = 0; k < HP; ++k) {
-    const int p = pair_p<M>(S, k);
-    ck[k] = __shfl_sync(FULL, mine.c, p, M);
-    sxk[k] = __shfl_sync(FULL, mine.sx, p, M);
-    syk[k] = __shfl_sync(FULL, mine.sy, p, M);
+    int ak = S + k; ak -= (ak >= R) ? R : 0;
+    ck[k] = __shfl_sync(FULL, mine.c, ak, M);
+    sxk[k] = __shfl_sync(FULL, mine.sx, ak, M);
+    syk[k] = __shfl_sync(FULL, mine.sy, ak, M);
   }
-  float cm = 1.0f, wx = 0.0f, wy = 0.0f;
-#pragma unroll
-  for (int k = 0; k < HP; ++k) {
-    const int p = pair_p<M>(S, k), q = pair_q<M>(S, k);
-    if (j == p) { cm = ck[k]; wx = -sxk[k]; wy = syk[k]; }   // col_p' = c col_p - conj(sigma) col_q
-    if (j == q) { cm = ck[k]; wx = sxk[k]; wy = syk[k]; }    // col_q' = sigma col_p + c col_q
-  }
+  // my pair's rotation: col_p' = c col_p - conj(sigma) col_q ; col_q' = sigma col_p + c col_q
+  const int asrc = is_a ? j : partner;
+  const float cm = __shfl_sync(FULL, mine.c, asrc, M);
+  const float sxm = __shfl_sync(FULL, mine.sx, asrc, M), wy = __shfl_sync(FULL, mine.sy, asrc, M);
+  const float wx = is_a ? -sxm : sxm;
   // columns: A <- A J, V <- V J
 #pragma unroll
   for (int i = 0; i < M; ++i) {
@@ -86,20 +98,26 @@ __device__ __forceinline__ void jacobi_step(float2 (&a)[M], float2 (&v)[M], cons
   // rows: A <- J^H A on my column: row_p' = c row_p - sigma row_q ; row_q' = conj(sigma) row_p + c row_q
 #pragma unroll
   for (int k = 0; k < HP; ++k) {
-    const int p = pair_p<M>(S, k), q = pair_q<M>(S, k);
-    const float2 x = a[p], y = a[q];
+    constexpr int dummy = 0; (void)dummy;
+    const int ip = k, iq = R - k;                            // register positions of rows a_k, b_k (pair 0: S and R)
+    const float2 x = a[ip], y = a[iq];
     const float c = ck[k], sx = sxk[k], sy = syk[k];
-    a[p] = make_float2(fmaf(-sx, y.x, fmaf(sy, y.y, c * x.x)), fmaf(-sx, y.y, fmaf(-sy, y.x, c * x.y)));
-    a[q] = make_float2(fmaf(sx, x.x, fmaf(sy, x.y, c * y.x)), fmaf(sx, x.y, fmaf(-sy, x.x, c * y.y)));
+    a[ip] = make_float2(fmaf(-sx, y.x, fmaf(sy, y.y, c * x.x)), fmaf(-sx, y.y, fmaf(-sy, y.x, c * x.y)));
+    a[iq] = make_float2(fmaf(sx, x.x, fmaf(sy, x.y, c * y.x)), fmaf(sx, x.y, fmaf(-sy, x.x, c * y.y)));
+  }
+  // next step's frame: ring rows move down one position
+  if constexpr (R > 1) {
+    const float2 t0 = a[0];
+#pragma unroll
+    for (int i = 0; i + 1 < R; ++i) a[i] = a[i + 1];
+    a[R - 1] = t0;
   }
 }
 
-template <int M, int S>
+template <int M>
 __device__ __forceinline__ void jacobi_sweep(float2 (&a)[M], float2 (&v)[M], const int j, const bool frozen) {
-  if constexpr (S < M - 1) {
-    jacobi_step<M, S>(a, v, j, frozen);
-    jacobi_sweep<M, S + 1>(a, v, j, frozen);
-  }
+#pragma unroll 1
+  for (int S = 0; S < M - 1; ++S) jacobi_step<M>(a, v, j, S, frozen);
 }
 
 
@@ -144,7 +162,7 @@ __device__ __forceinline__ void jacobi_group_solve(float2* S, const int j, const
     // (quadratic convergence) cannot improve the subspace any further
     done = done || (off <= dg * (1.5e-14f * M * M));
     if (__all_sync(FULL, done)) break;
-    jacobi_sweep<M, 0>(a, v, j, done);
+    jacobi_sweep<M>(a, v, j, done);
   }
 
   // undo the accumulated norm drift of the fast rotations: unit eigenvectors
