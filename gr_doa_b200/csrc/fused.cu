@@ -195,7 +195,9 @@ int launch_chain_fused(const float2* in, long long frame_stride, long long chan_
   // 2 stages x 4 tile buffers or 3 x 3: 1.59-1.64 ms (equal within box-to-box noise; 2 x 4 needs 201 KB of shared memory);
   // 4+12: 1.88-1.99, 5+11: 1.91, 6+10: 1.85, 7+9: 1.84, 9+7: 1.94, 10+6: 2.03, 12+4: 2.39; 4+16 (setmaxnreg re-allocation,
   // 96-register launch): 1.97.  Warp-stall sampling (profiles/) shows why: with 4 producers the consumers idle at the FULL
-  // barrier 41 % of the time while each producer warp, alone on its scheduler, issues at 0.25 IPC.
+  // barrier 41 % of the time while each producer warp, alone on its scheduler, issues at 0.25 IPC.  At 8+8 the tile barriers
+  // still hold 12 % of the warp samples, but that is slack, not lost throughput: a variant with pairwise hand-off (producer w
+  // feeds consumer w through a private ring of 4-frame slots and mbarriers, no CTA-wide barrier) measured the same 1.67 ms.
 #define WS_ARGS in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st
   // dev knobs (tools/ws_exp.py): ws_split = producers * 100 + consumers, ws_stages = cp.async ring depth, ws_nbuf = tile buffers
   switch ((dev_option("ws_split", 808) * 10 + dev_option("ws_stages", 2)) * 10 + dev_option("ws_nbuf", 4)) {
