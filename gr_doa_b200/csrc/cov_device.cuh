@@ -18,6 +18,14 @@ __device__ __forceinline__ float2 ldg_stream2(const float2* p) {
   return v;
 }
 
+// cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass registers; src_bytes = 0 zero-fills.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(NKEEP) : "memory"); }
+
 // Reduce-scatter over the warp: on entry every lane holds CNT partial sums a[0..CNT); on exit lane L holds the
 // full sums of max(1, CNT/32) consecutive elements starting at rs_base<CNT>(L).
 template <int CNT, int OFF>

@@ -26,13 +26,6 @@ constexpr int BAR_FULL = 1;                     // named barriers: FULL b = 1 + 
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(NKEEP) : "memory"); }
-
 template <int M, int KL, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF>
 __global__ void __launch_bounds__((WS_P + WS_C) * 32, 1)
 chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
