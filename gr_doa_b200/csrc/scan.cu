@@ -41,6 +41,36 @@ scan_peaks_kernel(const float2* __restrict__ u, const float2* __restrict__ G, co
                              out_val + (size_t)f * K, out_loc + (size_t)f * K, out_bin ? out_bin + (size_t)f * K : nullptr);
 }
 
+// Generic M (large arrays), few frames: one warp per frame leaves the machine empty and walks P x (M-1) Horner steps
+// serially (1.34 ms for 256 frames of 64 elements x 16,384 bins).  Here a CTA owns a frame: all its warps evaluate the
+// coarse spectrum into shared memory (same arithmetic, same z values: same bits), then one warp runs the unchanged
+// walker / merge / refinement on that table.
+constexpr int SCAN_WIDE_THREADS = 256;
+
+template <int KL>
+__global__ void __launch_bounds__(SCAN_WIDE_THREADS)
+scan_peaks_wide_kernel(const float2* __restrict__ u, const float2* __restrict__ G, const float2* __restrict__ z,
+                       const float* __restrict__ zpair, const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int M,
+                       int P, int nframes, int K, float* __restrict__ out_val, float* __restrict__ out_loc,
+                       int* __restrict__ out_bin) {
+  extern __shared__ float4 smem4[];
+  float* qtab = reinterpret_cast<float*>(smem4);                           // [P]
+  float2* us = reinterpret_cast<float2*>(qtab + ((P + 3) & ~3));            // [M]
+  const ZTab zt = ztab_view(zpair, P);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
+    __syncthreads();                                                       // the previous frame's walker is done with qtab / us
+    for (int l = threadIdx.x; l < M; l += SCAN_WIDE_THREADS) us[l] = u[(size_t)f * M + l];
+    __syncthreads();
+    const float2 dummy[1] = {make_float2(0.f, 0.f)};
+    for (int i = threadIdx.x; i < P; i += SCAN_WIDE_THREADS) qtab[i] = q_coarse<0>(dummy, us, M, z[i]);
+    __syncthreads();
+    if (warp == 0)
+      scan_frame_peaks<0, KL>(u + (size_t)f * M, G + (size_t)f * M * M, zt, us, Vtab, xaxis, M, P, K, lane, out_val + (size_t)f * K,
+                              out_loc + (size_t)f * K, out_bin ? out_bin + (size_t)f * K : nullptr, qtab);
+  }
+}
+
 // K == 1 uses index_max (find_local_max_impl.h:53-56): the global arg-max, no local-peak logic.
 template <int MT>
 __global__ void __launch_bounds__(SCAN_WARPS * 32)
@@ -207,6 +237,23 @@ int launch_peaks_mt(const float2* u, const float2* G, const ScanTables& tb, int 
     scan_argmax_kernel<MT><<<blocks, SCAN_WARPS * 32, smem, st>>>(u, G, tb.z, tb.V, tb.xaxis, M, P, nframes, out_val,
                                                                   out_loc, out_bin);
     return 1;
+  }
+  if constexpr (MT == 0) {
+    const size_t wsmem = (size_t)((P + 3) & ~3) * sizeof(float) + (size_t)M * sizeof(float2);
+    if (wsmem <= 200 * 1024 && nframes <= 8 * sm_count() && dev_option("scan_wide", 1)) {
+      const int per = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / wsmem));
+      const int grid = min(nframes, sm_count() * per);
+      if (K <= 4) {
+        auto kern = scan_peaks_wide_kernel<4>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+        kern<<<grid, SCAN_WIDE_THREADS, wsmem, st>>>(u, G, tb.z, tb.zpair, tb.V, tb.xaxis, M, P, nframes, K, out_val, out_loc, out_bin);
+      } else {
+        auto kern = scan_peaks_wide_kernel<16>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+        kern<<<grid, SCAN_WIDE_THREADS, wsmem, st>>>(u, G, tb.z, tb.zpair, tb.V, tb.xaxis, M, P, nframes, K, out_val, out_loc, out_bin);
+      }
+      return 1;
+    }
   }
   const size_t us_bytes = (MT > 0 ? 0 : (size_t)SCAN_WARPS * M) * sizeof(float2);
   const bool z_in_smem = ztab_floats(P) * sizeof(float) + us_bytes <= 200 * 1024;

@@ -234,7 +234,7 @@ __device__ __forceinline__ void scan_frame_peaks(const float2* __restrict__ uf, 
                                                  float2* us, const float2* __restrict__ Vtab,
                                                  const float* __restrict__ xaxis, int M, int P, int K, int lane,
                                                  float* __restrict__ o_val, float* __restrict__ o_loc,
-                                                 int* __restrict__ o_bin) {
+                                                 int* __restrict__ o_bin, const float* qtab = nullptr) {
   const int S = zt.S;
   const float* za = zt.za; const float* zb = zt.zb;
   const int s0 = lane * S, s1 = min(P, s0 + S);
@@ -247,7 +247,11 @@ __device__ __forceinline__ void scan_frame_peaks(const float2* __restrict__ uf, 
     for (int l = lane; l < M; l += 32) us[l] = uf[l];
     __syncwarp();
   }
-  auto q_at = [&](int bin) -> float { return q_coarse<MT>(uc, us, M, zt.at(bin)); };
+  // qtab (generic M only): the frame's coarse spectrum already evaluated by the whole CTA (scan_peaks_wide_kernel)
+  auto q_at = [&](int bin) -> float {
+    if constexpr (MT == 0) { if (qtab != nullptr) return qtab[bin]; }
+    return q_coarse<MT>(uc, us, M, zt.at(bin));
+  };
   Walker<KL, false> w; w.init(s0 > 0);
   bool exact = (MT == 0);        // generic M: always the exact walker
   if constexpr (MT > 0) {

@@ -319,3 +319,22 @@ def test_capacity_and_empty_batches(doa):
     assert v.shape == (0, 1)
     with pytest.raises(_lib.DoaCudaError):
         ch.run_host(np.zeros((5, 4, 64), np.complex64))
+
+
+@pytest.mark.parametrize("B,N,T,P,K", [(40, 128, 4, 1024, 3), (9, 130, 5, 333, 12), (20, 256, 2, 2000, 2)])
+def test_large_array_scan_cta_per_frame_equals_warp_per_frame(doa, torch_cuda, B, N, T, P, K):
+    """Generic-M scan with few frames: the CTA-per-frame kernel (coarse spectrum evaluated by all warps into shared memory,
+    then the unchanged walker) returns the same bits as the warp-per-frame kernel.  M = 64 with even N so that the covariance
+    in front of it is the deterministic tensor-core kernel."""
+    from gr_doa_b200 import synth, _lib
+    L = _lib.lib()
+    x, _ = synth.frames_torch(B, 64, N, [30.0 + 120.0 * i / max(1, T - 1) for i in range(T)], jitter_deg=2.0, device="cuda", chunk=16)
+    ch = doa.DoaChain(64, N, 0, 0, 0.5, T, P, K, max_frames=B)
+    got = {}
+    try:
+        for wide in (0, 1):
+            L.doa_cuda_dev_set(b"scan_wide", wide)
+            got[wide] = [t.clone() for t in ch.run_device(x)]
+    finally:
+        L.doa_cuda_dev_set(b"scan_wide", 1)
+    assert all(torch_cuda.equal(a.view(torch_cuda.int32), b.view(torch_cuda.int32)) for a, b in zip(got[0], got[1]))
