@@ -48,7 +48,7 @@ jacobi_group_kernel(const float2* __restrict__ R, int T, int nframes, float2* __
 // ---- generic M: one CTA per matrix ----------------------------------------------------------------------------
 // A and V live in shared memory with an odd leading dimension (M+1 float2) so that both the column phase (threads walk a
 // column) and the row phase (threads walk a row, stride LD) are bank-conflict free.
-constexpr int JB_THREADS = 256;
+constexpr int JB_THREADS = 512;
 
 __global__ void __launch_bounds__(JB_THREADS)
 jacobi_block_kernel(const float2* __restrict__ R, int M, int T, int nframes, float2* __restrict__ G,
