@@ -287,7 +287,7 @@ def main():
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": kern_bytes, "launch_ms": kern_ms,
                          "stage_ms": ({"fused_chain": kern_ms} if fused else {"cov": cov_ms, "eig": eig_ms, "scan_peaks": scan_ms}),
                          "chain": {"algorithmic_bytes_per_frame": ALG_BYTES_CHAIN(w), "achieved": chain_gbs,
-                                   "frac": chain_gbs / peak, "note": "whole step (3 kernels + gather) per GPU against the same HBM peak"}},
+                                   "frac": chain_gbs / peak, "note": "whole step (chain kernel" + ("" if fused else "s") + (" + peak gather" if world > 1 else "") + ") per GPU against the same HBM peak"}},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches,
