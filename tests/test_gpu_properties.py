@@ -95,13 +95,14 @@ def test_fused_kernel_equals_three_kernel_path(full):
 
 
 def test_fused_kernel_configurations_are_bit_identical(full):
-    """Producer/consumer split, cp.async ring depth, tile-buffer count, register re-allocation (setmaxnreg) and the SMs left
-    to NCCL only change the schedule: every configuration returns the same bits, at tile-boundary sizes and at full size."""
+    """Producer/consumer split, cp.async ring depth, tile-buffer count, register re-allocation (setmaxnreg), bulk (TMA) instead of
+    per-lane ring fills and the SMs left to NCCL only change the schedule: every configuration returns the same bits, at tile-boundary sizes and at full size."""
     from gr_doa_b200 import _lib
     torch = full["torch"]
     L = _lib.lib()
 
-    def select(split, stages, nbuf, reserve=0):
+    def select(split, stages, nbuf, reserve=0, tma=0):
+        L.doa_cuda_dev_set(b"ws_tma", tma)
         L.doa_cuda_dev_set(b"ws_split", split); L.doa_cuda_dev_set(b"ws_stages", stages); L.doa_cuda_dev_set(b"ws_nbuf", nbuf)
         L.doa_cuda_dev_set(b"chain_sms_reserve", reserve)
 
@@ -112,7 +113,7 @@ def test_fused_kernel_configurations_are_bit_identical(full):
             ref = [t.clone() for t in full["ch"].run_device(x)]
             assert full["ch"].launches() == 1
             for cfg in ((412, 3, 2), (412, 5, 2), (416, 4, 2), (610, 3, 2), (812, 3, 2), (808, 3, 2), (808, 3, 3), (808, 2, 5), (808, 2, 4, 2),
-                        (808, 2, 4, 147)):
+                        (808, 2, 4, 147), (808, 2, 4, 0, 1)):
                 select(*cfg)
                 got = full["ch"].run_device(x)
                 assert full["ch"].launches() == 1, cfg
