@@ -49,9 +49,9 @@ template <int M, int KL, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF, bool TM
 __global__ void __launch_bounds__((WS_P + WS_C) * 32, 1)
 chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
                 int avg_method, float scale, float bscale, int T, int max_sweeps, const float* __restrict__ zpair,
-                const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int P, int K,
+                const float2* __restrict__ zplain, const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int P, int K,
                 float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin) {
-  static_assert(M == 8, "tile geometry below assumes 8 lanes per matrix");
+  static_assert(M == 8 || M == 4, "instantiated for 8 and 4 lanes per matrix");
   constexpr int TILE = WS_C * 32 / M;          // frames per tile: every consumer warp owns 32/M of them
   constexpr int BAR_EMPTY = BAR_FULL + WS_NBUF; // WS_NBUF tile buffers between producers and consumers
   static_assert(BAR_EMPTY + WS_NBUF <= 16, "named barriers");
@@ -181,8 +181,12 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
       if (t + WS_NBUF < ntiles) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NTHREADS); }
       for (int i = cw * (32 / M); i < min(nt, (cw + 1) * (32 / M)); ++i) {
         const long long f = lo + (long long)t * TILE + i;
-        scan_frame_peaks<M, KL, true>(us + i * M, Gs + i * MM, zt, nullptr, Vtab, xaxis, M, P, K, lane, out_val + f * K,
-                                            out_loc + f * K, out_bin ? out_bin + f * K : nullptr);
+        if (K == 1)   // index_max: the global arg-max (find_local_max_impl.h:53-56), not a local-peak search
+          scan_frame_argmax<M>(us + i * M, Gs + i * MM, zplain, nullptr, Vtab, xaxis, M, P, lane, out_val + f, out_loc + f,
+                               out_bin ? out_bin + f : nullptr);
+        else
+          scan_frame_peaks<M, KL, true>(us + i * M, Gs + i * MM, zt, nullptr, Vtab, xaxis, M, P, K, lane, out_val + f * K,
+                                        out_loc + f * K, out_bin ? out_bin + f * K : nullptr);
       }
       __syncwarp();
     }
@@ -206,7 +210,7 @@ int launch_ws_cfg2(const float2* in, long long fs, long long cs, int N, int nfra
   sms = std::max(1, sms - std::max(0, dev_option("chain_sms_reserve", 0)));
   const int grid = std::max(1, std::min(sms, (nframes + TILE - 1) / TILE));
   const float scale = (float)(1.0 / N), bscale = (float)(0.5 / N);
-  kern<<<grid, (WS_P + WS_C) * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.V, tb.xaxis, tb.P,
+  kern<<<grid, (WS_P + WS_C) * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.z, tb.V, tb.xaxis, tb.P,
                                                K, out_val, out_loc, out_bin);
   return 1;
 }
@@ -227,13 +231,13 @@ int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nfram
 }  // namespace
 
 // Returns 1 if the fused kernel was launched, 0 if this shape is not covered (caller falls back to the three kernels).
-// Covered: M = 8, 2 <= K <= 4, 16-byte aligned even strides, scan table + tiles + rings within one SM's shared memory
-// (P <= ~6000).  M = 4 is HBM-dominated (covariance is 80 % of the step) and measured faster unfused.
+// Covered: M = 8 or 4, K <= 4 (K = 1: global arg-max), 16-byte aligned even strides, scan table + tiles + rings within one
+// SM's shared memory (P <= ~6000).  M = 4 (cfg1 / cfg2 shapes): 3.15 / 3.33 ms unfused -> 2.47 / 2.40 ms, ~7 TB/s of input.
 int launch_chain_fused(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
                        int avg_method, int T, const ScanTables& tb, int K, float* out_val, float* out_loc, int* out_bin,
                        cudaStream_t st) {
-  if (nframes <= 0 || M != 8) return 0;
-  if (K < 2 || K > 4) return 0;                       // K == 1 is the arg-max kernel, K > 4 the wide candidate lists
+  if (nframes <= 0 || (M != 8 && M != 4)) return 0;
+  if (K < 1 || K > 4) return 0;                       // K > 4: the wide candidate lists
   const bool vec2 = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
                     ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
   if (!vec2) return 0;
@@ -245,6 +249,19 @@ int launch_chain_fused(const float2* in, long long frame_stride, long long chan_
   // still hold 12 % of the warp samples, but that is slack, not lost throughput: a variant with pairwise hand-off (producer w
   // feeds consumer w through a private ring of 4-frame slots and mbarriers, no CTA-wide barrier) measured the same 1.67 ms.
 #define WS_ARGS in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st
+  if (M == 4) {   // covariance-dominated (80 % of the step): the consumers only have to hide 0.1 + 0.7 ms under 2.6 ms of streaming
+    switch (dev_option("ws4", 5)) {
+      case 0: return 0;
+      case 1: return launch_ws_cfg<4, 8, 8, 2, 4>(WS_ARGS);
+      case 2: return launch_ws_cfg<4, 12, 4, 2, 4>(WS_ARGS);
+      case 3: return launch_ws_cfg<4, 10, 6, 3, 4>(WS_ARGS);
+      case 4: return launch_ws_cfg<4, 8, 8, 4, 4>(WS_ARGS);
+      case 5: return launch_ws_cfg<4, 8, 8, 6, 4>(WS_ARGS);
+      case 6: return launch_ws_cfg<4, 10, 6, 4, 4>(WS_ARGS);
+      case 7: return launch_ws_cfg<4, 12, 4, 4, 4>(WS_ARGS);
+      default: return launch_ws_cfg<4, 6, 10, 4, 4>(WS_ARGS);
+    }
+  }
   // dev knobs (tools/ws_exp.py): ws_split = producers * 100 + consumers, ws_stages = cp.async ring depth, ws_nbuf = tile buffers
   switch ((dev_option("ws_split", 808) * 10 + dev_option("ws_stages", 2)) * 10 + dev_option("ws_nbuf", 4)) {
     case 41232: return launch_ws_cfg<8, 4, 12, 3, 2>(WS_ARGS);      // the first fused configuration (1.91 ms)

@@ -81,43 +81,9 @@ scan_argmax_kernel(const float2* __restrict__ u, const float2* __restrict__ G, c
   float2* us_all = smem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2* us = us_all + warp * (MT > 0 ? 0 : M);
-  for (int f = blockIdx.x * SCAN_WARPS + warp; f < nframes; f += gridDim.x * SCAN_WARPS) {
-    float2 uc[MT > 0 ? MT : 1];
-    const float2* uf = u + (size_t)f * M;
-    if constexpr (MT > 0) {
-#pragma unroll
-      for (int l = 0; l < MT; ++l) uc[l] = uf[l];
-    } else {
-      __syncwarp();
-      for (int l = lane; l < M; l += 32) us[l] = uf[l];
-      __syncwarp();
-    }
-    float bv = INFINITY; int bi = 0x7fffffff;
-    for (int i = lane; i < P; i += 32) {   // interleaved bins: coalesced table reads, no ordering needed
-      const float q = q_coarse<MT>(uc, us, M, ztab[i]);
-      if (q < bv) { bv = q; bi = i; }
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      const float ov = __shfl_xor_sync(FULL, bv, o); const int oi = __shfl_xor_sync(FULL, bi, o);
-      if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    // refine around the coarse arg-min with the reference arithmetic
-    const float2* Gf = G + (size_t)f * M * M;
-    const int b = bi + lane - REFINE_W;
-    float qf = INFINITY; int qb = 0x7fffffff;
-    if (lane <= 2 * REFINE_W && b >= 0 && b < P) { qf = q_faithful(Gf, Vtab + (size_t)b * M, M); qb = b; }
-#pragma unroll
-    for (int o = 4; o >= 1; o >>= 1) {
-      const float ov = __shfl_xor_sync(FULL, qf, o); const int ob = __shfl_xor_sync(FULL, qb, o);
-      if (ov < qf || (ov == qf && ob < qb)) { qf = ov; qb = ob; }
-    }
-    if (lane == 0) {
-      out_val[f] = db_value(qf, qf);
-      out_loc[f] = xaxis[qb];
-      if (out_bin) out_bin[f] = qb;
-    }
-  }
+  for (int f = blockIdx.x * SCAN_WARPS + warp; f < nframes; f += gridDim.x * SCAN_WARPS)
+    scan_frame_argmax<MT>(u + (size_t)f * M, G + (size_t)f * M * M, ztab, us, Vtab, xaxis, M, P, lane, out_val + f, out_loc + f,
+                          out_bin ? out_bin + f : nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

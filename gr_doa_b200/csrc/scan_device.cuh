@@ -225,6 +225,49 @@ __device__ __forceinline__ ZTab ztab_fill(float* smem, const float* __restrict__
   return ztab_view(smem, P);
 }
 
+// K == 1 (index_max, find_local_max_impl.h:53-56): the global arg-max of one frame by one warp -- coarse arg-min of Q over
+// interleaved bins, refinement around it with the reference arithmetic, outputs.  ztab: plain z[P] table (global memory).
+template <int MT>
+__device__ __forceinline__ void scan_frame_argmax(const float2* __restrict__ uf, const float2* __restrict__ Gf,
+                                                  const float2* __restrict__ ztab, float2* us, const float2* __restrict__ Vtab,
+                                                  const float* __restrict__ xaxis, int M, int P, int lane,
+                                                  float* __restrict__ o_val, float* __restrict__ o_loc, int* __restrict__ o_bin) {
+  constexpr unsigned FULLM = 0xffffffffu;
+  float2 uc[MT > 0 ? MT : 1];
+  if constexpr (MT > 0) {
+#pragma unroll
+    for (int l = 0; l < MT; ++l) uc[l] = uf[l];
+  } else {
+    __syncwarp();
+    for (int l = lane; l < M; l += 32) us[l] = uf[l];
+    __syncwarp();
+  }
+  float bv = INFINITY; int bi = 0x7fffffff;
+  for (int i = lane; i < P; i += 32) {   // interleaved bins: coalesced table reads, no ordering needed
+    const float q = q_coarse<MT>(uc, us, M, ztab[i]);
+    if (q < bv) { bv = q; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const float ov = __shfl_xor_sync(FULLM, bv, o); const int oi = __shfl_xor_sync(FULLM, bi, o);
+    if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  // refine around the coarse arg-min with the reference arithmetic
+  const int b = bi + lane - REFINE_W;
+  float qf = INFINITY; int qb = 0x7fffffff;
+  if (lane <= 2 * REFINE_W && b >= 0 && b < P) { qf = q_faithful(Gf, Vtab + (size_t)b * M, M); qb = b; }
+#pragma unroll
+  for (int o = 4; o >= 1; o >>= 1) {
+    const float ov = __shfl_xor_sync(FULLM, qf, o); const int ob = __shfl_xor_sync(FULLM, qb, o);
+    if (ov < qf || (ov == qf && ob < qb)) { qf = ov; qb = ob; }
+  }
+  if (lane == 0) {
+    o_val[0] = db_value(qf, qf);
+    o_loc[0] = xaxis[qb];
+    if (o_bin) o_bin[0] = qb;
+  }
+}
+
 // One frame by one warp: coarse scan over all P bins, peak picking, refinement with the reference arithmetic, dB
 // conversion, sorted outputs.  uf: the frame's M diagonal sums, Gf: its M x M projector (global or shared memory);
 // us: M float2 of per-warp shared scratch (runtime-M path only); o_*: this frame's K output slots.

@@ -338,3 +338,26 @@ def test_large_array_scan_cta_per_frame_equals_warp_per_frame(doa, torch_cuda, B
     finally:
         L.doa_cuda_dev_set(b"scan_wide", 1)
     assert all(torch_cuda.equal(a.view(torch_cuda.int32), b.view(torch_cuda.int32)) for a, b in zip(got[0], got[1]))
+
+
+@pytest.mark.parametrize("M,T,P,K,avg", [(4, 1, 2048, 1, 0), (4, 2, 1024, 2, 1), (8, 3, 4096, 1, 0), (4, 1, 512, 3, 0)])
+def test_fused_chain_equals_three_kernels_other_shapes(doa, torch_cuda, M, T, P, K, avg):
+    """The fused warp-specialised kernel also covers 4-element arrays and K = 1 (index_max: global arg-max): same bits as the
+    three stage kernels at sizes around the tile boundaries."""
+    from gr_doa_b200 import synth, _lib
+    L = _lib.lib()
+    N = 512
+    thetas = [60.0] if T == 1 else list(np.linspace(50.0, 130.0, T))
+    x, _ = synth.frames_torch(5000, M, N, thetas, jitter_deg=2.0, device="cuda", chunk=1024)
+    ch = doa.DoaChain(M, N, 0, avg, 0.5, T, P, K, max_frames=5000)
+    try:
+        for nb in (1, 63, 64, 65, 1000, 5000):
+            L.doa_cuda_dev_set(b"fused", 0)
+            a = [t.clone() for t in ch.run_device(x[:nb])]
+            assert ch.launches() == 3
+            L.doa_cuda_dev_set(b"fused", 1)
+            b = ch.run_device(x[:nb])
+            assert ch.launches() == 1
+            assert all(torch_cuda.equal(p, q) for p, q in zip(a, b)), nb
+    finally:
+        L.doa_cuda_dev_set(b"fused", 1)
