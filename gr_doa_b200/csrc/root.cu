@@ -10,6 +10,11 @@
 // ~1e-2 degree on these nearly-double roots, float64 roots agree with a float64 LAPACK twin to ~1e-6 degree (tests).
 // The working matrix lives in a frame-interleaved global scratch (element (i,j) of frame f at ((i*n+j)*stride + f)),
 // so neighbouring threads touch neighbouring addresses; it stays L1/L2 resident for the sizes gr-doa uses (n = 6..30).
+// Fast path (n <= 30): the same roots from an Aberth-Ehrlich simultaneous iteration on the monic polynomial itself --
+// coefficients and iterates of a frame live in a thread-interleaved shared-memory array, no global scratch, 8-14 iterations
+// of n Horner evaluations + n(n-1) reciprocal differences in float64 -- 80x faster than the QR at n = 14 (the QR is
+// latency-bound on its 205 MB scratch).  A frame whose iteration has not settled to a 1e-10 relative step in 40 rounds
+// (about 1 in 10^4 at seven sources) is redone by the QR kernel.
 // Root selection repeats the reference's float arithmetic (:122-141): dist = 1 - |z| in float, strictly inside only,
 // the T closest to the circle, angle = 180*acos(arg(z)/(2 pi d))/pi with the double math of :136, ascending sort.
 #include "doa_internal.h"
@@ -37,6 +42,36 @@ __device__ __forceinline__ cplx csqrt_(cplx a) {
   return {re, im};
 }
 
+// Root selection with the float arithmetic of the reference (:122-141): dist = 1 - |z| in float, strictly inside only, the T
+// closest to the circle, angle = 180*acos(arg(z)/(2 pi d))/pi with the double math of :136, ascending sort (NaNs last).
+template <class GetRoot>
+__device__ __forceinline__ void emit_angles(GetRoot root, int n, int T, bool failed, float norm_spacing, float* of) {
+  unsigned long long used0 = 0ull, used1 = 0ull;
+  const double two_pi_d = 2.0 * 3.14159265358979323846 * (double)norm_spacing;
+  for (int ii = 0; ii < T; ++ii) {
+    float best = INFINITY; int bk = -1; float bre = 0.f, bim = 0.f;
+    if (!failed) {
+      for (int k = 0; k < n; ++k) {
+        const bool used = (k < 64) ? ((used0 >> k) & 1ull) : ((used1 >> (k - 64)) & 1ull);
+        if (used) continue;
+        const cplx z = root(k);
+        const float re = (float)z.x, im = (float)z.y;
+        const float dist = 1.0f - hypotf(re, im);
+        if (dist > 0.0f && dist < best) { best = dist; bk = k; bre = re; bim = im; }
+      }
+    }
+    float aoa = __int_as_float(0x7fc00000);   // NaN: fewer than T roots strictly inside (reference undefined there)
+    if (bk >= 0) {
+      if (bk < 64) used0 |= 1ull << bk; else used1 |= 1ull << (bk - 64);
+      aoa = (float)(180.0 * acos((double)atan2f(bim, bre) / two_pi_d) / 3.14159265358979323846);
+    }
+    // insertion into the ascending prefix of[0..ii) (NaNs stay at the end)
+    int pos = ii;
+    while (pos > 0 && !(of[pos - 1] <= aoa) && !(aoa != aoa)) { of[pos] = of[pos - 1]; --pos; }
+    of[pos] = aoa;
+  }
+}
+
 struct Hmat {
   double2* base; long long stride; int n;
   __device__ __forceinline__ cplx get(int i, int j) const { const double2 v = base[((long long)i * n + j) * stride]; return {v.x, v.y}; }
@@ -45,9 +80,10 @@ struct Hmat {
 
 __global__ void __launch_bounds__(128)
 rootmusic_kernel(const float2* __restrict__ u, int M, int T, float norm_spacing, int nframes, double2* __restrict__ scratch,
-                 long long stride, float* __restrict__ out) {
+                 long long stride, float* __restrict__ out, int only_flagged) {
   const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= nframes) return;
+  if (only_flagged && out[f * T] != -INFINITY) return;      // the Aberth kernel marks the frames it gave up on
   const int n = 2 * M - 2;
   Hmat H{scratch + f, stride, n};
   const float2* uf = u + f * M;
@@ -121,32 +157,72 @@ rootmusic_kernel(const float2* __restrict__ u, int M, int T, float norm_spacing,
     for (int i = l; i <= hi; ++i) H.set(i, i, cadd(H.get(i, i), sigma));
   }
 
-  // root selection, float arithmetic of the reference
-  float* of = out + f * T;
-  unsigned long long used0 = 0ull, used1 = 0ull;
-  const double two_pi_d = 2.0 * 3.14159265358979323846 * (double)norm_spacing;
-  for (int ii = 0; ii < T; ++ii) {
-    float best = INFINITY; int bk = -1; float bre = 0.f, bim = 0.f;
-    if (!failed) {
-      for (int k = 0; k < n; ++k) {
-        const bool used = (k < 64) ? ((used0 >> k) & 1ull) : ((used1 >> (k - 64)) & 1ull);
-        if (used) continue;
-        const cplx z = H.get(k, k);
-        const float re = (float)z.x, im = (float)z.y;
-        const float dist = 1.0f - hypotf(re, im);
-        if (dist > 0.0f && dist < best) { best = dist; bk = k; bre = re; bim = im; }
-      }
+  emit_angles([&](int k) { return H.get(k, k); }, n, T, failed, norm_spacing, out + f * T);
+}
+
+// ---- Aberth-Ehrlich -------------------------------------------------------------------------------------------------------
+constexpr int AB_THREADS = 128;
+constexpr int AB_MAX_N = 30;
+constexpr int AB_MAX_ITER = 40;
+
+__global__ void __launch_bounds__(AB_THREADS)
+rootmusic_aberth_kernel(const float2* __restrict__ u, int M, int T, float norm_spacing, int nframes, float* __restrict__ out) {
+  extern __shared__ double2 ab_s[];                  // [2n][AB_THREADS]: coefficients c_0..c_{n-1} (monic), then the iterates
+  const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nframes) return;
+  const int n = 2 * M - 2;
+  double2* c = ab_s + threadIdx.x;                   // c[k] at c[k * AB_THREADS]
+  double2* z = ab_s + (size_t)n * AB_THREADS + threadIdx.x;
+  const float2* uf = u + f * M;
+  {
+    const cplx an = {(double)uf[M - 1].x, (double)uf[M - 1].y};     // a_n = u_{M-1}
+    const cplx inv = cdiv({1.0, 0.0}, an);
+    for (int k = 0; k < n; ++k) {
+      const int l = k - (M - 1);
+      cplx a;
+      if (l >= 0) a = {(double)uf[l].x, l == 0 ? 0.0 : (double)uf[l].y};
+      else a = {(double)uf[-l].x, -(double)uf[-l].y};
+      const cplx ck = cmul(inv, a);
+      c[k * AB_THREADS] = make_double2(ck.x, ck.y);
     }
-    float aoa = __int_as_float(0x7fc00000);   // NaN: fewer than T roots strictly inside (reference undefined there)
-    if (bk >= 0) {
-      if (bk < 64) used0 |= 1ull << bk; else used1 |= 1ull << (bk - 64);
-      aoa = (float)(180.0 * acos((double)atan2f(bim, bre) / two_pi_d) / 3.14159265358979323846);
+    // the roots come in pairs (z, 1/conj(z)) around the unit circle: start on two circles, irrational angle offset
+    for (int k = 0; k < n; ++k) {
+      double sn, cs;
+      sincos(6.283185307179586 * (double)k / (double)n + 0.35, &sn, &cs);
+      const double r = (k & 1) ? 1.15 : 0.85;
+      z[k * AB_THREADS] = make_double2(r * cs, r * sn);
     }
-    // insertion into the ascending prefix of[0..ii) (NaNs stay at the end)
-    int pos = ii;
-    while (pos > 0 && !(of[pos - 1] <= aoa) && !(aoa != aoa)) { of[pos] = of[pos - 1]; --pos; }
-    of[pos] = aoa;
   }
+  bool settled = false;
+  for (int it = 0; it < AB_MAX_ITER && !settled; ++it) {
+    settled = true;
+    for (int i = 0; i < n; ++i) {
+      const double2 zi2 = z[i * AB_THREADS];
+      const cplx zi = {zi2.x, zi2.y};
+      cplx p = {1.0, 0.0}, dp = {0.0, 0.0};
+      for (int k = n - 1; k >= 0; --k) {              // Horner: p(z_i), p'(z_i)
+        dp = cadd(cmul(dp, zi), p);
+        const double2 ck = c[k * AB_THREADS];
+        p = cadd(cmul(p, zi), {ck.x, ck.y});
+      }
+      cplx sum = {0.0, 0.0};
+      for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        const double2 zj = z[j * AB_THREADS];
+        const double dx = zi.x - zj.x, dy = zi.y - zj.y;
+        const double inv = 1.0 / (dx * dx + dy * dy);
+        sum.x += dx * inv; sum.y -= dy * inv;         // 1 / (z_i - z_j)
+      }
+      const cplx r = cdiv(p, dp);
+      const cplx w = cdiv(r, csub({1.0, 0.0}, cmul(r, sum)));
+      const cplx zn = csub(zi, w);
+      z[i * AB_THREADS] = make_double2(zn.x, zn.y);   // Gauss-Seidel: later roots of this round already see it
+      const double w2 = w.x * w.x + w.y * w.y, z2 = zn.x * zn.x + zn.y * zn.y;
+      if (!(w2 <= 1e-20 * fmax(1.0, z2))) settled = false;     // also catches NaN
+    }
+  }
+  if (!settled) { out[f * T] = -INFINITY; return; }  // left to the QR kernel
+  emit_angles([&](int k) { const double2 v = z[k * AB_THREADS]; return cplx{v.x, v.y}; }, n, T, false, norm_spacing, out + f * T);
 }
 
 }  // namespace
@@ -157,7 +233,15 @@ int launch_rootmusic_scratch(const float2* u, int M, int T, float norm_spacing, 
   if (nframes <= 0) return 0;
   const int threads = 128;
   const int blocks = (nframes + threads - 1) / threads;
-  rootmusic_kernel<<<blocks, threads, 0, st>>>(u, M, T, norm_spacing, nframes, scratch, stride, out);
+  const int n = 2 * M - 2;
+  int only_flagged = 0;
+  if (n >= 1 && n <= AB_MAX_N && dev_option("root_aberth", 1)) {
+    const size_t smem = (size_t)2 * n * AB_THREADS * sizeof(double2);
+    cudaFuncSetAttribute(rootmusic_aberth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    rootmusic_aberth_kernel<<<(nframes + AB_THREADS - 1) / AB_THREADS, AB_THREADS, smem, st>>>(u, M, T, norm_spacing, nframes, out);
+    only_flagged = 1;
+  }
+  rootmusic_kernel<<<blocks, threads, 0, st>>>(u, M, T, norm_spacing, nframes, scratch, stride, out, only_flagged);
   return 1;
 }
 

@@ -361,3 +361,31 @@ def test_fused_chain_equals_three_kernels_other_shapes(doa, torch_cuda, M, T, P,
             assert all(torch_cuda.equal(p, q) for p, q in zip(a, b)), nb
     finally:
         L.doa_cuda_dev_set(b"fused", 1)
+
+
+@pytest.mark.parametrize("M,T,snr", [(8, 3, 10.0), (4, 2, 10.0), (8, 7, 20.0), (16, 5, 10.0), (2, 1, 10.0)])
+def test_rootmusic_aberth_path_agrees_with_the_qr_path(doa, oracle, torch_cuda, M, T, snr):
+    """Root-MUSIC roots from the Aberth-Ehrlich iteration (registers / shared memory) and from the Hessenberg QR (global
+    scratch, also the fallback of frames the iteration gives up on) select the same angles, and both meet the tolerance
+    against the float64 LAPACK twin away from the unit circle."""
+    from gr_doa_b200 import synth, _lib
+    L = _lib.lib()
+    B = 3000
+    thetas = [75.0] if T == 1 else list(np.linspace(30.0, 150.0, T))
+    fr, _ = synth.frames_numpy(B, M, 256, thetas, snr_db=snr, seed=31 * M + T)
+    R = oracle.autocorrelate_frames(fr, 0, nthreads=oracle.max_threads())
+    rm = doa.rootMUSIC_linear_array(0.5, T, M, max_frames=B)
+    got = {}
+    try:
+        for ab in (0, 1):
+            L.doa_cuda_dev_set(b"root_aberth", ab)
+            got[ab] = rm.work(R)
+    finally:
+        L.doa_cuda_dev_set(b"root_aberth", 1)
+    a64, d64 = oracle.rootmusic_f64(R, 0.5, T, M, return_dist=True, nthreads=oracle.max_threads())
+    for ab in (0, 1):
+        worst, near_circle = parity.root_angles_ok(got[ab], a64, d64)
+        assert worst <= parity.ROOT_DEG, (ab, worst)
+    away = np.nanmin(d64, axis=1) >= parity.ROOT_NEAR_CIRCLE
+    both = np.isfinite(got[0]) & np.isfinite(got[1]) & away[:, None]
+    assert np.abs(got[0] - got[1])[both].max() <= parity.ROOT_DEG
