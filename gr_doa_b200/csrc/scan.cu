@@ -139,39 +139,71 @@ find_local_max_kernel(const float* __restrict__ in, int len, int nframes, int K,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   float* vs = fsm + (size_t)warp * 32 * SP;
   const int s0 = lane * S, s1 = min(len, s0 + S);
-  for (int f = blockIdx.x * nwarps + warp; f < nframes; f += gridDim.x * nwarps) {
-    const float* src = in + (size_t)f * len;
-    __syncwarp();
-    for (int i = lane; i < len; i += 32) vs[(i / S) * SP + (i % S)] = src[i];
-    __syncwarp();
-    const float* vl = vs + lane * SP;
-    auto v_at = [&](int b) -> float { return vs[(b / S) * SP + (b % S)]; };
-    Walker<KL, true> w; w.init(s0 > 0);
-    float bv = -INFINITY; int bi = 0x7fffffff;      // first occurrence of the maximum (index_max semantics)
-    if (s0 < s1) {
-      float prev; int k = 0;
-      if (s0 > 0) prev = vs[(lane - 1) * SP + (S - 1)];
-      else { prev = vl[0]; if (prev > bv) { bv = prev; bi = 0; } k = 1; }
-      for (; k < s1 - s0; ++k) {
-        const float c = vl[k];
-        if (c > bv) { bv = c; bi = s0 + k; }
-        if (K > 1) w.step(prev, c, s0 + k, v_at);
-        prev = c;
-      }
+  const bool pow2 = (S & (S - 1)) == 0;
+  const int lgS = 31 - __clz(S);
+  // first occurrence of the maximum over interleaved bins (index_max semantics: NaNs never win, ties -> lowest index)
+  auto arg_max = [&](const float* src) -> int {
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    constexpr int U = 8;
+    int i = lane;
+    for (; i + (U - 1) * 32 < len; i += U * 32) {
+      float t[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) t[j] = __ldg(src + i + j * 32);
+#pragma unroll
+      for (int j = 0; j < U; ++j) if (t[j] > bv) { bv = t[j]; bi = i + j * 32; }
     }
+    for (; i < len; i += 32) { const float c = src[i]; if (c > bv) { bv = c; bi = i; } }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       const float ov = __shfl_xor_sync(FULL, bv, o); const int oi = __shfl_xor_sync(FULL, bi, o);
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
-    if (bi == 0x7fffffff) bi = 0;   // nothing compared greater than -inf (all -inf / NaN): index 0 like index_max
+    return (bi == 0x7fffffff) ? 0 : bi;   // nothing compared greater than -inf (all -inf / NaN): index 0 like index_max
+  };
+  for (int f = blockIdx.x * nwarps + warp; f < nframes; f += gridDim.x * nwarps) {
+    const float* src = in + (size_t)f * len;
     int bin; float val;
-    if (K == 1) {   // index_max (find_local_max_impl.h:53-56)
-      bin = bi; val = src[bi];
+    if (K == 1) {   // index_max (find_local_max_impl.h:53-56): a pure stream, nothing is staged
+      bin = arg_max(src); val = src[bin];
     } else {
+      __syncwarp();
+      {   // coalesced in, padded per-lane segments out.  Sixteen independent loads are issued before the first store: with
+          // one load in flight per warp the kernel streamed at 1.1 TB/s (12 warps per SM x 128 B against ~1 us of latency)
+        constexpr int U = 16;
+        int i = lane;
+        for (; i + (U - 1) * 32 < len; i += U * 32) {
+          float t[U];
+#pragma unroll
+          for (int j = 0; j < U; ++j) t[j] = __ldg(src + i + j * 32);
+          if (pow2) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) { const int e = i + j * 32; vs[(e >> lgS) * SP + (e & (S - 1))] = t[j]; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < U; ++j) { const int e = i + j * 32; vs[(e / S) * SP + (e % S)] = t[j]; }
+          }
+        }
+        for (; i < len; i += 32) vs[(i / S) * SP + (i % S)] = src[i];
+      }
+      __syncwarp();
+      const float* vl = vs + lane * SP;
+      auto v_at = [&](int b) -> float { return vs[(b / S) * SP + (b % S)]; };
+      Walker<KL, true> w; w.init(s0 > 0);
+      if (s0 < s1) {
+        float prev; int k = 0;
+        if (s0 > 0) prev = vs[(lane - 1) * SP + (S - 1)];
+        else { prev = vl[0]; k = 1; }
+        for (; k < s1 - s0; ++k) {
+          const float c = vl[k];
+          w.step(prev, c, s0 + k, v_at);
+          prev = c;
+        }
+      }
       Merged m = stitch_and_merge<KL, true>(w, K, lane, v_at);
       const int nref = min(K, m.nvalid);
-      const int pad = (m.nvalid == 0) ? bi : m.best_ord;     // fill-in rule incl. the reference's index bug (:145-163)
+      // fill-in rule incl. the reference's index bug (:145-163); the arg-max is only needed when there is no peak at all
+      const int pad = (m.nvalid == 0) ? arg_max(src) : m.best_ord;
       bin = (lane < nref) ? m.bin : pad;
       val = (lane < K) ? src[min(bin, len - 1)] : 0.f;
     }
@@ -292,6 +324,11 @@ int launch_find_local_max(const float* in, int len, int nframes, int K, const fl
                           float* out_loc, int* out_bin, cudaStream_t st) {
   if (nframes <= 0) return 0;
   if (K < 1 || K > 16 || len < 1) return DOA_CUDA_EINVAL;
+  if (K == 1) {   // index_max streams the vectors: no staging area, full occupancy
+    auto kern = find_local_max_kernel<4>;
+    kern<<<min((nframes + FLM_WARPS - 1) / FLM_WARPS, sm_count() * 16), FLM_WARPS * 32, 0, st>>>(in, len, nframes, K, xaxis, out_val, out_loc, out_bin);
+    return 1;
+  }
   const int S = (len + 31) / 32, SP = S | 1;
   int warps = FLM_WARPS;                                        // fewer warps per CTA for very long vectors
   while (warps > 1 && (size_t)warps * 32 * SP * sizeof(float) > 200 * 1024) warps >>= 1;
