@@ -124,6 +124,50 @@ scan_spectrum_kernel(const float2* __restrict__ u, const float2* __restrict__ zt
   }
 }
 
+// Compile-time M, P floats of shared memory per warp: ONE Horner pass, over pairs of bins (i, i + 32) in fma.rn.f32x2 (the
+// same operations as the scalar form), lg2(1/Q) parked in shared memory, then the dB pass.
+// 10 log10(y / ymax) = 10 log10(2) (lg2 y - lg2 ymax): MUFU reciprocal and log2 (abs. error ~1e-6 dB against the 1e-3 dB
+// tolerance) instead of two IEEE divisions and log10f, which were 45 of the two-pass kernel's ~120 instructions per bin.
+template <int MT>
+__global__ void __launch_bounds__(128)
+scan_spectrum_smem_kernel(const float2* __restrict__ u, const float2* __restrict__ ztab, int P, int nframes, float* __restrict__ out) {
+  extern __shared__ float ysm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float* ys = ysm + (size_t)warp * P;
+  for (int f = blockIdx.x * nwarps + warp; f < nframes; f += gridDim.x * nwarps) {
+    float2 uc[MT];
+    const float2* uf = u + (size_t)f * MT;
+#pragma unroll
+    for (int l = 0; l < MT; ++l) uc[l] = uf[l];
+    f32x2 ux2[MT], muy2[MT];
+#pragma unroll
+    for (int l = 0; l < MT; ++l) { ux2[l] = pk2(uc[l].x, uc[l].x); muy2[l] = pk2(-uc[l].y, -uc[l].y); }
+    const f32x2 u0_2 = pk2(uc[0].x, uc[0].x), two2 = pk2(2.0f, 2.0f);
+    // max over bins of y = 1/Q taken on y itself so that negative/zero Q behave like the reference's float max
+    float ymax = -INFINITY;
+    __syncwarp();
+    int i = lane;
+    for (; i + 32 < P; i += 64) {
+      const float2 za = ztab[i], zb = ztab[i + 32];
+      float qa, qb;
+      upk2(q_coarse_pair<MT>(ux2, muy2, u0_2, two2, pk2(za.x, zb.x), pk2(za.y, zb.y), pk2(-za.y, -zb.y)), qa, qb);
+      const float ya = __fdividef(1.0f, qa), yb = __fdividef(1.0f, qb);
+      ys[i] = __log2f(ya); ys[i + 32] = __log2f(yb);
+      ymax = fmaxf(ymax, fmaxf(ya, yb));
+    }
+    if (i < P) {
+      const float y = __fdividef(1.0f, q_coarse<MT>(uc, nullptr, MT, ztab[i]));
+      ys[i] = __log2f(y);
+      ymax = fmaxf(ymax, y);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, o));
+    const float lmax = __log2f(ymax);
+    float* of = out + (size_t)f * P;
+    for (int k = lane; k < P; k += 32) of[k] = 3.0102999566f * (ys[k] - lmax);   // own entries: no barrier needed
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Standalone find_local_max on arbitrary float vectors: one warp per vector, vector staged in shared memory
 // (coalesced in, padded per-lane segments out), then the same walker in MAXIMA mode.  Bit-exact by construction:
@@ -272,6 +316,19 @@ int launch_peaks_mt(const float2* u, const float2* G, const ScanTables& tb, int 
 
 template <int MT>
 int launch_spectrum_mt(const float2* u, const ScanTables& tb, int nframes, float* out, cudaStream_t st) {
+  if constexpr (MT > 0) {
+    const size_t per_warp = (size_t)tb.P * sizeof(float);
+    if (per_warp <= 48 * 1024 && dev_option("spectrum_smem", 1)) {
+      const int warps = (int)std::max<size_t>(1, std::min<size_t>(4, (64 * 1024) / per_warp));
+      const size_t smem = per_warp * warps;
+      auto kern = scan_spectrum_smem_kernel<MT>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
+      const int blocks = min((nframes + warps - 1) / warps, sm_count() * per_sm);
+      kern<<<blocks, warps * 32, smem, st>>>(u, tb.z, tb.P, nframes, out);
+      return 1;
+    }
+  }
   const size_t smem = (MT > 0 ? 0 : (size_t)SCAN_WARPS * tb.M) * sizeof(float2);
   const int blocks = min((nframes + SCAN_WARPS - 1) / SCAN_WARPS, sm_count() * 8);
   scan_spectrum_kernel<MT><<<blocks, SCAN_WARPS * 32, smem, st>>>(u, tb.z, tb.M, tb.P, nframes, out);
