@@ -49,7 +49,15 @@ def lib():
 
 
 def max_threads() -> int:
-    return int(lib().oracle_max_threads())
+    """Host threads this process may use: the CPU affinity mask (torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    would otherwise turn the 'all host cores' baseline into a single-thread one); every entry point takes the count
+    explicitly (`num_threads` clause), so the environment variable does not cap it."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(int(lib().oracle_max_threads()), n)
 
 
 def _p(a, t=C.c_float):
