@@ -43,6 +43,19 @@ class _Block:
     def launches(self):
         return int(self._L.doa_cuda_last_launch_count(self._h))
 
+    def set_channel_gains(self, gains):
+        """Per-channel complex gains applied in front of the covariance as R' = D R D^H (autocorrelate and chain handles):
+        what an antenna_correction / phase_correct_hier block upstream would have multiplied into the samples
+        (lib/antenna_correction_impl.cc:90-96).  None removes them."""
+        import numpy as np
+        if gains is None:
+            check(self._L.doa_cuda_set_channel_gains(self._h, None), self._h)
+            return
+        g = np.ascontiguousarray(np.asarray(gains, dtype=np.complex64).reshape(-1))
+        if g.size != self.inputs:
+            raise ValueError(f"expected {self.inputs} gains, got {g.size}")
+        check(self._L.doa_cuda_set_channel_gains(self._h, g.ctypes.data), self._h)
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._L.doa_cuda_destroy(self._h)
@@ -53,6 +66,29 @@ class _Block:
             self.close()
         except Exception:
             pass
+
+
+class antenna_correction:
+    """gr::doa::antenna_correction (lib/antenna_correction_impl.cc:47-99) as a gain source: reads the reference's config file
+    ("gain phase" per channel, g_k = (1/gain_k) e^{-j phase_k}, same validation) into `.gains`; hand them to
+    autocorrelate.set_channel_gains / DoaChain.set_channel_gains instead of running a multiply pass over the samples.
+    `work(streams)` is the reference block's own work() for completeness (host, numpy)."""
+
+    def __init__(self, num_inputs, config_filename):
+        import numpy as np
+        self.num_inputs = num_inputs
+        L = _lib.lib()
+        g = np.empty(num_inputs, np.complex64)
+        rc = L.doa_cuda_antenna_gains_from_file(str(config_filename).encode(), num_inputs, g.ctypes.data)
+        if rc != 0:
+            txt = L.doa_cuda_last_error(None)
+            raise _lib.DoaCudaError(rc, txt.decode() if txt else "")
+        self.gains = g
+
+    def work(self, streams):
+        import numpy as np
+        x = np.asarray(streams, dtype=np.complex64)
+        return (self.gains[:, None] * x).astype(np.complex64)
 
 
 class autocorrelate(_Block):

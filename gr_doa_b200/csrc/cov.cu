@@ -32,7 +32,7 @@ int num_sms() {
 template <int M, int VEC, int G>
 __global__ void __launch_bounds__(COV_WARPS * 32, (G == 1 && M >= 8) ? 2 : 1)
 cov_small_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
-                 float2* __restrict__ out, float scale, float bscale, int avg_method) {
+                 float2* __restrict__ out, float scale, float bscale, int avg_method, const float2* __restrict__ gains) {
   constexpr int CNT = M * M;
   __shared__ float red_s[COV_WARPS][CNT];
   const unsigned lane = threadIdx.x & 31u;
@@ -40,7 +40,7 @@ cov_small_kernel(const float2* __restrict__ in, long long frame_stride, long lon
   float* red = red_s[warp];
   for (int f = blockIdx.x * COV_WARPS + warp; f < nframes; f += gridDim.x * COV_WARPS) {
     cov_warp_frame<M, VEC, G>(in + (long long)f * frame_stride, chan_stride, N, lane, red);
-    cov_warp_emit<M>(red, scale, bscale, avg_method, lane, out + (long long)f * CNT);
+    cov_warp_emit<M>(red, scale, bscale, avg_method, lane, out + (long long)f * CNT, gains);
   }
 }
 
@@ -77,7 +77,7 @@ __device__ __forceinline__ void cov16_load(const float2* __restrict__ base, long
 template <int VEC>
 __global__ void __launch_bounds__(C16_FRAMES * 64, 1)
 cov16_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
-             float2* __restrict__ out, float scale, float bscale, int avg_method) {
+             float2* __restrict__ out, float scale, float bscale, int avg_method, const float2* __restrict__ gains) {
   constexpr int M = 16, CNT = 256, NP16 = 120;
   __shared__ float red_s[C16_FRAMES][CNT];
   const unsigned lane = threadIdx.x & 31u;
@@ -154,9 +154,9 @@ cov16_kernel(const float2* __restrict__ in, long long frame_stride, long long ch
     float2* o = out + (long long)f * CNT;
     for (int e = role * 32 + (int)lane; e < CNT; e += 64) {
       const int r = e % M, c = e / M;
-      float2 v = folded_entry<M>(red, r, c, scale);
+      float2 v = apply_gain(folded_entry<M>(red, r, c, scale), gains, r, c);
       if (avg_method == 1) {   // 0.5*R + (0.5/N) * J conj(R) J, lib/autocorrelate_impl.cc:108
-        const float2 w = folded_entry<M>(red, M - 1 - r, M - 1 - c, scale);
+        const float2 w = apply_gain(folded_entry<M>(red, M - 1 - r, M - 1 - c, scale), gains, M - 1 - r, M - 1 - c);
         v.x = __fadd_rn(__fmul_rn(0.5f, v.x), __fmul_rn(bscale, w.x));
         v.y = __fadd_rn(__fmul_rn(0.5f, v.y), __fmul_rn(bscale, -w.y));
       }
@@ -175,7 +175,7 @@ constexpr int C16_STAGES = 5;
 template <int ROLE>
 __device__ __forceinline__ void cov16_ring_role(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N,
                                                 int nframes, float2* __restrict__ out, float scale, float bscale, int avg_method,
-                                                float4* ring, float* red, int slot, int lane) {
+                                                const float2* __restrict__ gains, float4* ring, float* red, int slot, int lane) {
   constexpr int M = 16, CNT = 256, NP16 = 120;
   const int bar_id = 1 + slot;
   const int nslots = gridDim.x * C16_FRAMES;
@@ -295,9 +295,9 @@ __device__ __forceinline__ void cov16_ring_role(const float2* __restrict__ in, l
       float2* o = out + (long long)f * CNT;
       for (int e = ROLE * 32 + lane; e < CNT; e += 64) {
         const int r = e % M, cc = e / M;
-        float2 v = folded_entry<M>(red, r, cc, scale);
+        float2 v = apply_gain(folded_entry<M>(red, r, cc, scale), gains, r, cc);
         if (avg_method == 1) {   // 0.5*R + (0.5/N) * J conj(R) J, lib/autocorrelate_impl.cc:108
-          const float2 wv = folded_entry<M>(red, M - 1 - r, M - 1 - cc, scale);
+          const float2 wv = apply_gain(folded_entry<M>(red, M - 1 - r, M - 1 - cc, scale), gains, M - 1 - r, M - 1 - cc);
           v.x = __fadd_rn(__fmul_rn(0.5f, v.x), __fmul_rn(bscale, wv.x));
           v.y = __fadd_rn(__fmul_rn(0.5f, v.y), __fmul_rn(bscale, -wv.y));
         }
@@ -311,29 +311,29 @@ __device__ __forceinline__ void cov16_ring_role(const float2* __restrict__ in, l
 
 __global__ void __launch_bounds__(C16_FRAMES * 64, 1)
 cov16_ring_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
-                  float2* __restrict__ out, float scale, float bscale, int avg_method) {
+                  float2* __restrict__ out, float scale, float bscale, int avg_method, const float2* __restrict__ gains) {
   extern __shared__ float4 ring_s[];                 // [C16_FRAMES][C16_STAGES][16][32]
   __shared__ float red_s[C16_FRAMES][256];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5, slot = warp >> 1;
   float4* ring = ring_s + (size_t)slot * C16_STAGES * 16 * 32;
-  if ((warp & 1) == 0) cov16_ring_role<0>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, ring, red_s[slot], slot, lane);
-  else cov16_ring_role<1>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, ring, red_s[slot], slot, lane);
+  if ((warp & 1) == 0) cov16_ring_role<0>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, gains, ring, red_s[slot], slot, lane);
+  else cov16_ring_role<1>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, gains, ring, red_s[slot], slot, lane);
 }
 
 int launch_cov16(const float2* in, long long fs, long long cs, int N, int nframes, float2* out, float scale, float bscale,
-                 int avg, cudaStream_t st) {
+                 int avg, cudaStream_t st, const float2* gains) {
   const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
   const int blocks = (nframes + C16_FRAMES - 1) / C16_FRAMES;
   if (vec2 && dev_option("cov16_ring", 1)) {
     const size_t smem = (size_t)C16_FRAMES * C16_STAGES * 16 * 32 * sizeof(float4);
     cudaFuncSetAttribute(cov16_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = std::min(blocks, num_sms());
-    cov16_ring_kernel<<<grid, C16_FRAMES * 64, smem, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg);
+    cov16_ring_kernel<<<grid, C16_FRAMES * 64, smem, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
     return 1;
   }
-  if (vec2) cov16_kernel<2><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg);
-  else cov16_kernel<1><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg);
+  if (vec2) cov16_kernel<2><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+  else cov16_kernel<1><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
   return 1;
 }
 
@@ -343,7 +343,7 @@ constexpr int CT_TT = 64;   // time samples per shared-memory tile
 
 __global__ void __launch_bounds__(CT_THREADS)
 cov_tiled_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int M, int N,
-                 int nframes, float2* __restrict__ out, float scale, float bscale, int avg_method) {
+                 int nframes, float2* __restrict__ out, float scale, float bscale, int avg_method, const float2* __restrict__ gains) {
   extern __shared__ float2 smem[];
   const int nb = (M + 3) / 4;           // 4-row blocks
   const int Mp = nb * 4;                // padded channel count
@@ -421,9 +421,9 @@ cov_tiled_kernel(const float2* __restrict__ in, long long frame_stride, long lon
     float2* o = out + (long long)f * M * M;
     for (int e = tid; e < M * M; e += CT_THREADS) {
       const int r = e % M, c = e / M;
-      float2 v = entry(r, c);
+      float2 v = apply_gain(entry(r, c), gains, r, c);
       if (avg_method == 1) {
-        const float2 w = entry(M - 1 - r, M - 1 - c);
+        const float2 w = apply_gain(entry(M - 1 - r, M - 1 - c), gains, M - 1 - r, M - 1 - c);
         v.x = __fadd_rn(__fmul_rn(0.5f, v.x), __fmul_rn(bscale, w.x));
         v.y = __fadd_rn(__fmul_rn(0.5f, v.y), __fmul_rn(bscale, -w.y));
       }
@@ -435,15 +435,15 @@ cov_tiled_kernel(const float2* __restrict__ in, long long frame_stride, long lon
 
 template <int M>
 int launch_small(const float2* in, long long fs, long long cs, int N, int nframes, float2* out, float scale,
-                 float bscale, int avg, cudaStream_t st) {
+                 float bscale, int avg, cudaStream_t st, const float2* gains) {
   const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
   const int blocks = (nframes + COV_WARPS - 1) / COV_WARPS;
   const int variant = dev_option("cov_groups", 1);   // 1: 128 regs, 2 CTAs/SM (6.4 TB/s at M=8); 2: 167 regs, 1 CTA/SM (5.9 TB/s)
   if (vec2) {
-    if (variant == 1) cov_small_kernel<M, 2, 1><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg);
-    else cov_small_kernel<M, 2, 2><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg);
+    if (variant == 1) cov_small_kernel<M, 2, 1><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+    else cov_small_kernel<M, 2, 2><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
   } else {
-    cov_small_kernel<M, 1, 2><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg);
+    cov_small_kernel<M, 1, 2><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
   }
   return 1;
 }
@@ -451,20 +451,20 @@ int launch_small(const float2* in, long long fs, long long cs, int N, int nframe
 }  // namespace
 
 int launch_covariance(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
-                      int avg_method, float2* out, cudaStream_t st) {
+                      int avg_method, float2* out, cudaStream_t st, const float2* gains) {
   if (nframes <= 0) return 0;
   const float scale = (float)(1.0 / N);     // (1.0/d_snapshot_size) narrowed to float, lib/autocorrelate_impl.cc:106
   const float bscale = (float)(0.5 / N);    // (0.5/d_snapshot_size), :108
   switch (M) {
-    case 2: return launch_small<2>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st);
-    case 4: return launch_small<4>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st);
-    case 8: return launch_small<8>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st);
-    case 16: return launch_cov16(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st);
+    case 2: return launch_small<2>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
+    case 4: return launch_small<4>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
+    case 8: return launch_small<8>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
+    case 16: return launch_cov16(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
     default: break;
   }
   if (M > 64) return DOA_CUDA_EINVAL;
   if (M == 64 && dev_option("herk_tc", 1)) {   // tensor-core complex HERK (3xTF32) when alignment allows
-    const int r = launch_covariance_tc(in, frame_stride, chan_stride, M, N, nframes, avg_method, out, st);
+    const int r = launch_covariance_tc(in, frame_stride, chan_stride, M, N, nframes, avg_method, out, st, gains);
     if (r != 0) return r;
   }
   const int Mp = ((M + 3) / 4) * 4;
@@ -472,7 +472,7 @@ int launch_covariance(const float2* in, long long frame_stride, long long chan_s
   cudaFuncSetAttribute(cov_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   const int blocks = min(nframes, num_sms() * 4);
   cov_tiled_kernel<<<blocks, CT_THREADS, smem, st>>>(in, frame_stride, chan_stride, M, N, nframes, out, scale, bscale,
-                                                     avg_method);
+                                                     avg_method, gains);
   return 1;
 }
 

@@ -158,18 +158,29 @@ __device__ __forceinline__ void cov_warp_frame(const float2* __restrict__ base, 
   acc.fold(lane, red);
 }
 
-// Scale, optional forward-backward term, Hermitian expansion; writes the M x M column-major matrix to `o`
-// (global or shared).
+// Per-channel complex gains applied in front of the covariance (the reference's antenna_correction block,
+// lib/antenna_correction_impl.cc:65-70,90-96, and phase_correct_hier: x'_k = g_k x_k) folded into the emit stage:
+// R'(r, c) = g_r conj(g_c) R(r, c).  g = nullptr: none.  The diagonal factor |g_r|^2 is kept exactly real.
+__device__ __forceinline__ float2 apply_gain(float2 v, const float2* __restrict__ g, int r, int c) {
+  if (g == nullptr) return v;
+  const float2 a = g[r], b = g[c];
+  const float gx = __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+  const float gy = (r == c) ? 0.0f : __fsub_rn(__fmul_rn(a.y, b.x), __fmul_rn(a.x, b.y));
+  return make_float2(__fsub_rn(__fmul_rn(v.x, gx), __fmul_rn(v.y, gy)), __fadd_rn(__fmul_rn(v.x, gy), __fmul_rn(v.y, gx)));
+}
+
+// Scale, optional channel gains, optional forward-backward term, Hermitian expansion; writes the M x M column-major matrix
+// to `o` (global or shared).
 template <int M>
 __device__ __forceinline__ void cov_warp_emit(const float* red, float scale, float bscale, int avg_method, unsigned lane,
-                                              float2* o) {
+                                              float2* o, const float2* __restrict__ gains = nullptr) {
   constexpr int CNT = M * M;
   for (int e = (int)lane; e < CNT; e += 32) {
     const int r = e % M, c = e / M;
-    float2 v = folded_entry<M>(red, r, c, scale);
+    float2 v = apply_gain(folded_entry<M>(red, r, c, scale), gains, r, c);
     if (avg_method == 1) {
       // 0.5*R + (0.5/N) * J conj(R) J : (J conj(R) J)(r,c) = conj(R(M-1-r, M-1-c))   lib/autocorrelate_impl.cc:108
-      const float2 w = folded_entry<M>(red, M - 1 - r, M - 1 - c, scale);
+      const float2 w = apply_gain(folded_entry<M>(red, M - 1 - r, M - 1 - c, scale), gains, M - 1 - r, M - 1 - c);
       v.x = __fadd_rn(__fmul_rn(0.5f, v.x), __fmul_rn(bscale, w.x));
       v.y = __fadd_rn(__fmul_rn(0.5f, v.y), __fmul_rn(bscale, -w.y));
     }

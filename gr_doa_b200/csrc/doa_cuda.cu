@@ -6,6 +6,8 @@
 #include "doa_internal.h"
 
 #include <cmath>
+#include <complex>
+#include <fstream>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -82,6 +84,7 @@ struct doa_cuda_handle {
   Lane lane[2];
   int nlanes = 1;
   float2* d_z = nullptr; float2* d_V = nullptr; float* d_x = nullptr; float* d_zpair = nullptr;
+  float2* d_gains = nullptr;     // per-channel complex gains folded into the covariance (null: none)
   std::vector<float> h_loc, h_theta, h_x; std::vector<float2> h_V, h_z;
   std::string err;
   int launches = 0;
@@ -115,7 +118,7 @@ extern "C" void doa_cuda_destroy(doa_cuda_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (int i = 0; i < 2; ++i) free_lane(h->lane[i]);
-  cudaFree(h->d_z); cudaFree(h->d_V); cudaFree(h->d_x); cudaFree(h->d_zpair);
+  cudaFree(h->d_z); cudaFree(h->d_V); cudaFree(h->d_x); cudaFree(h->d_zpair); cudaFree(h->d_gains);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
 }
@@ -185,6 +188,37 @@ int doa_cuda_dev_set(const char* key, int value) {
   return 0;
 }
 
+// ---- channel gains ------------------------------------------------------------------------------------------------
+int doa_cuda_set_channel_gains(doa_cuda_handle* h, const float* gains) {
+  if (!h || (h->kind != K_AUTOCORR && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
+  CK(h, cudaSetDevice(h->device));
+  // runs already queued on the handle's streams may still read the old gains
+  for (int i = 0; i < h->nlanes; ++i) if (h->lane[i].stream) CK(h, cudaStreamSynchronize(h->lane[i].stream));
+  if (gains == nullptr) { CK(h, cudaDeviceSynchronize()); cudaFree(h->d_gains); h->d_gains = nullptr; return DOA_CUDA_OK; }
+  for (int k = 0; k < 2 * h->M; ++k)
+    if (!std::isfinite(gains[k])) return fail(h, DOA_CUDA_EINVAL, "channel gains must be finite");
+  if (!h->d_gains && cudaMalloc(&h->d_gains, (size_t)h->M * sizeof(float2)) != cudaSuccess) return fail(h, DOA_CUDA_ENOMEM, "cudaMalloc(gains)");
+  CK(h, cudaMemcpy(h->d_gains, gains, (size_t)h->M * sizeof(float2), cudaMemcpyHostToDevice));
+  return DOA_CUDA_OK;
+}
+
+// lib/antenna_correction_impl.cc:54-74, statement by statement: float gain/phase pairs, g = gr_complex(1.0/Gain, 0) * exp(gr_complex(0, -Phase))
+int doa_cuda_antenna_gains_from_file(const char* config_filename, int num_ant_ele, float* gains_out) {
+  if (!config_filename || !gains_out || num_ant_ele < 1) return fail(nullptr, DOA_CUDA_EINVAL, "bad arguments");
+  std::ifstream infile(config_filename);
+  if (!infile.good()) return fail(nullptr, DOA_CUDA_EINVAL, "Cannot find configuration file.");
+  float GainEst, PhaseEst;
+  int i = 0;
+  while (infile >> GainEst >> PhaseEst) {
+    if (i >= num_ant_ele) return fail(nullptr, DOA_CUDA_EINVAL, "Configuration file has too many inputs.");
+    const std::complex<float> g = std::complex<float>((float)(1.0 / GainEst), 0.0f) * std::exp(std::complex<float>(0.0f, -PhaseEst));
+    gains_out[2 * i] = g.real(); gains_out[2 * i + 1] = g.imag();
+    ++i;
+  }
+  if (i != num_ant_ele) return fail(nullptr, DOA_CUDA_EINVAL, "Configuration file does not have enough inputs.");
+  return DOA_CUDA_OK;
+}
+
 // ---- autocorrelate ------------------------------------------------------------------------------------------------
 int doa_cuda_autocorrelate_create(doa_cuda_handle** out, int inputs, int snapshot_size, int overlap_size, int avg_method,
                                   int device, int max_frames) {
@@ -215,7 +249,7 @@ int doa_cuda_autocorrelate_run_device(doa_cuda_handle* h, const void* in_dev, lo
   if (nframes < 0) return fail(h, DOA_CUDA_EINVAL, "nframes < 0");
   CK(h, cudaSetDevice(h->device));
   int n = launch_covariance((const float2*)in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, (float2*)out_dev,
-                            (cudaStream_t)cuda_stream);
+                            (cudaStream_t)cuda_stream, h->d_gains);
   if (n < 0) return fail(h, n, "covariance launch rejected");
   h->launches = n;
   CK(h, cudaGetLastError());
@@ -469,7 +503,7 @@ static int chain_on_lane(doa_cuda_handle* h, Lane& l, const float2* in_dev, long
     // one persistent kernel for the whole chain when the shape allows it; stage events collapse to (0, 0, total)
     if (prof) { CK(h, cudaEventRecord(ev[1], st)); CK(h, cudaEventRecord(ev[2], st)); }
     int f = launch_chain_fused(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, h->T, tables_of(h), h->K, val,
-                               loc, bin, st);
+                               loc, bin, st, h->d_gains);
     if (f < 0) return fail(h, f, "fused chain launch rejected");
     if (f > 0) {
       if (prof) CK(h, cudaEventRecord(ev[3], st));
@@ -478,7 +512,7 @@ static int chain_on_lane(doa_cuda_handle* h, Lane& l, const float2* in_dev, long
       return DOA_CUDA_OK;
     }
   }
-  int a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st);
+  int a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains);
   if (a < 0) return fail(h, a, "covariance launch rejected");
   if (prof) CK(h, cudaEventRecord(ev[1], st));
   int b = launch_noise_subspace(l.R, h->M, h->T, nframes, l.G, l.u, nullptr, st);

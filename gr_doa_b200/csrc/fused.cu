@@ -50,7 +50,8 @@ __global__ void __launch_bounds__((WS_P + WS_C) * 32, 1)
 chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
                 int avg_method, float scale, float bscale, int T, int max_sweeps, const float* __restrict__ zpair,
                 const float2* __restrict__ zplain, const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int P, int K,
-                float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin) {
+                float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin,
+                const float2* __restrict__ gains) {
   static_assert(M == 8 || M == 4, "instantiated for 8 and 4 lanes per matrix");
   constexpr int TILE = WS_C * 32 / M;          // frames per tile: every consumer warp owns 32/M of them
   constexpr int BAR_EMPTY = BAR_FULL + WS_NBUF; // WS_NBUF tile buffers between producers and consumers
@@ -153,7 +154,7 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
           ++cur_tile; opened = false;
         }
         if (!opened) { if (cur_tile >= WS_NBUF) bar_sync(BAR_EMPTY + (cur_tile % WS_NBUF), NTHREADS); opened = true; }
-        cov_warp_emit<M>(red + w * MM, scale, bscale, avg_method, (unsigned)lane, Rbuf + ((size_t)(tf % WS_NBUF) * TILE + slot) * MM);
+        cov_warp_emit<M>(red + w * MM, scale, bscale, avg_method, (unsigned)lane, Rbuf + ((size_t)(tf % WS_NBUF) * TILE + slot) * MM, gains);
         acc.clear();
       }
     }
@@ -195,7 +196,7 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
 
 template <int M, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF, bool TMA>
 int launch_ws_cfg2(const float2* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
-                  int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st) {
+                  int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st, const float2* gains) {
   constexpr int TILE = WS_C * 32 / M;
   const size_t smem = ((ztab_floats(tb.P) + 3) & ~(size_t)3) * sizeof(float) + ((size_t)(WS_NBUF + 1) * TILE * M * M + (size_t)TILE * M) * sizeof(float2) +
                       (size_t)WS_P * M * M * sizeof(float) + (size_t)WS_P * WS_STAGES * M * 32 * sizeof(float4);
@@ -211,21 +212,21 @@ int launch_ws_cfg2(const float2* in, long long fs, long long cs, int N, int nfra
   const int grid = std::max(1, std::min(sms, (nframes + TILE - 1) / TILE));
   const float scale = (float)(1.0 / N), bscale = (float)(0.5 / N);
   kern<<<grid, (WS_P + WS_C) * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.z, tb.V, tb.xaxis, tb.P,
-                                               K, out_val, out_loc, out_bin);
+                                               K, out_val, out_loc, out_bin, gains);
   return 1;
 }
 
 template <int M, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF = 3>
 int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
-                  int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st) {
+                  int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st, const float2* gains) {
   // Bulk (TMA) ring fills, measured at cfg3: 1.99 ms against 1.67 ms with per-lane cp.async -- a 512-byte copy per channel and
   // chunk is too small for the bulk-copy engine (16.8 M copies per launch) and larger ones do not fit per-warp rings.  Kept
   // selectable (dev knob ws_tma) for the default configuration only.
   if constexpr (WS_P == 8 && WS_C == 8 && WS_STAGES == 2 && WS_NBUF == 4) {
     if (N % 64 == 0 && dev_option("ws_tma", 0))
-      return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, true>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st);
+      return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, true>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains);
   }
-  return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, false>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st);
+  return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, false>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains);
 }
 
 }  // namespace
@@ -235,7 +236,7 @@ int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nfram
 // SM's shared memory (P <= ~6000).  M = 4 (cfg1 / cfg2 shapes): 3.15 / 3.33 ms unfused -> 2.47 / 2.40 ms, ~7 TB/s of input.
 int launch_chain_fused(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
                        int avg_method, int T, const ScanTables& tb, int K, float* out_val, float* out_loc, int* out_bin,
-                       cudaStream_t st) {
+                       cudaStream_t st, const float2* gains) {
   if (nframes <= 0 || (M != 8 && M != 4)) return 0;
   if (K < 1 || K > 4) return 0;                       // K > 4: the wide candidate lists
   const bool vec2 = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
@@ -248,7 +249,7 @@ int launch_chain_fused(const float2* in, long long frame_stride, long long chan_
   // barrier 41 % of the time while each producer warp, alone on its scheduler, issues at 0.25 IPC.  At 8+8 the tile barriers
   // still hold 12 % of the warp samples, but that is slack, not lost throughput: a variant with pairwise hand-off (producer w
   // feeds consumer w through a private ring of 4-frame slots and mbarriers, no CTA-wide barrier) measured the same 1.67 ms.
-#define WS_ARGS in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st
+#define WS_ARGS in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains
   if (M == 4) {   // covariance-dominated (80 % of the step): the consumers only have to hide 0.1 + 0.7 ms under 2.6 ms of streaming
     switch (dev_option("ws4", 5)) {
       case 0: return 0;

@@ -38,7 +38,7 @@
 // Measured (B200, 592 frames of 64 x 16384): 2.2 ms = 2.2 TB/s of input = 0.34 of HBM, against 5.30 ms for the CUDA-core
 // tiled kernel.  Both sides of the pipeline now cost 700-900 clk per stage of dependent latency (converter iteration; MMA
 // issue + commit), against a 384 clk tensor-pipe floor: the next step is software-pipelining the converter's fences.
-#include "doa_internal.h"
+#include "cov_device.cuh"
 
 #include <algorithm>
 
@@ -105,7 +105,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __global__ void __launch_bounds__(TC_THREADS, 1)
 herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
-                 float2* __restrict__ out, float scale, float bscale, int avg_method) {
+                 float2* __restrict__ out, float scale, float bscale, int avg_method, const float2* __restrict__ gains) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment by OFFSETTING the shared array (an integer round trip would turn every access into a generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -308,12 +308,12 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
       float2* o = out + fcur * (long long)(TC_M * TC_M);
       for (int e = at; e < TC_M * TC_M; e += 128) {
         const int r = e % TC_M, c = e / TC_M;
-        float2 v = make_float2(stg[r * 65 + c] * scale, stg[(TC_M + r) * 65 + c] * scale);
+        float2 v = apply_gain(make_float2(stg[r * 65 + c] * scale, stg[(TC_M + r) * 65 + c] * scale), gains, r, c);
         if (avg_method == 1) {
           const int rr = TC_M - 1 - r, cc = TC_M - 1 - c;
-          const float wx = stg[rr * 65 + cc] * scale, wy = stg[(TC_M + rr) * 65 + cc] * scale;
-          v.x = __fadd_rn(__fmul_rn(0.5f, v.x), __fmul_rn(bscale, wx));
-          v.y = __fadd_rn(__fmul_rn(0.5f, v.y), __fmul_rn(bscale, -wy));
+          const float2 w = apply_gain(make_float2(stg[rr * 65 + cc] * scale, stg[(TC_M + rr) * 65 + cc] * scale), gains, rr, cc);
+          v.x = __fadd_rn(__fmul_rn(0.5f, v.x), __fmul_rn(bscale, w.x));
+          v.y = __fadd_rn(__fmul_rn(0.5f, v.y), __fmul_rn(bscale, -w.y));
         }
         o[e] = v;
       }
@@ -330,7 +330,7 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
 
 // Returns 1 if launched, 0 if the shape is not covered (caller uses the CUDA-core kernels).
 int launch_covariance_tc(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
-                         int avg_method, float2* out, cudaStream_t st) {
+                         int avg_method, float2* out, cudaStream_t st, const float2* gains) {
   if (M != TC_M || nframes <= 0) return 0;
   const bool aligned = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
                        ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
@@ -343,7 +343,7 @@ int launch_covariance_tc(const float2* in, long long frame_stride, long long cha
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(nframes, sms);
   herk_tc64_kernel<<<grid, TC_THREADS, smem, st>>>(in, frame_stride, chan_stride, N, nframes, out, (float)(1.0 / N),
-                                                   (float)(0.5 / N), avg_method);
+                                                   (float)(0.5 / N), avg_method, gains);
   return 1;
 }
 

@@ -47,6 +47,8 @@ int main(int argc, char** argv) {
   const gr_complex* src = (const gr_complex*)raw.data();
 
   gr::doa::autocorrelate::sptr ac = gr::doa::autocorrelate::make(M, N, overlap, avg);
+  /* optional: the antenna_correction block's config file folded into the covariance block */
+  if (std::getenv("DOA_HARNESS_ANTENNA_CFG")) ac->set_antenna_config(std::getenv("DOA_HARNESS_ANTENNA_CFG"));
   gr::doa::MUSIC_lin_array::sptr mus = gr::doa::MUSIC_lin_array::make(d, T, M, P);
   gr::doa::find_local_max::sptr flm = gr::doa::find_local_max::make(K, P, 0.0f, 180.0f);
   gr::doa::rootMUSIC_linear_array::sptr rm = gr::doa::rootMUSIC_linear_array::make(d, T, M);

@@ -7,6 +7,8 @@
 #include <gnuradio/io_signature.h>
 #include <algorithm>
 #include <cstdio>
+#include <stdexcept>
+#include <vector>
 #include "autocorrelate_impl.h"
 
 namespace gr {
@@ -30,6 +32,17 @@ autocorrelate_impl::autocorrelate_impl(int inputs, int snapshot_size, int overla
 }
 
 autocorrelate_impl::~autocorrelate_impl() { doa_cuda_destroy(d_cuda); }
+
+void autocorrelate_impl::set_antenna_config(const char* config_filename) {
+  if (config_filename == NULL || config_filename[0] == 0) {
+    if (doa_cuda_set_channel_gains(d_cuda, NULL) != DOA_CUDA_OK) throw std::runtime_error(doa_cuda_last_error(d_cuda));
+    return;
+  }
+  std::vector<float> g(2 * (size_t)d_num_inputs);
+  if (doa_cuda_antenna_gains_from_file(config_filename, d_num_inputs, &g[0]) != DOA_CUDA_OK)
+    throw std::invalid_argument(doa_cuda_last_error(NULL));      // same messages as the reference block
+  if (doa_cuda_set_channel_gains(d_cuda, &g[0]) != DOA_CUDA_OK) throw std::runtime_error(doa_cuda_last_error(d_cuda));
+}
 
 void autocorrelate_impl::forecast(int noutput_items, gr_vector_int& ninput_items_required) {
   for (size_t i = 0; i < ninput_items_required.size(); i++)

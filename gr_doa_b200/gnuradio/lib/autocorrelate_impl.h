@@ -14,6 +14,7 @@ class autocorrelate_impl : public autocorrelate {
  public:
   autocorrelate_impl(int inputs, int snapshot_size, int overlap_size, int avg_method);
   ~autocorrelate_impl();
+  void set_antenna_config(const char* config_filename);
   void forecast(int noutput_items, gr_vector_int& ninput_items_required);
   int general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
                    gr_vector_void_star& output_items);

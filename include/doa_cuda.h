@@ -108,6 +108,18 @@ int doa_cuda_last_launch_count(const doa_cuda_handle* h);
 int doa_cuda_set_profiling(doa_cuda_handle* h, int on);
 int doa_cuda_chain_stage_ms(doa_cuda_handle* h, float* cov_ms, float* eig_ms, float* scan_ms);
 
+/* ---- channel gains in front of the covariance ---------------------------------------------
+ * Replaces the antenna_correction block (lib/antenna_correction_impl.cc:47-99: out_k[i] = g_k * in_k[i]) and
+ * python/phase_correct_hier.py:91-102 (g_k = e^{j phi_k}) when they feed autocorrelate: instead of two more passes over the
+ * sample stream the gains are folded into the covariance, R' = D R D^H, D = diag(g).  Valid on an autocorrelate or a chain
+ * handle; `gains` = `inputs` complex floats (re, im interleaved, host memory), NULL restores "no gains".  Takes effect for
+ * the following runs. */
+int doa_cuda_set_channel_gains(doa_cuda_handle* h, const float* gains);
+/* The reference constructor's config-file reader (lib/antenna_correction_impl.cc:54-74): one "gain phase" pair per
+ * channel, g_k = (1/gain_k) e^{-j phase_k}; fails like the reference (missing file, too many / too few lines).
+ * Writes num_ant_ele complex floats to gains_out. */
+int doa_cuda_antenna_gains_from_file(const char* config_filename, int num_ant_ele, float* gains_out);
+
 void doa_cuda_destroy(doa_cuda_handle* h);
 
 #ifdef __cplusplus

@@ -74,3 +74,28 @@ def test_fake_scheduler_flowgraph_matches_oracle(oracle, tmp_path, M, N, overlap
     worst, near = parity.root_angles_ok(aoa, a64, d64)
     assert worst <= parity.ROOT_DEG and near <= 6
     assert np.abs(np.sort(loc, 1) - np.sort(np.array(thetas))[None, :]).max() < 2.0     # the reference QA's own bound
+
+
+@pytest.mark.gpu
+def test_fake_scheduler_with_antenna_config(oracle, tmp_path):
+    """The autocorrelate block with the antenna_correction config file folded in (set_antenna_config) produces the covariance
+    of the corrected streams: the reference's antenna_correction -> autocorrelate pair, one block and one pass fewer."""
+    from gr_doa_b200 import synth
+    from tests.test_channel_gains import reference_gains
+    exe = harness()
+    M, N, overlap, avg, T, P, K, n = 4, 256, 64, 1, 1, 512, 1, 23
+    gain = [1.0, 0.8, 1.3, 0.6]; phase = [0.0, 0.4, -0.9, 2.2]
+    cfg = tmp_path / "antenna.cfg"
+    cfg.write_text("".join(f"{g} {p}\n" for g, p in zip(gain, phase)))
+    x = synth.stream_numpy(n, M, N, overlap, [60.0], seed=99)
+    inp = tmp_path / "in.c64"
+    x.astype(np.complex64).tofile(inp)
+    env = dict(os.environ, DOA_HARNESS_ANTENNA_CFG=str(cfg))
+    r = subprocess.run([exe, str(inp), str(M), str(N), str(overlap), str(avg), "0.5", str(T), str(P), str(K), str(tmp_path / "out")],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr + r.stdout
+    R = np.fromfile(str(tmp_path / "out") + ".R.c64", dtype=np.complex64).reshape(-1, M * M)
+    g = reference_gains(gain, phase)
+    exp = oracle.autocorrelate((g[:, None] * x).astype(np.complex64), N, overlap, avg)
+    assert R.shape == exp.shape
+    assert parity.rel_fro(R, exp) <= parity.COV_REL_FRO
