@@ -11,6 +11,7 @@
  */
 #include <doa/MUSIC_lin_array.h>
 #include <doa/autocorrelate.h>
+#include <doa/music_chain.h>
 #include <doa/find_local_max.h>
 #include <doa/rootMUSIC_linear_array.h>
 
@@ -52,6 +53,13 @@ int main(int argc, char** argv) {
   gr::doa::MUSIC_lin_array::sptr mus = gr::doa::MUSIC_lin_array::make(d, T, M, P);
   gr::doa::find_local_max::sptr flm = gr::doa::find_local_max::make(K, P, 0.0f, 180.0f);
   gr::doa::rootMUSIC_linear_array::sptr rm = gr::doa::rootMUSIC_linear_array::make(d, T, M);
+  /* the fused block: same inputs as autocorrelate, same outputs as find_local_max */
+  gr::doa::music_chain::sptr mc = gr::doa::music_chain::make(M, N, overlap, avg, d, T, P, K, 0.0f, 180.0f);
+  if (std::getenv("DOA_HARNESS_ANTENNA_CFG")) mc->set_antenna_config(std::getenv("DOA_HARNESS_ANTENNA_CFG"));
+  if (mc->input_signature()->min_streams() != M || mc->output_signature()->max_streams() != 2 || (int)mc->history() != overlap + 1) {
+    std::fprintf(stderr, "music_chain io signature mismatch\n");
+    return 3;
+  }
 
   /* io signatures are the reference's (lib/autocorrelate_impl.cc:48-50 etc.) */
   if (ac->input_signature()->min_streams() != M || ac->output_signature()->sizeof_stream_item(0) != (int)sizeof(gr_complex) * M * M ||
@@ -65,7 +73,7 @@ int main(int argc, char** argv) {
   /* GNU Radio pre-fills history()-1 zeros in front of the stream; gr-doa's QA vectors are laid out so that the first
    * snapshot starts at sample 0, i.e. the scheduler view is: read pointer at sample 0, `overlap` samples of look-ahead
    * required beyond hop*n.  Emulate exactly that: available = L, a call may produce n frames iff hop*n + overlap <= avail. */
-  std::vector<gr_complex> Rbuf; std::vector<float> spec, val, loc, aoa;
+  std::vector<gr_complex> Rbuf; std::vector<float> spec, val, loc, aoa, cval, cloc;
   size_t rd = 0;                       /* read pointer (samples) shared by all channels */
   unsigned lcg = 12345;
   size_t frames_total = 0;
@@ -86,6 +94,14 @@ int main(int argc, char** argv) {
     gr_vector_void_star outs(1, Rbuf.data() + frames_total * (size_t)M * M);
     const int produced = ac->general_work(n, nin, ins, outs);
     if (produced != n || ac->last_consumed() != hop * n) { std::fprintf(stderr, "autocorrelate produced %d consumed %d\n", produced, ac->last_consumed()); return 3; }
+    {   /* the fused block sees the same scheduler call */
+      cval.resize((frames_total + n) * (size_t)K); cloc.resize(cval.size());
+      gr_vector_int need2(M, 0);
+      mc->forecast(n, need2);
+      if (need2[0] != need[0]) { std::fprintf(stderr, "music_chain forecast differs from autocorrelate\n"); return 3; }
+      gr_vector_void_star out_c(2); out_c[0] = cval.data() + frames_total * (size_t)K; out_c[1] = cloc.data() + frames_total * (size_t)K;
+      if (mc->general_work(n, nin, ins, out_c) != n || mc->last_consumed() != hop * n) { std::fprintf(stderr, "music_chain produced/consumed mismatch\n"); return 3; }
+    }
     rd += ac->last_consumed();
 
     /* downstream sync blocks see the same n items */
@@ -107,6 +123,8 @@ int main(int argc, char** argv) {
   dump(prefix + ".val.f32", val.data(), val.size() * sizeof(float));
   dump(prefix + ".loc.f32", loc.data(), loc.size() * sizeof(float));
   dump(prefix + ".aoa.f32", aoa.data(), aoa.size() * sizeof(float));
+  dump(prefix + ".cval.f32", cval.data(), cval.size() * sizeof(float));
+  dump(prefix + ".cloc.f32", cloc.data(), cloc.size() * sizeof(float));
   std::printf("frames %zu\n", frames_total);
   return 0;
 }

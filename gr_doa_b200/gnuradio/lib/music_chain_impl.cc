@@ -1,0 +1,76 @@
+/* autocorrelate -> MUSIC_lin_array -> find_local_max in one GNU Radio block: the input side (io signature, history,
+ * forecast, consume_each) is autocorrelate's (gr-doa lib/autocorrelate_impl.cc:47-118), the output side find_local_max's
+ * (lib/find_local_max_impl.cc:47-56: two ports of K floats); everything in between is ONE libdoa_cuda call per work(). */
+#ifdef HAVE_CONFIG_H
+#include "config.h"
+#endif
+#include <gnuradio/io_signature.h>
+#include <algorithm>
+#include <cstdio>
+#include <stdexcept>
+#include <vector>
+#include "music_chain_impl.h"
+
+namespace gr {
+namespace doa {
+
+music_chain::sptr music_chain::make(int inputs, int snapshot_size, int overlap_size, int avg_method, float norm_spacing,
+                                    int num_targets, int pspectrum_len, int num_max_vals, float x_min, float x_max) {
+  return gnuradio::get_initial_sptr(new music_chain_impl(inputs, snapshot_size, overlap_size, avg_method, norm_spacing,
+                                                         num_targets, pspectrum_len, num_max_vals, x_min, x_max));
+}
+
+music_chain_impl::music_chain_impl(int inputs, int snapshot_size, int overlap_size, int avg_method, float norm_spacing,
+                                   int num_targets, int pspectrum_len, int num_max_vals, float x_min, float x_max)
+    : gr::block("music_chain", gr::io_signature::make(inputs, inputs, sizeof(gr_complex)),
+                gr::io_signature::make2(2, 2, num_max_vals * sizeof(float), num_max_vals * sizeof(float))),
+      d_num_inputs(inputs), d_snapshot_size(snapshot_size), d_overlap_size(overlap_size), d_num_max_vals(num_max_vals),
+      d_cuda(NULL), d_ptrs(inputs) {
+  d_nonoverlap_size = d_snapshot_size - d_overlap_size;
+  set_history(d_overlap_size + 1);
+  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", 8192);
+  doa_require_created(doa_cuda_chain_create(&d_cuda, inputs, snapshot_size, overlap_size, avg_method, norm_spacing, num_targets,
+                                            pspectrum_len, num_max_vals, x_min, x_max, doa_env_int("DOA_CUDA_DEVICE", 0),
+                                            d_max_frames),
+                      "doa.music_chain");
+}
+
+music_chain_impl::~music_chain_impl() { doa_cuda_destroy(d_cuda); }
+
+void music_chain_impl::set_antenna_config(const char* config_filename) {
+  if (config_filename == NULL || config_filename[0] == 0) {
+    if (doa_cuda_set_channel_gains(d_cuda, NULL) != DOA_CUDA_OK) throw std::runtime_error(doa_cuda_last_error(d_cuda));
+    return;
+  }
+  std::vector<float> g(2 * (size_t)d_num_inputs);
+  if (doa_cuda_antenna_gains_from_file(config_filename, d_num_inputs, &g[0]) != DOA_CUDA_OK)
+    throw std::invalid_argument(doa_cuda_last_error(NULL));
+  if (doa_cuda_set_channel_gains(d_cuda, &g[0]) != DOA_CUDA_OK) throw std::runtime_error(doa_cuda_last_error(d_cuda));
+}
+
+void music_chain_impl::forecast(int noutput_items, gr_vector_int& ninput_items_required) {
+  for (size_t i = 0; i < ninput_items_required.size(); i++)
+    ninput_items_required[i] = d_nonoverlap_size * noutput_items;   // lib/autocorrelate_impl.cc:79
+}
+
+int music_chain_impl::general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
+                                   gr_vector_void_star& output_items) {
+  (void)ninput_items;
+  float* out1 = (float*)output_items[0];
+  float* out2 = (float*)output_items[1];
+  for (int done = 0; done < noutput_items; done += d_max_frames) {
+    const int n = std::min(d_max_frames, noutput_items - done);
+    for (int k = 0; k < d_num_inputs; k++)
+      d_ptrs[k] = (const gr_complex*)input_items[k] + (size_t)done * d_nonoverlap_size;
+    if (doa_cuda_chain_run_streams(d_cuda, &d_ptrs[0], n, out1 + (size_t)done * d_num_max_vals,
+                                   out2 + (size_t)done * d_num_max_vals, NULL) != DOA_CUDA_OK) {
+      std::fprintf(stderr, "doa.music_chain: %s\n", doa_cuda_last_error(d_cuda));
+      return -1;  // WORK_DONE
+    }
+  }
+  consume_each(d_nonoverlap_size * noutput_items);
+  return noutput_items;
+}
+
+}  // namespace doa
+}  // namespace gr

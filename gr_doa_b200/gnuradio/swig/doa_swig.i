@@ -9,6 +9,7 @@
 #include "doa/MUSIC_lin_array.h"
 #include "doa/rootMUSIC_linear_array.h"
 #include "doa/find_local_max.h"
+#include "doa/music_chain.h"
 %}
 %include "doa/autocorrelate.h"
 GR_SWIG_BLOCK_MAGIC2(doa, autocorrelate);
@@ -18,3 +19,5 @@ GR_SWIG_BLOCK_MAGIC2(doa, MUSIC_lin_array);
 GR_SWIG_BLOCK_MAGIC2(doa, rootMUSIC_linear_array);
 %include "doa/find_local_max.h"
 GR_SWIG_BLOCK_MAGIC2(doa, find_local_max);
+%include "doa/music_chain.h"
+GR_SWIG_BLOCK_MAGIC2(doa, music_chain);   /* not in gr-doa: the three blocks above in one GPU call */

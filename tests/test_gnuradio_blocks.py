@@ -74,6 +74,13 @@ def test_fake_scheduler_flowgraph_matches_oracle(oracle, tmp_path, M, N, overlap
     worst, near = parity.root_angles_ok(aoa, a64, d64)
     assert worst <= parity.ROOT_DEG and near <= 6
     assert np.abs(np.sort(loc, 1) - np.sort(np.array(thetas))[None, :]).max() < 2.0     # the reference QA's own bound
+    # the fused block (doa.music_chain: same inputs as autocorrelate, same outputs as find_local_max) under the same scheduler
+    cval = np.fromfile(tmp_path / "out.cval.f32", np.float32).reshape(nframes, K)
+    cloc = np.fromfile(tmp_path / "out.cloc.f32", np.float32).reshape(nframes, K)
+    step = 180.0 / P
+    same = np.abs(cloc - loc).max(1) <= 1e-6
+    assert same.mean() >= 0.98 and np.abs(cloc - loc).max() <= 1.001 * step      # +-1-bin near-ties only
+    assert np.abs(np.sort(cval, 1) - np.sort(val, 1))[same].max() <= 0.05        # dB; the chain refines with v^H G v
 
 
 @pytest.mark.gpu
