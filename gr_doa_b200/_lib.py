@@ -38,6 +38,9 @@ SYMBOLS = {
     "doa_cuda_last_launch_count": (_i, [_vp]),
     "doa_cuda_set_profiling": (_i, [_vp, _i]),
     "doa_cuda_chain_stage_ms": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f)]),
+    "doa_cuda_calibrate_create": (_i, [_hp, _f, _i, _f, _i, _i]),
+    "doa_cuda_calibrate_run": (_i, [_vp, _vp, _i, _vp]),
+    "doa_cuda_calibrate_run_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "doa_cuda_set_channel_gains": (_i, [_vp, _vp]),
     "doa_cuda_antenna_gains_from_file": (_i, [C.c_char_p, _i, _vp]),
     "doa_cuda_destroy": (None, [_vp]),

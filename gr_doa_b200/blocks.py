@@ -250,6 +250,32 @@ class find_local_max(_Block):
         return val, loc, bins
 
 
+class calibrate_lin_array(_Block):
+    """gr::doa::calibrate_lin_array (lib/calibrate_lin_array_impl.cc:46-134): antenna gain/phase estimates from the covariance
+    of a pilot at a known angle.  Output per covariance: num_ant_ele complex values, unit norm, defined up to a unit-modulus
+    factor exactly like the reference's (LAPACK-phase) eigenvector."""
+
+    def __init__(self, norm_spacing, num_ant_ele, pilot_angle, device=0, max_frames=4096):
+        super().__init__()
+        self.num_ant_ele, self.inputs = num_ant_ele, num_ant_ele
+        self._created(self._L.doa_cuda_calibrate_create(C.byref(self._h), C.c_float(norm_spacing), num_ant_ele, C.c_float(pilot_angle),
+                                                        device, max_frames))
+
+    def work(self, R):
+        M = self.num_ant_ele
+        R = np.ascontiguousarray(np.asarray(R, dtype=np.complex64).reshape(-1, M * M))
+        out = np.empty((R.shape[0], M), np.complex64)
+        check(self._L.doa_cuda_calibrate_run(self._h, R.ctypes.data, R.shape[0], out.ctypes.data), self._h)
+        return out
+
+    def work_device(self, R):
+        import torch
+        n, M = R.shape[0], self.num_ant_ele
+        out = torch.empty((n, M), dtype=torch.complex64, device=R.device)
+        check(self._L.doa_cuda_calibrate_run_device(self._h, R.data_ptr(), n, out.data_ptr(), _stream_ptr()), self._h)
+        return out
+
+
 class DoaChain(_Block):
     """autocorrelate -> MUSIC_lin_array -> find_local_max(K, P, x_min, x_max) in one call, peaks only."""
 

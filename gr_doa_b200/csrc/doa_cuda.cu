@@ -65,7 +65,7 @@ void build_x_axis(int len, float x_min, float x_max, std::vector<float>& x) {
 
 using namespace doa;
 
-enum Kind { K_AUTOCORR = 1, K_MUSIC, K_ROOTMUSIC, K_FLM, K_CHAIN };
+enum Kind { K_AUTOCORR = 1, K_MUSIC, K_ROOTMUSIC, K_FLM, K_CHAIN, K_CALIB };
 
 struct Lane {   // one stream's worth of buffers (the chain's host path double-buffers two of these)
   cudaStream_t stream = nullptr;
@@ -404,6 +404,65 @@ int doa_cuda_rootmusic_run(doa_cuda_handle* h, const void* in_host, int nframes,
   int rc = doa_cuda_rootmusic_run_device(h, l.R, nframes, l.aoa, l.stream);
   if (rc) return rc;
   CK(h, cudaMemcpyAsync(out_host, l.aoa, sizeof(float) * (size_t)nframes * h->T, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaStreamSynchronize(l.stream));
+  return DOA_CUDA_OK;
+}
+
+// ---- calibrate_lin_array ------------------------------------------------------------------------------------------------
+int doa_cuda_calibrate_create(doa_cuda_handle** out, float norm_spacing, int num_ant_ele, float pilot_angle, int device,
+                              int max_frames) {
+  int rc = check_array(norm_spacing, 1, num_ant_ele);
+  if (rc) return rc;
+  if (!std::isfinite(pilot_angle)) return fail(nullptr, DOA_CUDA_EINVAL, "pilot_angle must be finite");
+  doa_cuda_handle* h = nullptr;
+  rc = begin_create(out, h, K_CALIB, device, max_frames);
+  if (rc) return rc;
+  h->d = norm_spacing; h->T = 1; h->M = num_ant_ele;
+  // pilot steering vector with the constructor's own arithmetic (lib/calibrate_lin_array_impl.cc:57-74, amv :84-91)
+  const double kPi = 3.14159265358979323846;
+  const float theta = (float)(kPi * pilot_angle / 180.0);
+  const float s = (float)(-1.0 * 2 * kPi * std::cos((double)theta));
+  h->h_V.resize(h->M);
+  for (int nn = 0; nn < h->M; ++nn) {
+    const float loc = (float)(norm_spacing * 0.5 * (h->M - 1 - 2 * nn));
+    const float phi = s * loc;
+    h->h_V[nn] = make_float2(cosf(phi), sinf(phi));
+  }
+  Lane& l = h->lane[0];
+  const size_t mm = (size_t)h->M * h->M;
+  bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess && dalloc(&l.R, max_frames * mm) &&
+            dalloc(&l.G, max_frames * mm) && dalloc(&l.u, (size_t)max_frames * h->M) && dalloc(&h->d_V, (size_t)h->M) &&
+            cudaMemcpy(h->d_V, h->h_V.data(), sizeof(float2) * h->M, cudaMemcpyHostToDevice) == cudaSuccess;
+  return finish_create(out, h, ok);
+}
+
+int doa_cuda_calibrate_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_dev, void* cuda_stream) {
+  if (!h || h->kind != K_CALIB) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  Lane& l = h->lane[0];
+  int a = launch_noise_subspace((const float2*)in_dev, h->M, 1, nframes, l.G, nullptr, nullptr, st);
+  if (a < 0) return fail(h, a, "eigendecomposition launch rejected");
+  int b = launch_calibrate_emit((const float2*)in_dev, l.G, h->d_V, h->M, nframes, (float2*)out_dev, st);
+  if (b < 0) return fail(h, b, "calibration emit launch rejected");
+  h->launches = a + b;
+  CK(h, cudaGetLastError());
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_calibrate_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_host) {
+  if (!h || h->kind != K_CALIB) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  Lane& l = h->lane[0];
+  const size_t mm = (size_t)h->M * h->M;
+  CK(h, cudaMemcpyAsync(l.R, in_host, sizeof(float2) * nframes * mm, cudaMemcpyHostToDevice, l.stream));
+  int rc = doa_cuda_calibrate_run_device(h, l.R, nframes, l.u, l.stream);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(out_host, l.u, sizeof(float2) * (size_t)nframes * h->M, cudaMemcpyDeviceToHost, l.stream));
   CK(h, cudaStreamSynchronize(l.stream));
   return DOA_CUDA_OK;
 }

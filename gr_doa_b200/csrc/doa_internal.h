@@ -26,6 +26,10 @@ int launch_covariance_tc(const float2* in, long long frame_stride, long long cha
 //   w[f][M]       eigenvalues ascending                  (may be null)
 int launch_noise_subspace(const float2* R, int M, int T, int nframes, float2* G, float2* u, float* w, cudaStream_t st);
 
+// calibrate_lin_array: from the one-source noise projector G and the pilot steering vector v [M] to the unit-norm
+// gain/phase estimate conj(v) o u_S per frame ([nframes][M]).
+int launch_calibrate_emit(const float2* R, const float2* G, const float2* v, int M, int nframes, float2* out, cudaStream_t st);
+
 // Tables built on the host by the plan constructor (music_tables.cpp), uploaded once.
 struct ScanTables {
   int M = 0, P = 0;

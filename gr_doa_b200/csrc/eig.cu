@@ -174,6 +174,74 @@ jacobi_block_kernel(const float2* __restrict__ R, int M, int T, int nframes, flo
   }
 }
 
+// calibrate_lin_array (gr-doa lib/calibrate_lin_array_impl.cc:112-126).  With ONE source the noise
+// projector is G = I - u_S u_S^H, so U_S U_S^H = I - G and W = diag(conj v) U_S U_S^H diag(v) = w w^H with
+// w = conj(v) o u_S: the eigenvector of W for its unit eigenvalue is w itself (up to the unit-modulus factor LAPACK leaves
+// arbitrary in the reference).  u_S is read off the column of I - G with the largest diagonal entry (the best conditioned
+// one), polished by one power-iteration step with R, normalised, and its phase fixed so that that entry is real and
+// positive.  One warp per frame.
+__global__ void __launch_bounds__(128)
+calibrate_emit_kernel(const float2* __restrict__ R, const float2* __restrict__ G, const float2* __restrict__ v, int M, int nframes,
+                      float2* __restrict__ out) {
+  __shared__ float2 us_s[4][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (f >= nframes) return;
+  float2* us = us_s[warp];
+  const float2* Gf = G + f * M * M;
+  const float2* Rf = R + f * M * M;
+  float best = -INFINITY; int bc = 0;
+  for (int r = lane; r < M; r += 32) { const float dgn = 1.0f - Gf[r + (size_t)r * M].x; if (dgn > best) { best = dgn; bc = r; } }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o); const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+    if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+  }
+  // column bc of I - G = u_S conj(u_S[bc]): u_S up to a positive factor, with entry bc real and positive
+  for (int r = lane; r < M; r += 32) {
+    const float2 g = Gf[r + (size_t)bc * M];
+    us[r] = make_float2(((r == bc) ? 1.0f : 0.0f) - g.x, -g.y);
+  }
+  __syncwarp();
+  // one power-iteration step with R itself (upper triangle, like cheevd 'U'): contracts the error of the projector-derived
+  // vector by lambda_2 / lambda_1 and removes the dependence on how well the noise eigenvalues were separated
+  float2 y[2]; float n2 = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int r = lane + 32 * k;
+    float ax = 0.0f, ay = 0.0f;
+    if (r < M) {
+      for (int c = 0; c < M; ++c) {
+        float2 a;
+        if (r < c) a = Rf[r + (size_t)c * M];
+        else if (r == c) a = make_float2(Rf[r + (size_t)c * M].x, 0.0f);
+        else { const float2 t = Rf[c + (size_t)r * M]; a = make_float2(t.x, -t.y); }
+        const float2 u = us[c];
+        ax = fmaf(a.x, u.x, fmaf(-a.y, u.y, ax));
+        ay = fmaf(a.x, u.y, fmaf(a.y, u.x, ay));
+      }
+    }
+    y[k] = make_float2(ax, ay);
+    n2 = fmaf(ax, ax, fmaf(ay, ay, n2));
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  // phase reference: entry bc real and positive; unit norm
+  const int owner = bc & 31, kk = bc >> 5;
+  const float pbx = __shfl_sync(0xffffffffu, kk ? y[1].x : y[0].x, owner), pby = __shfl_sync(0xffffffffu, kk ? y[1].y : y[0].y, owner);
+  const float pm = rsqrtf(fmaxf(pbx * pbx + pby * pby, 1e-37f)), inv = rsqrtf(fmaxf(n2, 1e-37f));
+  const float rx = pbx * pm * inv, ry = -pby * pm * inv;                    // conj(y_bc)/|y_bc| / ||y||
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int r = lane + 32 * k;
+    if (r < M) {
+      const float ux = y[k].x * rx - y[k].y * ry, uy = y[k].x * ry + y[k].y * rx;
+      const float2 vr = v[r];
+      out[f * M + r] = make_float2(vr.x * ux + vr.y * uy, vr.x * uy - vr.y * ux);     // conj(v_r) * u_r
+    }
+  }
+}
+
 template <int M>
 int launch_group(const float2* R, int T, int nframes, float2* G, float2* u, float* w, cudaStream_t st) {
   constexpr int per_block = JG_WARPS * (32 / M);
@@ -202,6 +270,13 @@ int launch_noise_subspace(const float2* R, int M, int T, int nframes, float2* G,
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int blocks = min(nframes, sms * 4);
   jacobi_block_kernel<<<blocks, JB_THREADS, smem, st>>>(R, M, T, nframes, G, u, w, 20);
+  return 1;
+}
+
+int launch_calibrate_emit(const float2* R, const float2* G, const float2* v, int M, int nframes, float2* out, cudaStream_t st) {
+  if (nframes <= 0) return 0;
+  if (M > 64) return DOA_CUDA_EINVAL;
+  calibrate_emit_kernel<<<(nframes + 3) / 4, 128, 0, st>>>(R, G, v, M, nframes, out);
   return 1;
 }
 

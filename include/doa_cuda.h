@@ -108,6 +108,17 @@ int doa_cuda_last_launch_count(const doa_cuda_handle* h);
 int doa_cuda_set_profiling(doa_cuda_handle* h, int on);
 int doa_cuda_chain_stage_ms(doa_cuda_handle* h, float* cov_ms, float* eig_ms, float* scan_ms);
 
+/* ---- calibrate_lin_array ---------------------------------------------------------------
+ * gr::doa::calibrate_lin_array(norm_spacing, num_ant_ele, pilot_angle), lib/calibrate_lin_array_impl.cc:46-134: per input
+ * covariance (num_ant_ele^2 complex, column-major) one vector of num_ant_ele complex antenna gain/phase estimates from a
+ * pilot at pilot_angle degrees (Soon et al. 1994).  The reference returns the eigenvector LAPACK happens to produce, i.e.
+ * the estimate is defined up to a unit-modulus factor; here it has unit norm and the phase reference is the element of
+ * largest magnitude (the signal eigenvector is taken with that element real and positive). */
+int doa_cuda_calibrate_create(doa_cuda_handle** out, float norm_spacing, int num_ant_ele, float pilot_angle, int device,
+                              int max_frames);
+int doa_cuda_calibrate_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_host);
+int doa_cuda_calibrate_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_dev, void* cuda_stream);
+
 /* ---- channel gains in front of the covariance ---------------------------------------------
  * Replaces the antenna_correction block (lib/antenna_correction_impl.cc:47-99: out_k[i] = g_k * in_k[i]) and
  * python/phase_correct_hier.py:91-102 (g_k = e^{j phi_k}) when they feed autocorrelate: instead of two more passes over the

@@ -170,6 +170,30 @@ void noise_projector_f32(const cf* R, int M, int T, cf* G, std::vector<cf>& A, s
   L.cgemm("N", "C", &M, &M, &nn, &one, A.data(), &M, A.data(), &M, &zero, G, &M);
 }
 
+// ---- calibrate_lin_array (lib/calibrate_lin_array_impl.cc:46-134) ---------
+// ctor (:57-74): array_loc as in MUSIC, v = amv(pi*pilot_angle/180) with the float theta argument of amv() (:84).
+void calibrate_pilot_vector(float norm_spacing, int M, float pilot_angle, cf* v) {
+  const float theta = (float)(kPi * pilot_angle / 180.0);                       // :70, narrowed by amv's float parameter
+  const float s = (float)(-1.0 * 2 * kPi * std::cos((double)theta));           // :90, same overload note as music_tables
+  for (int nn = 0; nn < M; ++nn) {
+    const float loc = (float)(norm_spacing * 0.5 * (M - 1 - 2 * nn));          // :62
+    const float phi = s * loc;
+    v[nn] = cf(cosf(phi), sinf(phi));
+  }
+}
+// work (:112-126): eig_sym(R) -> U_S = last column; W = diag(conj v) U_S U_S^H diag(v); eig_sym(W) -> last column.
+void calibrate_one(const cf* R, int M, const cf* v, cf* out, std::vector<cf>& A, std::vector<cf>& W, std::vector<float>& w, HeevdWork& ws) {
+  A.assign(R, R + (size_t)M * M);
+  w.resize(M);
+  heevd_f32(M, A.data(), w.data(), ws);
+  const cf* us = A.data() + (size_t)(M - 1) * M;
+  W.resize((size_t)M * M);
+  for (int c = 0; c < M; ++c)
+    for (int r = 0; r < M; ++r) W[r + (size_t)c * M] = std::conj(v[r]) * (us[r] * std::conj(us[c])) * v[c];
+  heevd_f32(M, W.data(), w.data(), ws);
+  std::copy(W.begin() + (size_t)(M - 1) * M, W.end(), out);
+}
+
 // ---- stage 4 (lib/find_local_max_impl.cc:80-165, lib/find_local_max_impl.h:53-56) -----------------
 struct Packet { float val; unsigned idx; };
 
@@ -522,6 +546,23 @@ int oracle_rootmusic_f64(const float* R, int nframes, float norm_spacing, int T,
   return 0;
 }
 
+// calibrate_lin_array: R [n][M*M] c64 col-major -> gain/phase estimate vectors [n][M] c64 (defined up to a unit-modulus factor).
+int oracle_calibrate_lin_array(const float* R, int nframes, float norm_spacing, int M, float pilot_angle, float* out, int nthreads) {
+  std::vector<cf> v(M);
+  calibrate_pilot_vector(norm_spacing, M, pilot_angle, v.data());
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+  {
+    std::vector<cf> A, W; std::vector<float> w; HeevdWork ws;
+#pragma omp for schedule(static)
+    for (int i = 0; i < nframes; ++i)
+      calibrate_one((const cf*)R + (size_t)i * M * M, M, v.data(), (cf*)out + (size_t)i * M, A, W, w, ws);
+  }
+  return 0;
+}
+int oracle_calibrate_pilot_vector(float norm_spacing, int M, float pilot_angle, float* v) {
+  calibrate_pilot_vector(norm_spacing, M, pilot_angle, (cf*)v);
+  return 0;
+}
 int oracle_x_axis(int len, float x_min, float x_max, float* x) { x_axis_table(len, x_min, x_max, x); return 0; }
 
 // in [n][len] -> out_val [n][K] (descending by height), out_loc [n][K] (descending by x), out_idx [n][K] (optional, peak bins

@@ -137,6 +137,21 @@ def noise_projector_f64(R, num_targets, M, nthreads=1):
     return G, w
 
 
+def calibrate_lin_array(R, norm_spacing, M, pilot_angle, nthreads=1):
+    """lib/calibrate_lin_array_impl.cc:112-126: [n][M*M] covariances -> [n][M] complex64 gain/phase estimates (the
+    eigenvector LAPACK returns, i.e. defined up to a unit-modulus factor)."""
+    R = _c64(R).reshape(-1, M * M)
+    out = np.empty((R.shape[0], M), np.complex64)
+    lib().oracle_calibrate_lin_array(_p(R), R.shape[0], C.c_float(norm_spacing), M, C.c_float(pilot_angle), _p(out), nthreads)
+    return out
+
+
+def calibrate_pilot_vector(norm_spacing, M, pilot_angle):
+    v = np.empty(M, np.complex64)
+    lib().oracle_calibrate_pilot_vector(C.c_float(norm_spacing), M, C.c_float(pilot_angle), _p(v))
+    return v
+
+
 def rootmusic(R, norm_spacing, num_targets, M, nthreads=1, return_roots=False):
     R = _c64(R).reshape(-1, M * M)
     out = np.empty((R.shape[0], num_targets), np.float32)

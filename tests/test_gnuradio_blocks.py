@@ -35,11 +35,12 @@ def test_boundary_files_keep_the_reference_interface():
         "doa_MUSIC_lin_array.xml": "doa.MUSIC_lin_array($norm_spacing, $num_targets, $inputs, $pspectrum_len)",
         "doa_rootMUSIC_linear_array.xml": "doa.rootMUSIC_linear_array($norm_spacing, $num_targets, $inputs)",
         "doa_find_local_max.xml": "doa.find_local_max($num_max_vals, $vector_len, $x_min, $x_max)",
+        "doa_calibrate_lin_array.xml": "doa.calibrate_lin_array($norm_spacing, $num_ant_ele, $pilot_angle)",
     }
     for fn, make in want.items():
         assert "<make>" + make + "</make>" in open(os.path.join(base, "grc", fn)).read()
     swig = open(os.path.join(base, "swig", "doa_swig.i")).read()
-    for blk in ("autocorrelate", "MUSIC_lin_array", "rootMUSIC_linear_array", "find_local_max"):
+    for blk in ("autocorrelate", "MUSIC_lin_array", "rootMUSIC_linear_array", "find_local_max", "calibrate_lin_array"):
         assert f"GR_SWIG_BLOCK_MAGIC2(doa, {blk});" in swig
         hdr = open(os.path.join(base, "include", "doa", blk + ".h")).read()
         assert "static sptr make(" in hdr and "boost::shared_ptr<" + blk + ">" in hdr
