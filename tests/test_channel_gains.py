@@ -88,3 +88,27 @@ def test_chain_with_gains_equals_chain_on_corrected_samples(M, T, P, K):
     assert np.abs(np.sort(got[2], 1) - np.sort(ref[2], 1)).max() <= 1
     assert np.abs(np.sort(got[1], 1) - np.sort(np.tile(thetas, (B, 1)), 1)).max() < 3.0   # and the sources are found
     assert (np.sort(wrong[2], 1) == np.sort(ref[2], 1)).all(1).mean() < 0.5                # without the gains they are not
+
+
+@pytest.mark.gpu
+def test_error_behaviour_of_the_new_entry_points():
+    import ctypes as C
+    import gr_doa_b200 as doa
+    from gr_doa_b200 import _lib
+    from gr_doa_b200._lib import DoaCudaError
+    L = _lib.lib()
+    ac = doa.autocorrelate(4, 64, 0, 0, max_frames=8)
+    with pytest.raises(ValueError):
+        ac.set_channel_gains(np.ones(3, np.complex64))                       # wrong length
+    with pytest.raises(DoaCudaError):
+        ac.set_channel_gains(np.array([1, 1, np.nan, 1], np.complex64))      # non-finite
+    mu = doa.MUSIC_lin_array(0.5, 1, 4, 64, max_frames=8)
+    g = np.ones(4, np.complex64)
+    assert L.doa_cuda_set_channel_gains(mu._h, g.ctypes.data) != 0           # not a covariance-producing handle
+    for bad in ((0.5, 1, 45.0), (0.7, 4, 45.0), (0.5, 65, 45.0), (0.5, 4, float("nan"))):
+        with pytest.raises(DoaCudaError):
+            doa.calibrate_lin_array(*bad)
+    cal = doa.calibrate_lin_array(0.5, 4, 45.0, max_frames=4)
+    assert cal.work(np.zeros((0, 16), np.complex64)).shape == (0, 4)         # empty batch
+    with pytest.raises(DoaCudaError):
+        cal.work(np.tile(np.eye(4, dtype=np.complex64).reshape(1, 16), (5, 1)))   # beyond max_frames
