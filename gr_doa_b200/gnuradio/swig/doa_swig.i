@@ -2,6 +2,12 @@
 /* SWIG interface of the four GPU-backed blocks (GNU Radio 3.7: GR_SWIG_BLOCK_MAGIC2), same python names as gr-doa
    swig/doa_swig.i:22-36.  The remaining gr-doa blocks (antenna_correction, calibrate_lin_array, Connex variants) are not
    part of this hot path; keep their lines from the original file when merging. */
+/* Notes for whoever merges this into gr-doa's swig/doa_swig.i:
+   - every block listed here is backed by libdoa_cuda (link gnuradio-doa against it, lib/CMakeLists.snippet.txt); the python
+     names, constructor arguments and port shapes are the reference's, so apps/*.py and apps/*.grc keep working;
+   - autocorrelate gains one method, set_antenna_config(filename), which SWIG exposes automatically from the header;
+   - music_chain is new (autocorrelate -> MUSIC_lin_array -> find_local_max in one GPU call);
+   - GR_SWIG_BLOCK_MAGIC2 needs the headers both in the %{ %} block (for the wrapper's C++) and as %include (for SWIG). */
 #define DOA_API
 %include "gnuradio.i"
 %{
