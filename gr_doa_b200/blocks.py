@@ -72,7 +72,7 @@ class antenna_correction:
     """gr::doa::antenna_correction (lib/antenna_correction_impl.cc:47-99) as a gain source: reads the reference's config file
     ("gain phase" per channel, g_k = (1/gain_k) e^{-j phase_k}, same validation) into `.gains`; hand them to
     autocorrelate.set_channel_gains / DoaChain.set_channel_gains instead of running a multiply pass over the samples.
-    `work(streams)` is the reference block's own work() for completeness (host, numpy)."""
+    There is deliberately no work(): the multiply happens inside the covariance kernels (R' = D R D^H), never on the host."""
 
     def __init__(self, num_inputs, config_filename):
         import numpy as np
@@ -84,11 +84,6 @@ class antenna_correction:
             txt = L.doa_cuda_last_error(None)
             raise _lib.DoaCudaError(rc, txt.decode() if txt else "")
         self.gains = g
-
-    def work(self, streams):
-        import numpy as np
-        x = np.asarray(streams, dtype=np.complex64)
-        return (self.gains[:, None] * x).astype(np.complex64)
 
 
 class autocorrelate(_Block):
