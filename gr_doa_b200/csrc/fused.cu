@@ -209,7 +209,9 @@ int launch_ws_cfg2(const float2* in, long long fs, long long cs, int N, int nfra
   // Multi-GPU runs leave a few SMs to the peak gather's NCCL kernel so that it overlaps the next step's chain kernel
   // (a persistent CTA owns a whole SM's registers and shared memory: nothing else can co-reside).
   sms = std::max(1, sms - std::max(0, dev_option("chain_sms_reserve", 0)));
-  const int grid = std::max(1, std::min(sms, (nframes + TILE - 1) / TILE));
+  // small batches (a GNU Radio work() call): spread over the SMs down to one consumer warp's worth of frames per CTA
+  constexpr int GRP = 32 / M;
+  const int grid = std::max(1, std::min(sms, (nframes + GRP - 1) / GRP));
   const float scale = (float)(1.0 / N), bscale = (float)(0.5 / N);
   kern<<<grid, (WS_P + WS_C) * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.z, tb.V, tb.xaxis, tb.P,
                                                K, out_val, out_loc, out_bin, gains);
