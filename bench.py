@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=WORKLOAD["frames"], help="frames per GPU (default: the BASELINE config)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sc16", action="store_true", help="skip the informational sc16-input arm")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -242,6 +243,47 @@ def main():
         assert torch.equal(hout[2].cuda(), out[2][:eb]), "host path and device path disagree"
         del hx
 
+    # ---- informational: the same frames as sc16 (UHD int16 I/Q) -- NOT the BASELINE wire format ----
+    sc16 = None
+    if not args.no_e2e and not args.no_sc16:
+        try:
+            s15 = 1.0 / 32768
+            sb = min(B, 32768)
+            q = torch.view_as_real(x[:sb]).mul(8192.0).round_().clamp_(-32768, 32767).to(torch.int16)
+            fcq = torch.view_as_complex(q.to(torch.float32).mul_(s15))
+            ref_q = [t.clone() for t in chain.run_device(fcq)]
+            del fcq
+            chain.set_input_format("sc16", s15)
+            for _ in range(3):
+                got_q = chain.run_device(q)
+            fence()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(10):
+                chain.run_device(q)
+            q1.record()
+            fence()
+            same_q = all(torch.equal(a, b) for a, b in zip(got_q, ref_q))
+            hq = torch.empty(q.shape, dtype=torch.int16, pin_memory=True)
+            hq.copy_(q)
+            hout_q = (torch.empty((sb, K), dtype=torch.float32, pin_memory=True), torch.empty((sb, K), dtype=torch.float32, pin_memory=True),
+                      torch.empty((sb, K), dtype=torch.int32, pin_memory=True))
+            chain.run_host(hq, out=hout_q)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                chain.run_host(hq, out=hout_q)
+            torch.cuda.synchronize()
+            dtq = (time.perf_counter() - t0) / 5
+            sc16 = {"note": "informational, per GPU: int16 I/Q samples read directly by the covariance (half the bytes); not the BASELINE wire format",
+                    "frames": sb, "device_ms": q0.elapsed_time(q1) / 10, "device_frames_per_s": sb / (q0.elapsed_time(q1) / 10 * 1e-3),
+                    "e2e_frames_per_s": sb / dtq, "h2d_bytes_per_step": sb * M * N * 4,
+                    "bit_identical_to_fc32_on_converted_samples": bool(same_q)}
+            del q, hq
+        except Exception as ex:      # never lose the headline line to the informational arm
+            sc16 = {"error": repr(ex)}
+        finally:
+            chain.set_input_format("fc32")
+
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample of the same frames (rank 0, N = 1) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -290,6 +332,7 @@ def main():
                                    "frac": chain_gbs / peak, "note": "whole step (chain kernel" + ("" if fused else "s") + (" + peak gather" if world > 1 else "") + ") per GPU against the same HBM peak"}},
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "sc16_input": sc16,
             "gpu_launches": launches,
             "clocks": clocks,
         }

@@ -43,6 +43,7 @@ SYMBOLS = {
     "doa_cuda_calibrate_run_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "doa_cuda_set_channel_gains": (_i, [_vp, _vp]),
     "doa_cuda_antenna_gains_from_file": (_i, [C.c_char_p, _i, _vp]),
+    "doa_cuda_set_input_format": (_i, [_vp, _i, _f]),
     "doa_cuda_destroy": (None, [_vp]),
 }
 

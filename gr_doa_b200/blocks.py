@@ -56,6 +56,29 @@ class _Block:
             raise ValueError(f"expected {self.inputs} gains, got {g.size}")
         check(self._L.doa_cuda_set_channel_gains(self._h, g.ctypes.data), self._h)
 
+    _sc16 = False
+
+    def set_input_format(self, fmt="fc32", scale=1.0 / 32768):
+        """Sample format of the covariance input (autocorrelate and chain handles).  "fc32": complex64 (gr_complex, the
+        reference's only format).  "sc16": UHD's cpu_format "sc16" -- int16 arrays / tensors with a trailing axis of 2
+        (I, Q); a sample's value is int16 * scale.  Converted exactly inside the covariance kernel (include/doa_cuda.h)."""
+        if fmt not in ("fc32", "sc16"):
+            raise ValueError("fmt must be 'fc32' or 'sc16'")
+        check(self._L.doa_cuda_set_input_format(self._h, 1 if fmt == "sc16" else 0, C.c_float(scale)), self._h)
+        self._sc16 = fmt == "sc16"
+
+    def _samples(self, x):
+        """Host samples in the handle's input format: contiguous complex64 [...], or int16 [..., 2] for sc16."""
+        if not self._sc16:
+            return _np(x, np.complex64)
+        x = np.asarray(x)
+        if x.dtype != np.int16 or x.shape[-1] != 2:
+            raise ValueError("sc16 input: int16 array with a trailing (I, Q) axis of 2 expected")
+        return np.ascontiguousarray(x)
+
+    def _nsamp(self, x):
+        return x.size // 2 if self._sc16 else x.size
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._L.doa_cuda_destroy(self._h)
@@ -106,10 +129,10 @@ class autocorrelate(_Block):
     def general_work(self, noutput_items, input_items):
         """input_items: M arrays of complex64, each with >= hop*(n-1)+snapshot_size samples (history included).
         Returns ([n][M*M] complex64, consumed_per_port = hop*n) like general_work() + consume_each()."""
-        xs = [_np(x, np.complex64) for x in input_items]
+        xs = [self._samples(x) for x in input_items]
         need = (noutput_items - 1) * self.hop + self.snapshot_size if noutput_items > 0 else 0
         for x in xs:
-            if x.size < need:
+            if self._nsamp(x) < need:
                 raise ValueError("not enough input items for noutput_items")
         out = np.empty((noutput_items, self.inputs * self.inputs), np.complex64)
         ptrs = (C.c_void_p * self.inputs)(*[x.ctypes.data for x in xs])
@@ -118,7 +141,7 @@ class autocorrelate(_Block):
 
     def work(self, streams):
         """Whole-stream convenience: streams [M][L] -> all complete frames."""
-        x = _np(streams, np.complex64)
+        x = self._samples(streams)
         L = x.shape[1]
         n = (L - self.snapshot_size) // self.hop + 1 if L >= self.snapshot_size else 0
         outs = []
@@ -129,10 +152,11 @@ class autocorrelate(_Block):
         return np.concatenate(outs) if outs else np.empty((0, self.inputs ** 2), np.complex64)
 
     def work_device(self, x, frame_stride=None, chan_stride=None, nframes=None):
-        """x: torch complex64 CUDA tensor, [B][M][N] independent frames (default strides) or any strided layout."""
+        """x: torch complex64 CUDA tensor, [B][M][N] independent frames (default strides) or any strided layout
+        (sc16 input format: int16 [B][M][N][2])."""
         import torch
         if frame_stride is None:
-            B, M, N = x.shape
+            B, M, N = x.shape[:3]
             frame_stride, chan_stride, nframes = M * N, N, B
         out = torch.empty((nframes, self.inputs * self.inputs), dtype=torch.complex64, device=x.device)
         check(self._L.doa_cuda_autocorrelate_run_device(self._h, x.data_ptr(), frame_stride, chan_stride, nframes,
@@ -296,10 +320,11 @@ class DoaChain(_Block):
         return a.value, b.value, c.value
 
     def run_device(self, x, out=None, frame_stride=None, chan_stride=None, nframes=None):
-        """x: torch complex64 CUDA tensor [B][M][N] (or explicit strides).  Returns (val, loc, bins) CUDA tensors."""
+        """x: torch complex64 CUDA tensor [B][M][N] (or explicit strides; sc16 input format: int16 [B][M][N][2]).
+        Returns (val, loc, bins) CUDA tensors."""
         import torch
         if frame_stride is None:
-            B, M, N = x.shape
+            B, M, N = x.shape[:3]
             frame_stride, chan_stride, nframes = M * N, N, B
         if out is None:
             val = torch.empty((nframes, self.K), dtype=torch.float32, device=x.device)
@@ -310,11 +335,12 @@ class DoaChain(_Block):
         return val, loc, bins
 
     def run_host(self, frames, out=None):
-        """frames: host complex64 [B][M][N] (numpy, or a pinned torch tensor).  Returns numpy (val, loc, bins)."""
+        """frames: host complex64 [B][M][N] (numpy, or a pinned torch tensor; sc16 input format: int16 [B][M][N][2]).
+        Returns numpy (val, loc, bins)."""
         if hasattr(frames, "data_ptr"):
             ptr, B = frames.data_ptr(), frames.shape[0]
         else:
-            frames = _np(frames, np.complex64)
+            frames = self._samples(frames)
             ptr, B = frames.ctypes.data, frames.shape[0]
         if out is None:
             out = (np.empty((B, self.K), np.float32), np.empty((B, self.K), np.float32), np.empty((B, self.K), np.int32))
@@ -324,7 +350,7 @@ class DoaChain(_Block):
         return val, loc, bins
 
     def run_streams(self, streams, nframes):
-        xs = [_np(x, np.complex64) for x in streams]
+        xs = [self._samples(x) for x in streams]
         val, loc, bins = (np.empty((nframes, self.K), np.float32), np.empty((nframes, self.K), np.float32),
                           np.empty((nframes, self.K), np.int32))
         ptrs = (C.c_void_p * self.inputs)(*[x.ctypes.data for x in xs])

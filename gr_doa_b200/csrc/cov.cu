@@ -29,9 +29,9 @@ int num_sms() {
 }
 
 
-template <int M, int VEC, int G>
+template <int M, int VEC, int G, typename S>
 __global__ void __launch_bounds__(COV_WARPS * 32, (G == 1 && M >= 8) ? 2 : 1)
-cov_small_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
+cov_small_kernel(const S* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
                  float2* __restrict__ out, float scale, float bscale, int avg_method, const float2* __restrict__ gains) {
   constexpr int CNT = M * M;
   __shared__ float red_s[COV_WARPS][CNT];
@@ -39,7 +39,7 @@ cov_small_kernel(const float2* __restrict__ in, long long frame_stride, long lon
   const int warp = threadIdx.x >> 5;
   float* red = red_s[warp];
   for (int f = blockIdx.x * COV_WARPS + warp; f < nframes; f += gridDim.x * COV_WARPS) {
-    cov_warp_frame<M, VEC, G>(in + (long long)f * frame_stride, chan_stride, N, lane, red);
+    cov_warp_frame<M, VEC, G, S>(in + (long long)f * frame_stride, chan_stride, N, lane, red);
     cov_warp_emit<M>(red, scale, bscale, avg_method, lane, out + (long long)f * CNT, gains);
   }
 }
@@ -55,28 +55,21 @@ constexpr int C16_FRAMES = 4;   // frames in flight per CTA (8 warps)
 __device__ const unsigned char kTri8Row[28] = {1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7};
 __device__ const unsigned char kTri8Col[28] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 6};
 
-template <int VEC>
-__device__ __forceinline__ void cov16_load(const float2* __restrict__ base, long long chan_stride, int t, bool ok,
+template <int VEC, typename S>
+__device__ __forceinline__ void cov16_load(const S* __restrict__ base, long long chan_stride, int t, bool ok,
                                            float2 (&x)[VEC][16]) {
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const float2* p = base + (long long)k * chan_stride + t;
-    if constexpr (VEC == 2) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) v = ldg_stream4(reinterpret_cast<const float4*>(p));
-      x[0][k] = make_float2(v.x, v.y);
-      x[1][k] = make_float2(v.z, v.w);
-    } else {
-      float2 v = make_float2(0.f, 0.f);
-      if (ok) v = ldg_stream2(p);
-      x[0][k] = v;
-    }
+    float2 v[VEC];
+    load_samples<VEC, S>(base + (long long)k * chan_stride + t, ok, v);
+#pragma unroll
+    for (int s = 0; s < VEC; ++s) x[s][k] = v[s];
   }
 }
 
-template <int VEC>
+template <int VEC, typename S>
 __global__ void __launch_bounds__(C16_FRAMES * 64, 1)
-cov16_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
+cov16_kernel(const S* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
              float2* __restrict__ out, float scale, float bscale, int avg_method, const float2* __restrict__ gains) {
   constexpr int M = 16, CNT = 256, NP16 = 120;
   __shared__ float red_s[C16_FRAMES][CNT];
@@ -86,14 +79,14 @@ cov16_kernel(const float2* __restrict__ in, long long frame_stride, long long ch
   const int nslots = gridDim.x * C16_FRAMES;
   // every warp of a pair runs the same number of iterations (the pair barrier needs both)
   for (int f = blockIdx.x * C16_FRAMES + slot; f < nframes; f += nslots) {
-    const float2* base = in + (long long)f * frame_stride;
+    const S* base = in + (long long)f * frame_stride;
     float a[128];
     if (role == 0) {
       CovAcc<8> d0, d1;
       d0.clear(); d1.clear();
       for (int t = (int)lane * VEC; t < N; t += 32 * VEC) {
         float2 x[VEC][16];
-        cov16_load<VEC>(base, chan_stride, t, true, x);
+        cov16_load<VEC, S>(base, chan_stride, t, true, x);
 #pragma unroll
         for (int s = 0; s < VEC; ++s) {
           float2 lo8[8], hi8[8];
@@ -113,7 +106,7 @@ cov16_kernel(const float2* __restrict__ in, long long frame_stride, long long ch
       for (int i = 0; i < 64; ++i) od[i] = 0ull;
       for (int t = (int)lane * VEC; t < N; t += 32 * VEC) {
         float2 x[VEC][16];
-        cov16_load<VEC>(base, chan_stride, t, true, x);
+        cov16_load<VEC, S>(base, chan_stride, t, true, x);
 #pragma unroll
         for (int s = 0; s < VEC; ++s)
 #pragma unroll
@@ -321,6 +314,16 @@ cov16_ring_kernel(const float2* __restrict__ in, long long frame_stride, long lo
   else cov16_ring_role<1>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, gains, ring, red_s[slot], slot, lane);
 }
 
+// sc16 input: the LDG kernel (bit-identical to the ring kernel; a ring of 8-byte cp.async is the obvious next step).
+int launch_cov16_sc16(const unsigned* in, long long fs, long long cs, int N, int nframes, float2* out, float scale, float bscale,
+                      int avg, cudaStream_t st, const float2* gains) {
+  const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 7u) == 0);
+  const int blocks = (nframes + C16_FRAMES - 1) / C16_FRAMES;
+  if (vec2) cov16_kernel<2, unsigned><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+  else cov16_kernel<1, unsigned><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+  return 1;
+}
+
 int launch_cov16(const float2* in, long long fs, long long cs, int N, int nframes, float2* out, float scale, float bscale,
                  int avg, cudaStream_t st, const float2* gains) {
   const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
@@ -332,8 +335,8 @@ int launch_cov16(const float2* in, long long fs, long long cs, int N, int nframe
     cov16_ring_kernel<<<grid, C16_FRAMES * 64, smem, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
     return 1;
   }
-  if (vec2) cov16_kernel<2><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
-  else cov16_kernel<1><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+  if (vec2) cov16_kernel<2, float2><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+  else cov16_kernel<1, float2><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
   return 1;
 }
 
@@ -341,8 +344,9 @@ int launch_cov16(const float2* in, long long fs, long long cs, int N, int nframe
 constexpr int CT_THREADS = 512;
 constexpr int CT_TT = 64;   // time samples per shared-memory tile
 
+template <typename S>
 __global__ void __launch_bounds__(CT_THREADS)
-cov_tiled_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int M, int N,
+cov_tiled_kernel(const S* __restrict__ in, long long frame_stride, long long chan_stride, int M, int N,
                  int nframes, float2* __restrict__ out, float scale, float bscale, int avg_method, const float2* __restrict__ gains) {
   extern __shared__ float2 smem[];
   const int nb = (M + 3) / 4;           // 4-row blocks
@@ -365,7 +369,7 @@ cov_tiled_kernel(const float2* __restrict__ in, long long frame_stride, long lon
   }
 
   for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
-    const float2* base = in + (long long)f * frame_stride;
+    const S* base = in + (long long)f * frame_stride;
     float are[4][4], aim[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -377,9 +381,9 @@ cov_tiled_kernel(const float2* __restrict__ in, long long frame_stride, long lon
       __syncthreads();
       for (int i = tid; i < Mp * CT_TT; i += CT_THREADS) {
         const int r = i / CT_TT, t = i % CT_TT;
-        float2 v = make_float2(0.f, 0.f);
-        if (r < M && t0 + t < N) v = ldg_stream2(base + (long long)r * chan_stride + t0 + t);
-        tile[r * LDT + t] = v;
+        float2 v[1];
+        load_samples<1, S>(base + (long long)r * chan_stride + t0 + t, r < M && t0 + t < N, v);
+        tile[r * LDT + t] = v[0];
       }
       __syncthreads();
       if (active) {
@@ -433,28 +437,56 @@ cov_tiled_kernel(const float2* __restrict__ in, long long frame_stride, long lon
   }
 }
 
-template <int M>
-int launch_small(const float2* in, long long fs, long long cs, int N, int nframes, float2* out, float scale,
+template <int M, typename S>
+int launch_small(const S* in, long long fs, long long cs, int N, int nframes, float2* out, float scale,
                  float bscale, int avg, cudaStream_t st, const float2* gains) {
-  const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
+  // two samples per load (LDG.128 for fc32, LDG.64 for sc16) when the layout is aligned for it
+  const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & (2 * sizeof(S) - 1)) == 0);
   const int blocks = (nframes + COV_WARPS - 1) / COV_WARPS;
   const int variant = dev_option("cov_groups", 1);   // 1: 128 regs, 2 CTAs/SM (6.4 TB/s at M=8); 2: 167 regs, 1 CTA/SM (5.9 TB/s)
   if (vec2) {
-    if (variant == 1) cov_small_kernel<M, 2, 1><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
-    else cov_small_kernel<M, 2, 2><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+    if (variant == 1) cov_small_kernel<M, 2, 1, S><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+    else cov_small_kernel<M, 2, 2, S><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
   } else {
-    cov_small_kernel<M, 1, 2><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+    cov_small_kernel<M, 1, 2, S><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
   }
+  return 1;
+}
+
+template <typename S>
+int launch_tiled(const S* in, long long frame_stride, long long chan_stride, int M, int N, int nframes, float2* out,
+                 float scale, float bscale, int avg_method, cudaStream_t st, const float2* gains) {
+  const int Mp = ((M + 3) / 4) * 4;
+  const size_t smem = (size_t)Mp * (CT_TT + 1) * sizeof(float2) + (size_t)Mp * Mp * 2 * sizeof(float);
+  cudaFuncSetAttribute(cov_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  const int blocks = min(nframes, num_sms() * 4);
+  cov_tiled_kernel<S><<<blocks, CT_THREADS, smem, st>>>(in, frame_stride, chan_stride, M, N, nframes, out, scale, bscale,
+                                                        avg_method, gains);
   return 1;
 }
 
 }  // namespace
 
-int launch_covariance(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
-                      int avg_method, float2* out, cudaStream_t st, const float2* gains) {
+int launch_covariance(const void* in_v, long long frame_stride, long long chan_stride, int M, int N, int nframes,
+                      int avg_method, float2* out, cudaStream_t st, const float2* gains, InputFormat fmt) {
   if (nframes <= 0) return 0;
+  if (M > 64) return DOA_CUDA_EINVAL;
+  const float bscale = (float)(0.5 / N);    // (0.5/d_snapshot_size), lib/autocorrelate_impl.cc:108
+  if (fmt.sc16) {
+    // The kernels accumulate the int16 values as exact floats; the converter's scale s enters once, squared, in the
+    // emit factor.  For a power-of-two s that is bit-identical to the fc32 path fed float(i16) * s.
+    const float scale = (float)(1.0 / N) * (fmt.scale * fmt.scale);
+    const unsigned* in = static_cast<const unsigned*>(in_v);
+    switch (M) {
+      case 2: return launch_small<2>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
+      case 4: return launch_small<4>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
+      case 8: return launch_small<8>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
+      case 16: return launch_cov16_sc16(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
+      default: return launch_tiled(in, frame_stride, chan_stride, M, N, nframes, out, scale, bscale, avg_method, st, gains);
+    }
+  }
+  const float2* in = static_cast<const float2*>(in_v);
   const float scale = (float)(1.0 / N);     // (1.0/d_snapshot_size) narrowed to float, lib/autocorrelate_impl.cc:106
-  const float bscale = (float)(0.5 / N);    // (0.5/d_snapshot_size), :108
   switch (M) {
     case 2: return launch_small<2>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
     case 4: return launch_small<4>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
@@ -462,18 +494,11 @@ int launch_covariance(const float2* in, long long frame_stride, long long chan_s
     case 16: return launch_cov16(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
     default: break;
   }
-  if (M > 64) return DOA_CUDA_EINVAL;
   if (M == 64 && dev_option("herk_tc", 1)) {   // tensor-core complex HERK (3xTF32) when alignment allows
     const int r = launch_covariance_tc(in, frame_stride, chan_stride, M, N, nframes, avg_method, out, st, gains);
     if (r != 0) return r;
   }
-  const int Mp = ((M + 3) / 4) * 4;
-  const size_t smem = (size_t)Mp * (CT_TT + 1) * sizeof(float2) + (size_t)Mp * Mp * 2 * sizeof(float);
-  cudaFuncSetAttribute(cov_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  const int blocks = min(nframes, num_sms() * 4);
-  cov_tiled_kernel<<<blocks, CT_THREADS, smem, st>>>(in, frame_stride, chan_stride, M, N, nframes, out, scale, bscale,
-                                                     avg_method, gains);
-  return 1;
+  return launch_tiled(in, frame_stride, chan_stride, M, N, nframes, out, scale, bscale, avg_method, st, gains);
 }
 
 }  // namespace doa

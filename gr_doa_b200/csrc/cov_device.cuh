@@ -18,10 +18,58 @@ __device__ __forceinline__ float2 ldg_stream2(const float2* p) {
   return v;
 }
 
+// ---- sc16 input (UHD wire / cpu format "sc16": one little-endian 32-bit word per complex sample, I in the low half) ----
+// The reference flowgraphs receive fc32 from UHD (python/twinrx_usrp_source.py:57), i.e. the host converts every int16 to
+// float before the sample reaches autocorrelate; accepting the int16 pairs directly halves the bytes the whole chain is
+// bound by.  Conversion is exact and stays off the conversion unit: bias the halves to
+// unsigned (xor 0x8000), splice them under the exponent of 2^23 (PRMT) and subtract 2^23 + 32768 (one packed add).
+__device__ __forceinline__ float2 sc16_to_c64(unsigned w) {
+  const unsigned b = w ^ 0x80008000u;
+  const unsigned lo = __byte_perm(b, 0x4B000000u, 0x7410);
+  const unsigned hi = __byte_perm(b, 0x4B000000u, 0x7432);
+  float2 r;   // one packed add for the pair (FADD2): 4 issue slots per sample
+  upk2(add2(pk2(__uint_as_float(lo), __uint_as_float(hi)), pk2(-8421376.0f, -8421376.0f)), r.x, r.y);
+  return r;
+}
+// VEC consecutive samples of one channel, fc32 (S = float2) or sc16 (S = unsigned), streaming loads; !ok: zeros.
+// Both formats give a lane the same samples, so the two paths accumulate in the same order.
+template <int VEC, typename S>
+__device__ __forceinline__ void load_samples(const S* p, bool ok, float2 (&x)[VEC]) {
+  static_assert(VEC == 1 || VEC == 2, "one or two samples per load");
+  if constexpr (sizeof(S) == 8) {
+    if constexpr (VEC == 2) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) v = ldg_stream4(reinterpret_cast<const float4*>(p));
+      x[0] = make_float2(v.x, v.y);
+      x[1] = make_float2(v.z, v.w);
+    } else {
+      float2 v = make_float2(0.f, 0.f);
+      if (ok) v = ldg_stream2(reinterpret_cast<const float2*>(p));
+      x[0] = v;
+    }
+  } else {
+    if constexpr (VEC == 2) {
+      unsigned a = 0u, b = 0u;
+      if (ok) asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+      x[0] = sc16_to_c64(a);
+      x[1] = sc16_to_c64(b);
+    } else {
+      unsigned a = 0u;
+      if (ok) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(a) : "l"(p));
+      x[0] = sc16_to_c64(a);
+    }
+  }
+}
+
 // cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass registers; src_bytes = 0 zero-fills.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// 8-byte variant (two sc16 samples); .cg exists for 16 bytes only
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(NKEEP) : "memory"); }
@@ -123,12 +171,12 @@ struct CovAcc {
 
 // One frame by one warp: accumulate the Hermitian lower half over the frame's time axis and fold the 32 partial
 // matrices; on return `red` (M*M floats, shared memory, this warp's) holds the raw sums (layout: see folded_entry).
-template <int M, int VEC, int G>
-__device__ __forceinline__ void cov_warp_frame(const float2* __restrict__ base, long long chan_stride, int N, unsigned lane,
+template <int M, int VEC, int G, typename S>
+__device__ __forceinline__ void cov_warp_frame(const S* __restrict__ base, long long chan_stride, int N, unsigned lane,
                                                float* red) {
   CovAcc<M> acc;
   acc.clear();
-  // G independent load groups per iteration (G*M LDG.128 in flight per lane).
+  // G independent load groups per iteration (G*M LDG.128 in flight per lane; LDG.64 for sc16).
   for (int t0 = (int)lane * VEC; t0 < N; t0 += G * 32 * VEC) {
     float2 x[G][VEC][M];
 #pragma unroll
@@ -137,17 +185,10 @@ __device__ __forceinline__ void cov_warp_frame(const float2* __restrict__ base, 
       const bool ok = t < N;   // N % VEC == 0 is guaranteed by the launcher
 #pragma unroll
       for (int k = 0; k < M; ++k) {
-        const float2* p = base + (long long)k * chan_stride + t;
-        if constexpr (VEC == 2) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) v = ldg_stream4(reinterpret_cast<const float4*>(p));
-          x[g][0][k] = make_float2(v.x, v.y);
-          x[g][1][k] = make_float2(v.z, v.w);
-        } else {
-          float2 v = make_float2(0.f, 0.f);
-          if (ok) v = ldg_stream2(p);
-          x[g][0][k] = v;
-        }
+        float2 v[VEC];
+        load_samples<VEC, S>(base + (long long)k * chan_stride + t, ok, v);
+#pragma unroll
+        for (int s = 0; s < VEC; ++s) x[g][s][k] = v[s];
       }
     }
 #pragma unroll

@@ -85,6 +85,8 @@ struct doa_cuda_handle {
   int nlanes = 1;
   float2* d_z = nullptr; float2* d_V = nullptr; float* d_x = nullptr; float* d_zpair = nullptr;
   float2* d_gains = nullptr;     // per-channel complex gains folded into the covariance (null: none)
+  InputFormat fmt;               // sample format of the covariance input (fc32 unless doa_cuda_set_input_format said sc16)
+  size_t sample_bytes() const { return fmt.sc16 ? 4 : sizeof(float2); }
   std::vector<float> h_loc, h_theta, h_x; std::vector<float2> h_V, h_z;
   std::string err;
   int launches = 0;
@@ -202,6 +204,19 @@ int doa_cuda_set_channel_gains(doa_cuda_handle* h, const float* gains) {
   return DOA_CUDA_OK;
 }
 
+// ---- input sample format ------------------------------------------------------------------------------------------
+int doa_cuda_set_input_format(doa_cuda_handle* h, int format, float scale) {
+  if (!h || (h->kind != K_AUTOCORR && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
+  if (format != DOA_CUDA_FMT_FC32 && format != DOA_CUDA_FMT_SC16) return fail(h, DOA_CUDA_EINVAL, "unknown input format");
+  if (format == DOA_CUDA_FMT_SC16 && !(std::isfinite(scale) && scale > 0.0f))
+    return fail(h, DOA_CUDA_EINVAL, "sc16 scale must be finite and > 0");
+  CK(h, cudaSetDevice(h->device));
+  for (int i = 0; i < h->nlanes; ++i) if (h->lane[i].stream) CK(h, cudaStreamSynchronize(h->lane[i].stream));
+  h->fmt.sc16 = format == DOA_CUDA_FMT_SC16;
+  h->fmt.scale = h->fmt.sc16 ? scale : 1.0f;
+  return DOA_CUDA_OK;
+}
+
 // lib/antenna_correction_impl.cc:54-74, statement by statement: float gain/phase pairs, g = gr_complex(1.0/Gain, 0) * exp(gr_complex(0, -Phase))
 int doa_cuda_antenna_gains_from_file(const char* config_filename, int num_ant_ele, float* gains_out) {
   if (!config_filename || !gains_out || num_ant_ele < 1) return fail(nullptr, DOA_CUDA_EINVAL, "bad arguments");
@@ -248,8 +263,8 @@ int doa_cuda_autocorrelate_run_device(doa_cuda_handle* h, const void* in_dev, lo
   if (!h || (h->kind != K_AUTOCORR && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
   if (nframes < 0) return fail(h, DOA_CUDA_EINVAL, "nframes < 0");
   CK(h, cudaSetDevice(h->device));
-  int n = launch_covariance((const float2*)in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, (float2*)out_dev,
-                            (cudaStream_t)cuda_stream, h->d_gains);
+  int n = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, (float2*)out_dev,
+                            (cudaStream_t)cuda_stream, h->d_gains, h->fmt);
   if (n < 0) return fail(h, n, "covariance launch rejected");
   h->launches = n;
   CK(h, cudaGetLastError());
@@ -261,8 +276,9 @@ static int stage_streams(doa_cuda_handle* h, Lane& l, const void* const* in_host
   const size_t L = (size_t)(nframes - 1) * h->hop + h->N;
   const size_t Lpad = (L + 1) & ~(size_t)1;
   if (Lpad * h->M > l.in_elems) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  const size_t sb = h->sample_bytes();
   for (int k = 0; k < h->M; ++k)
-    CK(h, cudaMemcpyAsync(l.in + (size_t)k * Lpad, in_host[k], L * sizeof(float2), cudaMemcpyHostToDevice, l.stream));
+    CK(h, cudaMemcpyAsync((char*)l.in + (size_t)k * Lpad * sb, in_host[k], L * sb, cudaMemcpyHostToDevice, l.stream));
   *Lpad_out = Lpad;
   return DOA_CUDA_OK;
 }
@@ -553,7 +569,7 @@ int doa_cuda_chain_create(doa_cuda_handle** out, int inputs, int snapshot_size, 
   return finish_create(out, h, ok);
 }
 
-static int chain_on_lane(doa_cuda_handle* h, Lane& l, const float2* in_dev, long long frame_stride, long long chan_stride,
+static int chain_on_lane(doa_cuda_handle* h, Lane& l, const void* in_dev, long long frame_stride, long long chan_stride,
                          int nframes, float* val, float* loc, int* bin, cudaStream_t st, bool prof) {
   cudaEvent_t* ev = nullptr;
   if (prof) { ev = &h->ev[(size_t)(h->prof_calls % PROF_SETS) * 4]; ++h->prof_calls; }
@@ -562,7 +578,7 @@ static int chain_on_lane(doa_cuda_handle* h, Lane& l, const float2* in_dev, long
     // one persistent kernel for the whole chain when the shape allows it; stage events collapse to (0, 0, total)
     if (prof) { CK(h, cudaEventRecord(ev[1], st)); CK(h, cudaEventRecord(ev[2], st)); }
     int f = launch_chain_fused(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, h->T, tables_of(h), h->K, val,
-                               loc, bin, st, h->d_gains);
+                               loc, bin, st, h->d_gains, h->fmt);
     if (f < 0) return fail(h, f, "fused chain launch rejected");
     if (f > 0) {
       if (prof) CK(h, cudaEventRecord(ev[3], st));
@@ -571,7 +587,7 @@ static int chain_on_lane(doa_cuda_handle* h, Lane& l, const float2* in_dev, long
       return DOA_CUDA_OK;
     }
   }
-  int a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains);
+  int a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains, h->fmt);
   if (a < 0) return fail(h, a, "covariance launch rejected");
   if (prof) CK(h, cudaEventRecord(ev[1], st));
   int b = launch_noise_subspace(l.R, h->M, h->T, nframes, l.G, l.u, nullptr, st);
@@ -592,7 +608,7 @@ int doa_cuda_chain_run_device(doa_cuda_handle* h, const void* in_dev, long long 
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
   CK(h, cudaSetDevice(h->device));
   h->launches = 0;
-  return chain_on_lane(h, h->lane[0], (const float2*)in_dev, frame_stride, chan_stride, nframes, (float*)out_val_dev,
+  return chain_on_lane(h, h->lane[0], in_dev, frame_stride, chan_stride, nframes, (float*)out_val_dev,
                        (float*)out_loc_dev, (int*)out_bin_dev, (cudaStream_t)cuda_stream, h->profiling);
 }
 
@@ -605,12 +621,13 @@ int doa_cuda_chain_run(doa_cuda_handle* h, const void* in_host, int nframes, voi
   h->launches = 0;
   const size_t fe = (size_t)h->M * h->N;
   const int chunk = h->lane[1].frames;
-  const float2* src = (const float2*)in_host;
+  const size_t sb = h->sample_bytes();
+  const char* src = (const char*)in_host;
   int c = 0;
   for (int f0 = 0; f0 < nframes; f0 += chunk, ++c) {
     Lane& l = h->lane[c & 1];
     const int nf = std::min(chunk, nframes - f0);
-    CK(h, cudaMemcpyAsync(l.in, src + (size_t)f0 * fe, sizeof(float2) * nf * fe, cudaMemcpyHostToDevice, l.stream));
+    CK(h, cudaMemcpyAsync(l.in, src + (size_t)f0 * fe * sb, sb * nf * fe, cudaMemcpyHostToDevice, l.stream));
     int rc = chain_on_lane(h, l, l.in, (long long)fe, h->N, nf, l.val, l.loc, l.bin, l.stream, false);
     if (rc) return rc;
     const size_t nk = (size_t)nf * h->K, off = (size_t)f0 * h->K;

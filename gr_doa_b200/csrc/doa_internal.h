@@ -11,10 +11,18 @@ namespace doa {
 
 // ---- launch interfaces (one per kernel family; each returns the number of kernel launches it issued or <0) ----
 
+// Sample format of the covariance input: fc32 (interleaved float re, im; the reference's gr_complex) or sc16 (UHD's
+// interleaved int16 I, Q; the value of a sample is int16 * scale).  Strides are in complex samples either way.
+struct InputFormat {
+  int sc16 = 0;
+  float scale = 1.0f;
+};
+
 // Stage 1.  Sample (f,k,t) at in[f*frame_stride + k*chan_stride + t]; out[f][r + c*M] column-major.
 // gains (may be null): M per-channel complex gains applied in front of the covariance, R' = D R D^H.
-int launch_covariance(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
-                      int avg_method, float2* out, cudaStream_t st, const float2* gains = nullptr);
+int launch_covariance(const void* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
+                      int avg_method, float2* out, cudaStream_t st, const float2* gains = nullptr,
+                      InputFormat fmt = InputFormat());
 
 // Tensor-core path of stage 1 for M = 64 (herk_tc.cu): 1 if launched, 0 if the shape is not covered.
 int launch_covariance_tc(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
@@ -46,9 +54,9 @@ int launch_scan_peaks(const float2* u, const float2* G, const ScanTables& tb, in
 
 // The whole chain in one persistent kernel (fused.cu).  Returns 1 if launched, 0 if the shape is not covered (the caller
 // then runs the three stage kernels), <0 on error.  Bit-identical to the three-kernel path.
-int launch_chain_fused(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
+int launch_chain_fused(const void* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
                        int avg_method, int T, const ScanTables& tb, int K, float* out_val, float* out_loc, int* out_bin,
-                       cudaStream_t st, const float2* gains = nullptr);
+                       cudaStream_t st, const float2* gains = nullptr, InputFormat fmt = InputFormat());
 
 // Stage 2b standalone: the full dB pseudo-spectrum [nframes][P].
 int launch_scan_spectrum(const float2* u, const float2* G, const ScanTables& tb, int nframes, float* out,

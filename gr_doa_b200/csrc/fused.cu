@@ -45,14 +45,23 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
                :: "r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
-template <int M, int KL, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF, bool TMA>
+// S = float2: fc32 samples, a ring slot is one float4 (two samples) per lane and channel; S = unsigned: sc16 samples, a ring
+// slot is one uint2 (the same two samples in 8 bytes).  Either way lane l of chunk c holds samples 64 c + 2 l and + 1, so the
+// two formats accumulate in the same order.
+template <typename S> struct RingSlot { typedef float4 type; };
+template <> struct RingSlot<unsigned> { typedef uint2 type; };
+
+template <int M, int KL, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF, bool TMA, typename S>
 __global__ void __launch_bounds__((WS_P + WS_C) * 32, 1)
-chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
+chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
                 int avg_method, float scale, float bscale, int T, int max_sweeps, const float* __restrict__ zpair,
                 const float2* __restrict__ zplain, const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int P, int K,
                 float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin,
                 const float2* __restrict__ gains) {
   static_assert(M == 8 || M == 4, "instantiated for 8 and 4 lanes per matrix");
+  static_assert(!TMA || sizeof(S) == 8, "bulk ring fills are an fc32 variant");
+  typedef typename RingSlot<S>::type Slot;
+  constexpr bool SC16 = sizeof(S) == 4;
   constexpr int TILE = WS_C * 32 / M;          // frames per tile: every consumer warp owns 32/M of them
   constexpr int BAR_EMPTY = BAR_FULL + WS_NBUF; // WS_NBUF tile buffers between producers and consumers
   static_assert(BAR_EMPTY + WS_NBUF <= 16, "named barriers");
@@ -65,7 +74,7 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
   float2* Gs = Rbuf + WS_NBUF * TILE * MM;                                 // [TILE][MM]
   float2* us = Gs + TILE * MM;                                       // [TILE][M]
   float* red = reinterpret_cast<float*>(us + TILE * M);              // [WS_P][MM]
-  float4* ring = reinterpret_cast<float4*>(red + WS_P * MM);         // [WS_P][WS_STAGES][M][32]
+  Slot* ring = reinterpret_cast<Slot*>(red + WS_P * MM);             // [WS_P][WS_STAGES][M][32]
   __shared__ unsigned long long ring_bar[TMA ? WS_P * WS_STAGES : 1];
   if constexpr (TMA) {
     if (threadIdx.x < WS_P * WS_STAGES) mbar_init(&ring_bar[threadIdx.x], 1);
@@ -94,25 +103,28 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
     const int NCH = (N + 63) / 64;                                   // 64-sample chunks per frame (2 samples per lane)
     const int nfw = (w < nf) ? (nf - w + WS_P - 1) / WS_P : 0;       // frames of this warp: w, w+P, w+2P, ...
     const int total = nfw * NCH;                                     // chunks of this warp, frame-major
-    float4* myring = ring + (size_t)w * WS_STAGES * M * 32;
+    Slot* myring = ring + (size_t)w * WS_STAGES * M * 32;
     // issue cursor (frame base pointer, chunk in frame, ring stage) advances incrementally: no divisions in the loop
-    const float2* ibase = in + (lo + w) * frame_stride;
+    const S* ibase = in + (lo + w) * frame_stride;
     int ic = 0, istage = 0, issued = 0;
     auto issue = [&]() {
       if constexpr (TMA) {
         if (lane == 0) {
           unsigned long long* bar = &ring_bar[w * WS_STAGES + istage];
           mbar_expect_tx(bar, M * 512u);
-          float4* dst = myring + (size_t)istage * M * 32;
+          Slot* dst = myring + (size_t)istage * M * 32;
 #pragma unroll
           for (int k = 0; k < M; ++k) bulk_g2s(dst + k * 32, ibase + (long long)k * chan_stride + ic * 64, 512u, bar);
         }
       } else {
         const int t = ic * 64 + lane * 2;
-        const int nbytes = (t < N) ? 16 : 0;                           // beyond the frame: zero fill
-        float4* dst = myring + (size_t)istage * M * 32 + lane;
+        const int nbytes = (t < N) ? (int)sizeof(Slot) : 0;            // beyond the frame: zero fill (sc16 zero = 0.0f)
+        Slot* dst = myring + (size_t)istage * M * 32 + lane;
 #pragma unroll
-        for (int k = 0; k < M; ++k) cp_async16(dst + k * 32, ibase + (long long)k * chan_stride + (nbytes ? t : 0), nbytes);
+        for (int k = 0; k < M; ++k) {
+          if constexpr (SC16) cp_async8(dst + k * 32, ibase + (long long)k * chan_stride + (nbytes ? t : 0), nbytes);
+          else cp_async16(dst + k * 32, ibase + (long long)k * chan_stride + (nbytes ? t : 0), nbytes);
+        }
       }
       if (++ic == NCH) { ic = 0; ibase += (long long)WS_P * frame_stride; }
       if (++istage == WS_STAGES) istage = 0;
@@ -134,11 +146,15 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
         cp_async_commit();
         cp_async_wait<WS_STAGES - 1>();
       }
-      const float4* src = myring + (size_t)rstage * M * 32 + lane;
+      const Slot* src = myring + (size_t)rstage * M * 32 + lane;
       if (++rstage == WS_STAGES) { rstage = 0; rphase ^= 1u; }
       float2 x0[M], x1[M];
 #pragma unroll
-      for (int k = 0; k < M; ++k) { const float4 v = src[k * 32]; x0[k] = make_float2(v.x, v.y); x1[k] = make_float2(v.z, v.w); }
+      for (int k = 0; k < M; ++k) {
+        const Slot v = src[k * 32];
+        if constexpr (SC16) { x0[k] = sc16_to_c64(v.x); x1[k] = sc16_to_c64(v.y); }
+        else { x0[k] = make_float2(v.x, v.y); x1[k] = make_float2(v.z, v.w); }
+      }
       acc.add(x0);
       acc.add(x1);
       if (++c == NCH) {
@@ -194,14 +210,14 @@ chain_ws_kernel(const float2* __restrict__ in, long long frame_stride, long long
   }
 }
 
-template <int M, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF, bool TMA>
-int launch_ws_cfg2(const float2* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
-                  int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st, const float2* gains) {
+template <int M, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF, bool TMA, typename S>
+int launch_ws_cfg2(const S* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
+                  int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st, const float2* gains, float in_scale2) {
   constexpr int TILE = WS_C * 32 / M;
   const size_t smem = ((ztab_floats(tb.P) + 3) & ~(size_t)3) * sizeof(float) + ((size_t)(WS_NBUF + 1) * TILE * M * M + (size_t)TILE * M) * sizeof(float2) +
-                      (size_t)WS_P * M * M * sizeof(float) + (size_t)WS_P * WS_STAGES * M * 32 * sizeof(float4);
+                      (size_t)WS_P * M * M * sizeof(float) + (size_t)WS_P * WS_STAGES * M * 32 * sizeof(typename RingSlot<S>::type);
   if (smem > 225 * 1024) return 0;
-  auto kern = chain_ws_kernel<M, 4, WS_P, WS_C, WS_STAGES, WS_NBUF, TMA>;
+  auto kern = chain_ws_kernel<M, 4, WS_P, WS_C, WS_STAGES, WS_NBUF, TMA, S>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -212,7 +228,7 @@ int launch_ws_cfg2(const float2* in, long long fs, long long cs, int N, int nfra
   // small batches (a GNU Radio work() call): spread over the SMs down to one consumer warp's worth of frames per CTA
   constexpr int GRP = 32 / M;
   const int grid = std::max(1, std::min(sms, (nframes + GRP - 1) / GRP));
-  const float scale = (float)(1.0 / N), bscale = (float)(0.5 / N);
+  const float scale = (float)(1.0 / N) * in_scale2, bscale = (float)(0.5 / N);   // in_scale2: sc16 converter scale squared (cov.cu)
   kern<<<grid, (WS_P + WS_C) * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.z, tb.V, tb.xaxis, tb.P,
                                                K, out_val, out_loc, out_bin, gains);
   return 1;
@@ -221,14 +237,15 @@ int launch_ws_cfg2(const float2* in, long long fs, long long cs, int N, int nfra
 template <int M, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF = 3>
 int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
                   int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st, const float2* gains) {
+  const float in_scale2 = 1.0f;
   // Bulk (TMA) ring fills, measured at cfg3: 1.99 ms against 1.67 ms with per-lane cp.async -- a 512-byte copy per channel and
   // chunk is too small for the bulk-copy engine (16.8 M copies per launch) and larger ones do not fit per-warp rings.  Kept
   // selectable (dev knob ws_tma) for the default configuration only.
   if constexpr (WS_P == 8 && WS_C == 8 && WS_STAGES == 2 && WS_NBUF == 4) {
     if (N % 64 == 0 && dev_option("ws_tma", 0))
-      return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, true>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains);
+      return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, true>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
   }
-  return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, false>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains);
+  return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, false>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
 }
 
 }  // namespace
@@ -236,14 +253,24 @@ int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nfram
 // Returns 1 if the fused kernel was launched, 0 if this shape is not covered (caller falls back to the three kernels).
 // Covered: M = 8 or 4, K <= 4 (K = 1: global arg-max), 16-byte aligned even strides, scan table + tiles + rings within one
 // SM's shared memory (P <= ~6000).  M = 4 (cfg1 / cfg2 shapes): 3.15 / 3.33 ms unfused -> 2.47 / 2.40 ms, ~7 TB/s of input.
-int launch_chain_fused(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
+int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_stride, int M, int N, int nframes,
                        int avg_method, int T, const ScanTables& tb, int K, float* out_val, float* out_loc, int* out_bin,
-                       cudaStream_t st, const float2* gains) {
+                       cudaStream_t st, const float2* gains, InputFormat fmt) {
   if (nframes <= 0 || (M != 8 && M != 4)) return 0;
   if (K < 1 || K > 4) return 0;                       // K > 4: the wide candidate lists
   const bool vec2 = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
-                    ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
+                    ((reinterpret_cast<uintptr_t>(in_v) & (fmt.sc16 ? 7u : 15u)) == 0);
   if (!vec2) return 0;
+  if (fmt.sc16) {
+    // sc16 samples: same warp split as fc32; the ring slots are half as wide, which buys a third stage (M = 8) in the same
+    // shared memory.  Not tuned separately yet.
+    const unsigned* in = static_cast<const unsigned*>(in_v);
+    const float s2 = fmt.scale * fmt.scale;
+    if (M == 4)
+      return launch_ws_cfg2<4, 8, 8, 6, 4, false>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
+    return launch_ws_cfg2<8, 8, 8, 3, 4, false>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
+  }
+  const float2* in = static_cast<const float2*>(in_v);
   // Producer/consumer split, ring depth and tile buffers, measured at cfg3 with the packed (FFMA2) covariance: 8+8 warps,
   // 2 stages x 4 tile buffers or 3 x 3: 1.59-1.64 ms (equal within box-to-box noise; 2 x 4 needs 201 KB of shared memory);
   // 4+12: 1.88-1.99, 5+11: 1.91, 6+10: 1.85, 7+9: 1.84, 9+7: 1.94, 10+6: 2.03, 12+4: 2.39; 4+16 (setmaxnreg re-allocation,

@@ -131,6 +131,20 @@ int doa_cuda_set_channel_gains(doa_cuda_handle* h, const float* gains);
  * Writes num_ant_ele complex floats to gains_out. */
 int doa_cuda_antenna_gains_from_file(const char* config_filename, int num_ant_ele, float* gains_out);
 
+/* ---- sample format of the covariance input -------------------------------------------------
+ * The reference's flowgraphs ask UHD for cpu_format "fc32" (python/twinrx_usrp_source.py:57): the host converts the
+ * radio's int16 I/Q pairs to gr_complex before autocorrelate reads them.  With DOA_CUDA_FMT_SC16 an autocorrelate or a
+ * chain handle reads the int16 pairs directly (UHD cpu_format "sc16": one little-endian 32-bit word per complex sample,
+ * I in the low half), converts exactly inside the covariance kernel, and the value of a sample is int16 * scale (UHD's
+ * converter uses 1/32767; 1/32768 is a power of two).  That halves the bytes the chain moves over PCIe and HBM.
+ * Every `in` pointer of the run functions (host and device) is then read as sc16; strides stay in complex samples.
+ * Result: for a power-of-two scale bit-identical to the fc32 path fed float(int16) * scale; for any other scale the
+ * covariance differs from that by at most 2 ulp per entry (the scale enters once, squared, instead of per sample).
+ * Takes effect for the following runs; DOA_CUDA_FMT_FC32 (the default) ignores `scale`. */
+#define DOA_CUDA_FMT_FC32 0
+#define DOA_CUDA_FMT_SC16 1
+int doa_cuda_set_input_format(doa_cuda_handle* h, int format, float scale);
+
 void doa_cuda_destroy(doa_cuda_handle* h);
 
 #ifdef __cplusplus
