@@ -8,6 +8,8 @@
  * usage: fake_scheduler <in.c64> <M> <N> <overlap> <avg> <d> <T> <P> <K> <out_prefix>
  *   in.c64: M channel streams of equal length, channel-major, raw complex64.
  *   writes <out_prefix>.R.c64, .spec.f32, .val.f32, .loc.f32, .aoa.f32 (raw) for the test suite to check.
+ *   DOA_HARNESS_SC16_IN=<file of the same streams as int16 I/Q, channel-major>: a doa.music_chain made with make_sc16
+ *   (scale 1/32768) sees the same scheduler calls on those items; its outputs go to <out_prefix>.sval.f32 / .sloc.f32.
  */
 #include <doa/MUSIC_lin_array.h>
 #include <doa/autocorrelate.h>
@@ -61,6 +63,19 @@ int main(int argc, char** argv) {
     return 3;
   }
 
+  /* optional: the sc16-fed fused block next to it */
+  gr::doa::music_chain::sptr mc16;
+  std::vector<char> raw16;
+  if (std::getenv("DOA_HARNESS_SC16_IN")) {
+    raw16 = slurp(std::getenv("DOA_HARNESS_SC16_IN"));
+    if (raw16.size() != L * M * 4) { std::fprintf(stderr, "sc16 input length mismatch\n"); return 2; }
+    mc16 = gr::doa::music_chain::make_sc16(M, N, overlap, avg, d, T, P, K, 0.0f, 180.0f, 1.0f / 32768);
+    if (mc16->input_signature()->sizeof_stream_item(0) != 4 || (int)mc16->history() != overlap + 1) {
+      std::fprintf(stderr, "music_chain (sc16) io signature mismatch\n");
+      return 3;
+    }
+  }
+
   /* io signatures are the reference's (lib/autocorrelate_impl.cc:48-50 etc.) */
   if (ac->input_signature()->min_streams() != M || ac->output_signature()->sizeof_stream_item(0) != (int)sizeof(gr_complex) * M * M ||
       mus->output_signature()->sizeof_stream_item(0) != (int)sizeof(float) * P || flm->output_signature()->max_streams() != 2 ||
@@ -73,7 +88,7 @@ int main(int argc, char** argv) {
   /* GNU Radio pre-fills history()-1 zeros in front of the stream; gr-doa's QA vectors are laid out so that the first
    * snapshot starts at sample 0, i.e. the scheduler view is: read pointer at sample 0, `overlap` samples of look-ahead
    * required beyond hop*n.  Emulate exactly that: available = L, a call may produce n frames iff hop*n + overlap <= avail. */
-  std::vector<gr_complex> Rbuf; std::vector<float> spec, val, loc, aoa, cval, cloc;
+  std::vector<gr_complex> Rbuf; std::vector<float> spec, val, loc, aoa, cval, cloc, sval, sloc;
   size_t rd = 0;                       /* read pointer (samples) shared by all channels */
   unsigned lcg = 12345;
   size_t frames_total = 0;
@@ -102,6 +117,13 @@ int main(int argc, char** argv) {
       gr_vector_void_star out_c(2); out_c[0] = cval.data() + frames_total * (size_t)K; out_c[1] = cloc.data() + frames_total * (size_t)K;
       if (mc->general_work(n, nin, ins, out_c) != n || mc->last_consumed() != hop * n) { std::fprintf(stderr, "music_chain produced/consumed mismatch\n"); return 3; }
     }
+    if (mc16) {
+      sval.resize((frames_total + n) * (size_t)K); sloc.resize(sval.size());
+      gr_vector_const_void_star ins16(M);
+      for (int k = 0; k < M; ++k) ins16[k] = raw16.data() + ((size_t)k * L + rd) * 4;
+      gr_vector_void_star out_s(2); out_s[0] = sval.data() + frames_total * (size_t)K; out_s[1] = sloc.data() + frames_total * (size_t)K;
+      if (mc16->general_work(n, nin, ins16, out_s) != n || mc16->last_consumed() != hop * n) { std::fprintf(stderr, "music_chain (sc16) produced/consumed mismatch\n"); return 3; }
+    }
     rd += ac->last_consumed();
 
     /* downstream sync blocks see the same n items */
@@ -125,6 +147,10 @@ int main(int argc, char** argv) {
   dump(prefix + ".aoa.f32", aoa.data(), aoa.size() * sizeof(float));
   dump(prefix + ".cval.f32", cval.data(), cval.size() * sizeof(float));
   dump(prefix + ".cloc.f32", cloc.data(), cloc.size() * sizeof(float));
+  if (mc16) {
+    dump(prefix + ".sval.f32", sval.data(), sval.size() * sizeof(float));
+    dump(prefix + ".sloc.f32", sloc.data(), sloc.size() * sizeof(float));
+  }
   std::printf("frames %zu\n", frames_total);
   return 0;
 }

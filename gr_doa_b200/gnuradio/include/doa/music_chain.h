@@ -17,6 +17,12 @@ class DOA_API music_chain : virtual public gr::block {
    *  find_local_max(num_max_vals, [vector_len = pspectrum_len], x_min, x_max). */
   static sptr make(int inputs, int snapshot_size, int overlap_size, int avg_method, float norm_spacing, int num_targets,
                    int pspectrum_len, int num_max_vals, float x_min, float x_max);
+  /*! The same block fed UHD cpu_format "sc16" items (std::complex<short>, 4 bytes: what the radio delivers before the host
+   *  converts it to gr_complex for python/twinrx_usrp_source.py:57's "fc32"): half the bytes per sample into the GPU.
+   *  A sample's value is int16 * sc16_scale (UHD's converter: 1/32767; a power of two such as 1/32768 makes the block
+   *  bit-identical to make() fed the converted samples). */
+  static sptr make_sc16(int inputs, int snapshot_size, int overlap_size, int avg_method, float norm_spacing, int num_targets,
+                        int pspectrum_len, int num_max_vals, float x_min, float x_max, float sc16_scale);
   /*! Same as autocorrelate::set_antenna_config: fold the Antenna Correction block's config file into the covariance. */
   virtual void set_antenna_config(const char* config_filename) = 0;
 };

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <stdexcept>
+#include <string>
 #include <vector>
 #include "music_chain_impl.h"
 
@@ -20,12 +21,21 @@ music_chain::sptr music_chain::make(int inputs, int snapshot_size, int overlap_s
                                                          num_targets, pspectrum_len, num_max_vals, x_min, x_max));
 }
 
+music_chain::sptr music_chain::make_sc16(int inputs, int snapshot_size, int overlap_size, int avg_method, float norm_spacing,
+                                         int num_targets, int pspectrum_len, int num_max_vals, float x_min, float x_max,
+                                         float sc16_scale) {
+  if (!(sc16_scale > 0.0f)) throw std::invalid_argument("doa.music_chain: sc16_scale must be > 0");
+  return gnuradio::get_initial_sptr(new music_chain_impl(inputs, snapshot_size, overlap_size, avg_method, norm_spacing,
+                                                         num_targets, pspectrum_len, num_max_vals, x_min, x_max, sc16_scale));
+}
+
 music_chain_impl::music_chain_impl(int inputs, int snapshot_size, int overlap_size, int avg_method, float norm_spacing,
-                                   int num_targets, int pspectrum_len, int num_max_vals, float x_min, float x_max)
-    : gr::block("music_chain", gr::io_signature::make(inputs, inputs, sizeof(gr_complex)),
+                                   int num_targets, int pspectrum_len, int num_max_vals, float x_min, float x_max,
+                                   float sc16_scale)
+    : gr::block("music_chain", gr::io_signature::make(inputs, inputs, sc16_scale > 0.0f ? 2 * sizeof(short) : sizeof(gr_complex)),
                 gr::io_signature::make2(2, 2, num_max_vals * sizeof(float), num_max_vals * sizeof(float))),
       d_num_inputs(inputs), d_snapshot_size(snapshot_size), d_overlap_size(overlap_size), d_num_max_vals(num_max_vals),
-      d_cuda(NULL), d_ptrs(inputs) {
+      d_item_bytes(sc16_scale > 0.0f ? 2 * sizeof(short) : sizeof(gr_complex)), d_cuda(NULL), d_ptrs(inputs) {
   d_nonoverlap_size = d_snapshot_size - d_overlap_size;
   set_history(d_overlap_size + 1);
   d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", 8192);
@@ -33,6 +43,11 @@ music_chain_impl::music_chain_impl(int inputs, int snapshot_size, int overlap_si
                                             pspectrum_len, num_max_vals, x_min, x_max, doa_env_int("DOA_CUDA_DEVICE", 0),
                                             d_max_frames),
                       "doa.music_chain");
+  if (sc16_scale > 0.0f && doa_cuda_set_input_format(d_cuda, DOA_CUDA_FMT_SC16, sc16_scale) != DOA_CUDA_OK) {
+    const std::string msg = std::string("doa.music_chain: ") + doa_cuda_last_error(d_cuda);
+    doa_cuda_destroy(d_cuda);
+    throw std::runtime_error(msg);
+  }
 }
 
 music_chain_impl::~music_chain_impl() { doa_cuda_destroy(d_cuda); }
@@ -61,7 +76,7 @@ int music_chain_impl::general_work(int noutput_items, gr_vector_int& ninput_item
   for (int done = 0; done < noutput_items; done += d_max_frames) {
     const int n = std::min(d_max_frames, noutput_items - done);
     for (int k = 0; k < d_num_inputs; k++)
-      d_ptrs[k] = (const gr_complex*)input_items[k] + (size_t)done * d_nonoverlap_size;
+      d_ptrs[k] = (const char*)input_items[k] + (size_t)done * d_nonoverlap_size * d_item_bytes;
     if (doa_cuda_chain_run_streams(d_cuda, &d_ptrs[0], n, out1 + (size_t)done * d_num_max_vals,
                                    out2 + (size_t)done * d_num_max_vals, NULL) != DOA_CUDA_OK) {
       std::fprintf(stderr, "doa.music_chain: %s\n", doa_cuda_last_error(d_cuda));

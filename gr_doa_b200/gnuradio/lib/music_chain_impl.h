@@ -8,12 +8,13 @@ class music_chain_impl : public music_chain {
  private:
   const int d_num_inputs, d_snapshot_size, d_overlap_size, d_num_max_vals;
   int d_nonoverlap_size, d_max_frames;
+  const size_t d_item_bytes;   /* sizeof(gr_complex), or 4 for sc16 items */
   doa_cuda_handle* d_cuda;
   std::vector<const void*> d_ptrs;
 
  public:
   music_chain_impl(int inputs, int snapshot_size, int overlap_size, int avg_method, float norm_spacing, int num_targets,
-                   int pspectrum_len, int num_max_vals, float x_min, float x_max);
+                   int pspectrum_len, int num_max_vals, float x_min, float x_max, float sc16_scale = 0.0f);
   ~music_chain_impl();
   void set_antenna_config(const char* config_filename);
   void forecast(int noutput_items, gr_vector_int& ninput_items_required);

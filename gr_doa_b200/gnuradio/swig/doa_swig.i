@@ -6,7 +6,9 @@
    - every block listed here is backed by libdoa_cuda (link gnuradio-doa against it, lib/CMakeLists.snippet.txt); the python
      names, constructor arguments and port shapes are the reference's, so apps/*.py and apps/*.grc keep working;
    - autocorrelate gains one method, set_antenna_config(filename), which SWIG exposes automatically from the header;
-   - music_chain is new (autocorrelate -> MUSIC_lin_array -> find_local_max in one GPU call);
+   - music_chain is new (autocorrelate -> MUSIC_lin_array -> find_local_max in one GPU call); its second factory,
+     music_chain::make_sc16 (UHD "sc16" input items), reaches python as the flat SWIG name doa.music_chain_make_sc16
+     (GR_SWIG_BLOCK_MAGIC2 rebinds doa.music_chain to make(); grc/doa_music_chain_sc16.xml uses the flat name);
    - GR_SWIG_BLOCK_MAGIC2 needs the headers both in the %{ %} block (for the wrapper's C++) and as %include (for SWIG). */
 #define DOA_API
 %include "gnuradio.i"

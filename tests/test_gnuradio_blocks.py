@@ -107,3 +107,26 @@ def test_fake_scheduler_with_antenna_config(oracle, tmp_path):
     exp = oracle.autocorrelate((g[:, None] * x).astype(np.complex64), N, overlap, avg)
     assert R.shape == exp.shape
     assert parity.rel_fro(R, exp) <= parity.COV_REL_FRO
+
+
+@pytest.mark.gpu
+def test_fake_scheduler_music_chain_fed_sc16_items(tmp_path):
+    """doa.music_chain made with make_sc16 (4-byte Complex Int16 items, what UHD delivers before its host-side conversion to
+    gr_complex) under the same scheduler calls as the fc32 block fed the converted samples: identical peaks, bit for bit."""
+    from gr_doa_b200 import synth
+    from tests.test_sc16_input import S15, quantise, to_fc32
+    exe = harness()
+    M, N, overlap, avg, T, P, K, n = 4, 2048, 512, 1, 1, 2048, 1, 150
+    q = quantise(synth.stream_numpy(n, M, N, overlap, [60.0], seed=31))
+    inp, inp16 = tmp_path / "in.c64", tmp_path / "in.sc16"
+    to_fc32(q, S15).tofile(inp)
+    q.tofile(inp16)
+    env = dict(os.environ, DOA_HARNESS_SC16_IN=str(inp16))
+    r = subprocess.run([exe, str(inp), str(M), str(N), str(overlap), str(avg), "0.5", str(T), str(P), str(K), str(tmp_path / "out")],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert f"frames {n}" in r.stdout
+    got = [np.fromfile(str(tmp_path / "out") + ext, np.float32).reshape(n, K) for ext in (".sval.f32", ".sloc.f32")]
+    ref = [np.fromfile(str(tmp_path / "out") + ext, np.float32).reshape(n, K) for ext in (".cval.f32", ".cloc.f32")]
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    assert np.abs(got[1] - 60.0).max() < 2.0
