@@ -51,7 +51,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 template <typename S> struct RingSlot { typedef float4 type; };
 template <> struct RingSlot<unsigned> { typedef uint2 type; };
 
-template <int M, int KL, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF, bool TMA, typename S>
+// FILL: how a producer warp fills a ring stage (the stage's layout is the same in all three).
+//   0  lane l copies samples 2l, 2l+1 of the chunk for each of the M channels: M cp.async per lane, each with its own 64-bit
+//      source address (k * chan_stride is a run-time stride);
+//   1  bulk (TMA) copies issued by one lane (fc32 only);
+//   2  lane l copies for channel l / (32/M) only: its M cp.async are 64 bytes apart (sc16: 32) in that channel, i.e. ONE 64-bit
+//      address and immediates -- about 30 fewer address instructions per chunk in an issue-bound loop.  A warp-wide copy
+//      then touches M segments of 64 bytes instead of 512 contiguous bytes (the same 16 sectors).  Measured at cfg3
+//      (tools/ws_exp.py 80824 80824c): 1.705 against 1.688 ms -- the 12 instructions it saves per 228-instruction chunk do
+//      not show, so FILL 0 stays the default (dev knob ws_fill = 2 selects this one; bit-identical, tested).
+template <int M, int KL, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF, int FILL, typename S>
 __global__ void __launch_bounds__((WS_P + WS_C) * 32, 1)
 chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
                 int avg_method, float scale, float bscale, int T, int max_sweeps, const float* __restrict__ zpair,
@@ -59,6 +68,7 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
                 float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin,
                 const float2* __restrict__ gains) {
   static_assert(M == 8 || M == 4, "instantiated for 8 and 4 lanes per matrix");
+  constexpr bool TMA = FILL == 1;
   static_assert(!TMA || sizeof(S) == 8, "bulk ring fills are an fc32 variant");
   typedef typename RingSlot<S>::type Slot;
   constexpr bool SC16 = sizeof(S) == 4;
@@ -105,7 +115,9 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
     const int total = nfw * NCH;                                     // chunks of this warp, frame-major
     Slot* myring = ring + (size_t)w * WS_STAGES * M * 32;
     // issue cursor (frame base pointer, chunk in frame, ring stage) advances incrementally: no divisions in the loop
+    constexpr int LPC = 32 / M;                                      // FILL 2: lanes per channel
     const S* ibase = in + (lo + w) * frame_stride;
+    if constexpr (FILL == 2) ibase += (long long)(lane / LPC) * chan_stride + (lane % LPC) * 2;
     int ic = 0, istage = 0, issued = 0;
     auto issue = [&]() {
       if constexpr (TMA) {
@@ -115,6 +127,23 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
           Slot* dst = myring + (size_t)istage * M * 32;
 #pragma unroll
           for (int k = 0; k < M; ++k) bulk_g2s(dst + k * 32, ibase + (long long)k * chan_stride + ic * 64, 512u, bar);
+        }
+      } else if constexpr (FILL == 2) {
+        const S* src = ibase + ic * 64;
+        Slot* dst = myring + (size_t)istage * M * 32 + (lane / LPC) * 32 + (lane % LPC);
+        if (ic * 64 + 64 <= N) {                                       // whole chunk inside the frame (warp-uniform)
+#pragma unroll
+          for (int j = 0; j < M; ++j) {
+            if constexpr (SC16) cp_async8(dst + j * LPC, src + j * LPC * 2, 8);
+            else cp_async16(dst + j * LPC, src + j * LPC * 2, 16);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < M; ++j) {
+            const int nbytes = (ic * 64 + (j * LPC + lane % LPC) * 2 < N) ? (int)sizeof(Slot) : 0;   // beyond the frame: zero fill
+            if constexpr (SC16) cp_async8(dst + j * LPC, src + (nbytes ? j * LPC * 2 : 0), nbytes);
+            else cp_async16(dst + j * LPC, src + (nbytes ? j * LPC * 2 : 0), nbytes);
+          }
         }
       } else {
         const int t = ic * 64 + lane * 2;
@@ -210,14 +239,14 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
   }
 }
 
-template <int M, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF, bool TMA, typename S>
+template <int M, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF, int FILL, typename S>
 int launch_ws_cfg2(const S* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
                   int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st, const float2* gains, float in_scale2) {
   constexpr int TILE = WS_C * 32 / M;
   const size_t smem = ((ztab_floats(tb.P) + 3) & ~(size_t)3) * sizeof(float) + ((size_t)(WS_NBUF + 1) * TILE * M * M + (size_t)TILE * M) * sizeof(float2) +
                       (size_t)WS_P * M * M * sizeof(float) + (size_t)WS_P * WS_STAGES * M * 32 * sizeof(typename RingSlot<S>::type);
   if (smem > 225 * 1024) return 0;
-  auto kern = chain_ws_kernel<M, 4, WS_P, WS_C, WS_STAGES, WS_NBUF, TMA, S>;
+  auto kern = chain_ws_kernel<M, 4, WS_P, WS_C, WS_STAGES, WS_NBUF, FILL, S>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -243,9 +272,14 @@ int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nfram
   // selectable (dev knob ws_tma) for the default configuration only.
   if constexpr (WS_P == 8 && WS_C == 8 && WS_STAGES == 2 && WS_NBUF == 4) {
     if (N % 64 == 0 && dev_option("ws_tma", 0))
-      return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, true>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
+      return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 1>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
   }
-  return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, false>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
+  // channel-major fills (FILL 2): instantiated for the shipped configurations only
+  if constexpr ((M == 8 && WS_P == 8 && WS_C == 8 && WS_STAGES == 2 && WS_NBUF == 4) || (M == 4 && WS_P == 8 && WS_C == 8 && WS_STAGES == 6 && WS_NBUF == 4)) {
+    if (dev_option("ws_fill", 0) == 2)
+      return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 2>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
+  }
+  return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 0>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
 }
 
 }  // namespace
@@ -266,9 +300,13 @@ int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_
     // shared memory.  Not tuned separately yet.
     const unsigned* in = static_cast<const unsigned*>(in_v);
     const float s2 = fmt.scale * fmt.scale;
-    if (M == 4)
-      return launch_ws_cfg2<4, 8, 8, 6, 4, false>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
-    return launch_ws_cfg2<8, 8, 8, 3, 4, false>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
+    const bool f2 = dev_option("ws_fill", 0) == 2;
+    if (M == 4) {
+      if (f2) return launch_ws_cfg2<4, 8, 8, 6, 4, 2>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
+      return launch_ws_cfg2<4, 8, 8, 6, 4, 0>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
+    }
+    if (f2) return launch_ws_cfg2<8, 8, 8, 3, 4, 2>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
+    return launch_ws_cfg2<8, 8, 8, 3, 4, 0>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
   }
   const float2* in = static_cast<const float2*>(in_v);
   // Producer/consumer split, ring depth and tile buffers, measured at cfg3 with the packed (FFMA2) covariance: 8+8 warps,

@@ -101,8 +101,9 @@ def test_fused_kernel_configurations_are_bit_identical(full):
     torch = full["torch"]
     L = _lib.lib()
 
-    def select(split, stages, nbuf, reserve=0, tma=0):
+    def select(split, stages, nbuf, reserve=0, tma=0, fill=0):
         L.doa_cuda_dev_set(b"ws_tma", tma)
+        L.doa_cuda_dev_set(b"ws_fill", fill)       # 2: channel-major ring fills (one address + immediates per lane)
         L.doa_cuda_dev_set(b"ws_split", split); L.doa_cuda_dev_set(b"ws_stages", stages); L.doa_cuda_dev_set(b"ws_nbuf", nbuf)
         L.doa_cuda_dev_set(b"chain_sms_reserve", reserve)
 
@@ -113,7 +114,7 @@ def test_fused_kernel_configurations_are_bit_identical(full):
             ref = [t.clone() for t in full["ch"].run_device(x)]
             assert full["ch"].launches() == 1
             for cfg in ((412, 3, 2), (412, 5, 2), (416, 4, 2), (610, 3, 2), (812, 3, 2), (808, 3, 2), (808, 3, 3), (808, 2, 5), (808, 2, 4, 2),
-                        (808, 2, 4, 147), (808, 2, 4, 0, 1)):
+                        (808, 2, 4, 147), (808, 2, 4, 0, 1), (808, 2, 4, 0, 0, 2)):
                 select(*cfg)
                 got = full["ch"].run_device(x)
                 assert full["ch"].launches() == 1, cfg

@@ -173,3 +173,29 @@ def test_error_behaviour_of_set_input_format():
     assert ac.work(np.zeros((4, 10, 2), np.int16)).shape == (0, 16)         # shorter than one snapshot: no frames
     out = ac.work(np.full((4, 64, 2), 16384, np.int16))                     # x = 0.5 + 0.5j everywhere: R = 0.5
     assert np.array_equal(out, np.full((1, 16), 0.5 + 0j, np.complex64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,T,P,K,N", [(8, 3, 1024, 3, 200), (8, 2, 512, 2, 2048), (4, 1, 512, 1, 136), (4, 2, 1024, 2, 1024)])
+def test_channel_major_ring_fills_change_nothing(M, T, P, K, N):
+    """Dev knob ws_fill = 2 (a producer lane fills ONE channel with immediates on a single address instead of one slot of every
+    channel): same ring contents, hence the same bits, for both sample formats, ragged last chunk (N % 64 != 0) included."""
+    import torch
+    import gr_doa_b200 as doa
+    from gr_doa_b200 import synth
+    L = doa._lib.lib()
+    B = 900
+    fr, _ = synth.frames_numpy(B, M, N, list(np.linspace(50.0, 130.0, T)), snr_db=10.0, seed=M + N)
+    q = quantise(fr)
+    ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
+    try:
+        for fmt, x in (("fc32", torch.from_numpy(to_fc32(q, S15)).cuda()), ("sc16", torch.from_numpy(q).cuda())):
+            ch.set_input_format(fmt, S15)
+            L.doa_cuda_dev_set(b"ws_fill", 0)
+            ref = [t.clone() for t in ch.run_device(x)]
+            L.doa_cuda_dev_set(b"ws_fill", 2)
+            got = ch.run_device(x)
+            assert ch.launches() == 1
+            assert all(torch.equal(a, b) for a, b in zip(got, ref)), fmt
+    finally:
+        L.doa_cuda_dev_set(b"ws_fill", 0)

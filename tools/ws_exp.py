@@ -9,10 +9,11 @@ L = _lib.lib()
 B, M, N, T, P, K = 65536, 8, 2048, 3, 4096, 3
 x, _ = synth.frames_torch(B, M, N, [40.0, 90.0, 140.0], jitter_deg=2.0, device="cuda", chunk=2048)
 ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
-cfgs = sys.argv[1:] or ["80824"]            # a trailing 't' = bulk (TMA) ring fills instead of per-lane cp.async (80824 only)
+cfgs = sys.argv[1:] or ["80824"]            # a trailing 't' = bulk (TMA) ring fills instead of per-lane cp.async (80824 only); 'c' = channel-major fills
 def select(cs):
     L.doa_cuda_dev_set(b"ws_tma", 1 if cs.endswith("t") else 0)
-    c = int(cs.rstrip("t"))
+    L.doa_cuda_dev_set(b"ws_fill", 2 if cs.endswith("c") else 0)
+    c = int(cs.rstrip("tc"))
     L.doa_cuda_dev_set(b"ws_split", c // 100); L.doa_cuda_dev_set(b"ws_stages", (c // 10) % 10); L.doa_cuda_dev_set(b"ws_nbuf", c % 10)
 ref, same, times, launches = None, {}, {c: [] for c in cfgs}, {}
 for c in cfgs:
