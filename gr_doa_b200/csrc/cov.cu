@@ -11,7 +11,8 @@
 // M <= 8 the kernel is HBM-bound on B200.
 //
 // cov_tiled_kernel (any M <= 64): one CTA per frame, time tiles staged in shared memory, 4x4 complex register
-// blocks over the lower block triangle, slices of the tile's time axis per thread, shared-memory fold at the end.
+// blocks over the lower block triangle, slices of the tile's time axis per thread, fixed-order shared-memory fold at the end
+// (no atomics: the result does not depend on the schedule).
 #include "cov_device.cuh"
 
 #include <algorithm>
@@ -354,8 +355,10 @@ cov_tiled_kernel(const S* __restrict__ in, long long frame_stride, long long cha
   const int nbp = nb * (nb + 1) / 2;    // lower block triangle
   const int TS = max(1, min(CT_TT, CT_THREADS / nbp));   // time slices per block pair
   const int LDT = CT_TT + 1;            // padded row stride (float2 units)
-  float2* tile = smem;                  // [Mp][LDT]
-  float* Racc = reinterpret_cast<float*>(smem + (size_t)Mp * LDT);   // [Mp*Mp*2] folded sums (re,im), row r col c at (r*Mp+c)*2
+  float2* tile = smem;                  // [Mp][LDT]; after the time loop the same memory holds the threads' partial blocks
+  float* part = reinterpret_cast<float*>(smem);                       // [32][CT_THREADS]: float q of thread t at q*CT_THREADS + t
+  const size_t tile_f2 = max((size_t)Mp * LDT, (size_t)16 * CT_THREADS);
+  float* Racc = reinterpret_cast<float*>(smem + tile_f2);            // [Mp*Mp*2] folded sums (re,im), row r col c at (r*Mp+c)*2
 
   const int tid = threadIdx.x;
   const int item_bp = tid / TS, ts = tid % TS;
@@ -375,7 +378,6 @@ cov_tiled_kernel(const S* __restrict__ in, long long frame_stride, long long cha
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) { are[i][j] = 0.f; aim[i][j] = 0.f; }
-    for (int i = tid; i < Mp * Mp * 2; i += CT_THREADS) Racc[i] = 0.f;
 
     for (int t0 = 0; t0 < N; t0 += CT_TT) {
       __syncthreads();
@@ -403,16 +405,27 @@ cov_tiled_kernel(const S* __restrict__ in, long long frame_stride, long long cha
         }
       }
     }
-    __syncthreads();
+    __syncthreads();                      // the tile is dead: park every thread's 4 x 4 partial block in its place
     if (active) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int r = bi * 4 + i, c = bj * 4 + j;
-          atomicAdd(&Racc[(r * Mp + c) * 2], are[i][j]);
-          atomicAdd(&Racc[(r * Mp + c) * 2 + 1], aim[i][j]);
+          part[((i * 4 + j) * 2) * CT_THREADS + tid] = are[i][j];
+          part[((i * 4 + j) * 2 + 1) * CT_THREADS + tid] = aim[i][j];
         }
+    }
+    __syncthreads();
+    // fold the TS time slices of every block pair in slice order (deterministic, unlike atomics)
+    for (int e = tid; e < nbp * 32; e += CT_THREADS) {
+      const int p = e >> 5, q = e & 31;
+      float acc = 0.f;
+      for (int s2 = 0; s2 < TS; ++s2) acc += part[q * CT_THREADS + p * TS + s2];
+      int b = (int)((sqrtf(8.0f * p + 1.0f) - 1.0f) * 0.5f);
+      while ((b + 1) * (b + 2) / 2 <= p) ++b;
+      while (b * (b + 1) / 2 > p) --b;
+      const int r = b * 4 + (q >> 3), c = (p - b * (b + 1) / 2) * 4 + ((q >> 1) & 3);
+      Racc[(r * Mp + c) * 2 + (q & 1)] = acc;
     }
     __syncthreads();
     // Racc holds R(r,c) = sum x_r conj(x_c) for block-lower entries (bi >= bj); mirror the rest.
@@ -457,8 +470,9 @@ template <typename S>
 int launch_tiled(const S* in, long long frame_stride, long long chan_stride, int M, int N, int nframes, float2* out,
                  float scale, float bscale, int avg_method, cudaStream_t st, const float2* gains) {
   const int Mp = ((M + 3) / 4) * 4;
-  const size_t smem = (size_t)Mp * (CT_TT + 1) * sizeof(float2) + (size_t)Mp * Mp * 2 * sizeof(float);
-  cudaFuncSetAttribute(cov_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  const size_t tile_f2 = std::max((size_t)Mp * (CT_TT + 1), (size_t)16 * CT_THREADS);   // time tile, later the partial blocks
+  const size_t smem = tile_f2 * sizeof(float2) + (size_t)Mp * Mp * 2 * sizeof(float);
+  cudaFuncSetAttribute(cov_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int blocks = min(nframes, num_sms() * 4);
   cov_tiled_kernel<S><<<blocks, CT_THREADS, smem, st>>>(in, frame_stride, chan_stride, M, N, nframes, out, scale, bscale,
                                                         avg_method, gains);

@@ -177,6 +177,25 @@ def test_covariance_ragged_streams(doa, oracle, M, N, overlap, avg):
     assert parity.rel_fro(got, exp) <= parity.COV_REL_FRO
 
 
+@pytest.mark.parametrize("M,N", [(2, 64), (4, 256), (8, 200), (16, 192), (16, 255), (12, 300), (32, 256), (64, 129), (64, 512)])
+def test_covariance_is_deterministic_and_frame_independent(doa, torch_cuda, M, N):
+    """Every covariance kernel family (one warp, warp pair, tiled, tensor core) returns the same bits run after run, and a
+    frame's matrix does not depend on which other frames share the launch (the property frame sharding relies on)."""
+    from gr_doa_b200 import synth
+    B = 301
+    fr, _ = synth.frames_numpy(B, M, N, [70.0], snr_db=10.0, seed=M + N)
+    x = torch_cuda.from_numpy(fr).cuda()
+    ac = doa.autocorrelate(M, N, 0, 1, max_frames=B)
+    ref = ac.work_device(x).clone()
+    for _ in range(3):
+        assert torch_cuda.equal(ac.work_device(x).view(torch_cuda.float32), ref.view(torch_cuda.float32))
+    perm = torch_cuda.randperm(B, device="cuda")
+    got = ac.work_device(x[perm].contiguous())
+    assert torch_cuda.equal(got.view(torch_cuda.float32), ref[perm].view(torch_cuda.float32))
+    one = ac.work_device(x[7:8].contiguous())
+    assert torch_cuda.equal(one.view(torch_cuda.float32), ref[7:8].view(torch_cuda.float32))
+
+
 @pytest.mark.parametrize("M,T,P,K", [(6, 2, 1000, 2), (5, 1, 333, 1), (12, 4, 2048, 4), (8, 3, 4096, 5), (8, 2, 1024, 8),
                                      (32, 4, 1024, 4), (3, 1, 100, 2)])
 def test_generic_sizes_chain(doa, oracle, M, T, P, K):
