@@ -357,3 +357,56 @@ class DoaChain(_Block):
         check(self._L.doa_cuda_chain_run_streams(self._h, ptrs, nframes, val.ctypes.data, loc.ctypes.data, bins.ctypes.data),
               self._h)
         return val, loc, bins
+
+
+class DoaChainMulti(_Block):
+    """DoaChain over several GPUs from ONE process (doa_cuda_multi_*): a batch of independent host frames is cut into contiguous
+    blocks, one per entry of `devices`; every device runs the fused chain on its block concurrently and writes its peaks into
+    the shared output arrays -- per frame the same bits as DoaChain on one device."""
+
+    def __init__(self, inputs, snapshot_size, overlap_size, avg_method, norm_spacing, num_targets, pspectrum_len,
+                 num_max_vals, x_min=0.0, x_max=180.0, devices=None, max_frames_per_device=4096):
+        super().__init__()
+        if devices is None:
+            devices = list(range(int(self._L.doa_cuda_device_count())))
+        self.devices = [int(d) for d in devices]
+        self.inputs, self.snapshot_size, self.overlap_size = inputs, snapshot_size, overlap_size
+        self.K, self.max_frames = num_max_vals, max_frames_per_device * max(1, len(self.devices))
+        dv = (C.c_int * max(1, len(self.devices)))(*self.devices)
+        self._created(self._L.doa_cuda_multi_create(C.byref(self._h), inputs, snapshot_size, overlap_size, int(avg_method),
+                                                    C.c_float(norm_spacing), num_targets, pspectrum_len, num_max_vals,
+                                                    C.c_float(x_min), C.c_float(x_max), dv, len(self.devices),
+                                                    max_frames_per_device))
+
+    def blocks(self, nframes):
+        """[(first, count)] per device for a batch of nframes."""
+        out = []
+        for g in range(len(self.devices)):
+            a, b = C.c_int(), C.c_int()
+            check(self._L.doa_cuda_multi_block(self._h, nframes, g, C.byref(a), C.byref(b)), self._h)
+            out.append((a.value, b.value))
+        return out
+
+    def run_host(self, frames, out=None):
+        """frames: host [B][M][N] complex64 (numpy or pinned torch tensor; sc16 format: int16 [B][M][N][2]).
+        Returns numpy (val, loc, bins)."""
+        if hasattr(frames, "data_ptr"):
+            ptr, B = frames.data_ptr(), frames.shape[0]
+        else:
+            frames = self._samples(frames)
+            ptr, B = frames.ctypes.data, frames.shape[0]
+        if out is None:
+            out = (np.empty((B, self.K), np.float32), np.empty((B, self.K), np.float32), np.empty((B, self.K), np.int32))
+        p = [o.data_ptr() if hasattr(o, "data_ptr") else o.ctypes.data for o in out]
+        check(self._L.doa_cuda_multi_run(self._h, ptr, B, p[0], p[1], p[2]), self._h)
+        return out
+
+    def run_streams(self, streams, nframes):
+        """streams: M channel arrays holding hop*(nframes-1)+snapshot_size samples each (a general_work() view)."""
+        xs = [self._samples(x) for x in streams]
+        val, loc, bins = (np.empty((nframes, self.K), np.float32), np.empty((nframes, self.K), np.float32),
+                          np.empty((nframes, self.K), np.int32))
+        ptrs = (C.c_void_p * self.inputs)(*[x.ctypes.data for x in xs])
+        check(self._L.doa_cuda_multi_run_streams(self._h, ptrs, nframes, val.ctypes.data, loc.ctypes.data, bins.ctypes.data),
+              self._h)
+        return val, loc, bins

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 
 namespace doa {
 
@@ -65,7 +66,7 @@ void build_x_axis(int len, float x_min, float x_max, std::vector<float>& x) {
 
 using namespace doa;
 
-enum Kind { K_AUTOCORR = 1, K_MUSIC, K_ROOTMUSIC, K_FLM, K_CHAIN, K_CALIB };
+enum Kind { K_AUTOCORR = 1, K_MUSIC, K_ROOTMUSIC, K_FLM, K_CHAIN, K_CALIB, K_MULTI };
 
 struct Lane {   // one stream's worth of buffers (the chain's host path double-buffers two of these)
   cudaStream_t stream = nullptr;
@@ -91,6 +92,7 @@ struct doa_cuda_handle {
   std::string err;
   int launches = 0;
   bool profiling = false;
+  std::vector<doa_cuda_handle*> children;   // K_MULTI: one chain handle per listed device
   std::vector<cudaEvent_t> ev;   // profiling: 4 events per recorded chain call (ring of PROF_SETS calls)
   int prof_calls = 0;
 };
@@ -118,6 +120,8 @@ static void free_lane(Lane& l) {
 
 extern "C" void doa_cuda_destroy(doa_cuda_handle* h) {
   if (!h) return;
+  for (doa_cuda_handle* c : h->children) doa_cuda_destroy(c);
+  h->children.clear();
   cudaSetDevice(h->device);
   for (int i = 0; i < 2; ++i) free_lane(h->lane[i]);
   cudaFree(h->d_z); cudaFree(h->d_V); cudaFree(h->d_x); cudaFree(h->d_zpair); cudaFree(h->d_gains);
@@ -192,6 +196,13 @@ int doa_cuda_dev_set(const char* key, int value) {
 
 // ---- channel gains ------------------------------------------------------------------------------------------------
 int doa_cuda_set_channel_gains(doa_cuda_handle* h, const float* gains) {
+  if (h && h->kind == K_MULTI) {
+    for (doa_cuda_handle* c : h->children) {
+      const int rc = doa_cuda_set_channel_gains(c, gains);
+      if (rc) return fail(h, rc, c->err);
+    }
+    return DOA_CUDA_OK;
+  }
   if (!h || (h->kind != K_AUTOCORR && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
   CK(h, cudaSetDevice(h->device));
   // runs already queued on the handle's streams may still read the old gains
@@ -206,6 +217,14 @@ int doa_cuda_set_channel_gains(doa_cuda_handle* h, const float* gains) {
 
 // ---- input sample format ------------------------------------------------------------------------------------------
 int doa_cuda_set_input_format(doa_cuda_handle* h, int format, float scale) {
+  if (h && h->kind == K_MULTI) {
+    for (doa_cuda_handle* c : h->children) {
+      const int rc = doa_cuda_set_input_format(c, format, scale);
+      if (rc) return fail(h, rc, c->err);
+    }
+    h->fmt = h->children[0]->fmt;
+    return DOA_CUDA_OK;
+  }
   if (!h || (h->kind != K_AUTOCORR && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
   if (format != DOA_CUDA_FMT_FC32 && format != DOA_CUDA_FMT_SC16) return fail(h, DOA_CUDA_EINVAL, "unknown input format");
   if (format == DOA_CUDA_FMT_SC16 && !(std::isfinite(scale) && scale > 0.0f))
@@ -658,6 +677,111 @@ int doa_cuda_chain_run_streams(doa_cuda_handle* h, const void* const* in_host, i
   CK(h, cudaMemcpyAsync(out_loc_host, l.loc, sizeof(float) * nk, cudaMemcpyDeviceToHost, l.stream));
   if (out_bin_host) CK(h, cudaMemcpyAsync(out_bin_host, l.bin, sizeof(int) * nk, cudaMemcpyDeviceToHost, l.stream));
   CK(h, cudaStreamSynchronize(l.stream));
+  return DOA_CUDA_OK;
+}
+
+// ---- every GPU of the box from ONE process (a GNU Radio flowgraph is one process) --------------------------------------
+// Frames are independent (lib/autocorrelate_impl.cc:92, lib/MUSIC_lin_array_impl.cc:121, lib/find_local_max_impl.cc:179), so a
+// batch is cut into contiguous blocks of frames, one per listed device; every device runs the chain on its block from the
+// caller's host buffer (its own PCIe link, its own streams) and writes its K peaks per frame straight into the caller's
+// output arrays at the block's offset.  That write IS the gather: nothing else crosses between devices, so no collective
+// is needed in this single-process form (the one-process-per-GPU form gathers with NCCL, gr_doa_b200/sharding.py).
+int doa_cuda_multi_create(doa_cuda_handle** out, int inputs, int snapshot_size, int overlap_size, int avg_method,
+                          float norm_spacing, int num_targets, int pspectrum_len, int num_max_vals, float x_min, float x_max,
+                          const int* devices, int ndevices, int max_frames_per_device) {
+  if (!out) return fail(nullptr, DOA_CUDA_EINVAL, "null handle pointer");
+  *out = nullptr;
+  if (!devices || ndevices < 1 || ndevices > 64) return fail(nullptr, DOA_CUDA_EINVAL, "need 1 <= ndevices <= 64 and a device list");
+  doa_cuda_handle* h = nullptr;
+  int rc = begin_create(out, h, K_MULTI, devices[0], max_frames_per_device);
+  if (rc) return rc;
+  h->M = inputs; h->N = snapshot_size; h->K = num_max_vals; h->overlap = overlap_size; h->hop = snapshot_size - overlap_size;
+  for (int g = 0; g < ndevices; ++g) {
+    doa_cuda_handle* c = nullptr;
+    rc = doa_cuda_chain_create(&c, inputs, snapshot_size, overlap_size, avg_method, norm_spacing, num_targets, pspectrum_len,
+                               num_max_vals, x_min, x_max, devices[g], max_frames_per_device);
+    if (rc) { doa_cuda_destroy(h); return rc; }   // g_create_err holds the child's text
+    h->children.push_back(c);
+  }
+  h->max_frames = max_frames_per_device * ndevices;
+  *out = h;
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_multi_device_count(const doa_cuda_handle* h) { return (h && h->kind == K_MULTI) ? (int)h->children.size() : DOA_CUDA_EINVAL; }
+
+// Frames [first, first + count) of device g out of nframes over G devices: contiguous, sizes differ by at most one.
+static void multi_block(int nframes, int G, int g, int* first, int* count) {
+  const int per = nframes / G, rem = nframes % G;
+  *first = g * per + std::min(g, rem);
+  *count = per + (g < rem ? 1 : 0);
+}
+
+int doa_cuda_multi_block(const doa_cuda_handle* h, int nframes, int index, int* first, int* count) {
+  if (!h || h->kind != K_MULTI || nframes < 0 || index < 0 || index >= (int)h->children.size() || !first || !count) return DOA_CUDA_EINVAL;
+  multi_block(nframes, (int)h->children.size(), index, first, count);
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_multi_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_val_host, void* out_loc_host,
+                       void* out_bin_host) {
+  if (!h || h->kind != K_MULTI) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames_per_device * ndevices");
+  const int G = (int)h->children.size();
+  const size_t frame_bytes = (size_t)h->M * h->N * h->children[0]->sample_bytes();
+  std::vector<int> rcs(G, DOA_CUDA_OK);
+  auto work = [&](int g) {
+    int first = 0, count = 0;
+    multi_block(nframes, G, g, &first, &count);
+    if (count == 0) return;
+    const size_t off = (size_t)first * h->K;
+    rcs[g] = doa_cuda_chain_run(h->children[g], (const char*)in_host + (size_t)first * frame_bytes, count,
+                                (float*)out_val_host + off, (float*)out_loc_host + off,
+                                out_bin_host ? (void*)((int*)out_bin_host + off) : nullptr);
+  };
+  std::vector<std::thread> th;
+  for (int g = 1; g < G; ++g) th.emplace_back(work, g);   // one host thread per additional device; the caller's drives device 0
+  work(0);
+  for (auto& t : th) t.join();
+  h->launches = 0;
+  for (int g = 0; g < G; ++g) {
+    if (rcs[g]) return fail(h, rcs[g], "device " + std::to_string(h->children[g]->device) + ": " + h->children[g]->err);
+    h->launches += h->children[g]->launches;
+  }
+  return DOA_CUDA_OK;
+}
+
+// Streaming form (what a GNU Radio general_work() holds: `inputs` channel pointers, frame i at hop * i): device g gets the
+// channel pointers advanced to its first frame; the `overlap` samples its last frame shares with the next device's first are
+// simply read by both (the halo of SURVEY section 8(e), free here because every device reads the same host buffer).
+int doa_cuda_multi_run_streams(doa_cuda_handle* h, const void* const* in_host, int nframes, void* out_val_host,
+                               void* out_loc_host, void* out_bin_host) {
+  if (!h || h->kind != K_MULTI) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames_per_device * ndevices");
+  const int G = (int)h->children.size();
+  const size_t sb = h->children[0]->sample_bytes();
+  std::vector<int> rcs(G, DOA_CUDA_OK);
+  auto work = [&](int g) {
+    int first = 0, count = 0;
+    multi_block(nframes, G, g, &first, &count);
+    if (count == 0) return;
+    std::vector<const void*> ptrs(h->M);
+    for (int k = 0; k < h->M; ++k) ptrs[k] = (const char*)in_host[k] + (size_t)first * h->hop * sb;
+    const size_t off = (size_t)first * h->K;
+    rcs[g] = doa_cuda_chain_run_streams(h->children[g], ptrs.data(), count, (float*)out_val_host + off, (float*)out_loc_host + off,
+                                        out_bin_host ? (void*)((int*)out_bin_host + off) : nullptr);
+  };
+  std::vector<std::thread> th;
+  for (int g = 1; g < G; ++g) th.emplace_back(work, g);
+  work(0);
+  for (auto& t : th) t.join();
+  h->launches = 0;
+  for (int g = 0; g < G; ++g) {
+    if (rcs[g]) return fail(h, rcs[g], "device " + std::to_string(h->children[g]->device) + ": " + h->children[g]->err);
+    h->launches += h->children[g]->launches;
+  }
   return DOA_CUDA_OK;
 }
 

@@ -35,14 +35,22 @@ music_chain_impl::music_chain_impl(int inputs, int snapshot_size, int overlap_si
     : gr::block("music_chain", gr::io_signature::make(inputs, inputs, sc16_scale > 0.0f ? 2 * sizeof(short) : sizeof(gr_complex)),
                 gr::io_signature::make2(2, 2, num_max_vals * sizeof(float), num_max_vals * sizeof(float))),
       d_num_inputs(inputs), d_snapshot_size(snapshot_size), d_overlap_size(overlap_size), d_num_max_vals(num_max_vals),
-      d_item_bytes(sc16_scale > 0.0f ? 2 * sizeof(short) : sizeof(gr_complex)), d_cuda(NULL), d_ptrs(inputs) {
+      d_item_bytes(sc16_scale > 0.0f ? 2 * sizeof(short) : sizeof(gr_complex)), d_cuda(NULL), d_multi(false), d_ptrs(inputs) {
   d_nonoverlap_size = d_snapshot_size - d_overlap_size;
   set_history(d_overlap_size + 1);
   d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", 8192);
-  doa_require_created(doa_cuda_chain_create(&d_cuda, inputs, snapshot_size, overlap_size, avg_method, norm_spacing, num_targets,
-                                            pspectrum_len, num_max_vals, x_min, x_max, doa_env_int("DOA_CUDA_DEVICE", 0),
-                                            d_max_frames),
-                      "doa.music_chain");
+  const std::vector<int> devs = doa_env_devices();
+  d_multi = devs.size() > 1;
+  if (d_multi) {   /* one block instance, every listed GPU: frames of a work() call are cut into one block per device */
+    const int per_dev = (d_max_frames + (int)devs.size() - 1) / (int)devs.size();
+    doa_require_created(doa_cuda_multi_create(&d_cuda, inputs, snapshot_size, overlap_size, avg_method, norm_spacing, num_targets,
+                                              pspectrum_len, num_max_vals, x_min, x_max, &devs[0], (int)devs.size(), per_dev),
+                        "doa.music_chain");
+  } else {
+    doa_require_created(doa_cuda_chain_create(&d_cuda, inputs, snapshot_size, overlap_size, avg_method, norm_spacing, num_targets,
+                                              pspectrum_len, num_max_vals, x_min, x_max, devs[0], d_max_frames),
+                        "doa.music_chain");
+  }
   if (sc16_scale > 0.0f && doa_cuda_set_input_format(d_cuda, DOA_CUDA_FMT_SC16, sc16_scale) != DOA_CUDA_OK) {
     const std::string msg = std::string("doa.music_chain: ") + doa_cuda_last_error(d_cuda);
     doa_cuda_destroy(d_cuda);
@@ -77,8 +85,11 @@ int music_chain_impl::general_work(int noutput_items, gr_vector_int& ninput_item
     const int n = std::min(d_max_frames, noutput_items - done);
     for (int k = 0; k < d_num_inputs; k++)
       d_ptrs[k] = (const char*)input_items[k] + (size_t)done * d_nonoverlap_size * d_item_bytes;
-    if (doa_cuda_chain_run_streams(d_cuda, &d_ptrs[0], n, out1 + (size_t)done * d_num_max_vals,
-                                   out2 + (size_t)done * d_num_max_vals, NULL) != DOA_CUDA_OK) {
+    const int rc = d_multi ? doa_cuda_multi_run_streams(d_cuda, &d_ptrs[0], n, out1 + (size_t)done * d_num_max_vals,
+                                                        out2 + (size_t)done * d_num_max_vals, NULL)
+                           : doa_cuda_chain_run_streams(d_cuda, &d_ptrs[0], n, out1 + (size_t)done * d_num_max_vals,
+                                                        out2 + (size_t)done * d_num_max_vals, NULL);
+    if (rc != DOA_CUDA_OK) {
       std::fprintf(stderr, "doa.music_chain: %s\n", doa_cuda_last_error(d_cuda));
       return -1;  // WORK_DONE
     }

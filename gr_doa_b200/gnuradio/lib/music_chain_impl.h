@@ -10,6 +10,7 @@ class music_chain_impl : public music_chain {
   int d_nonoverlap_size, d_max_frames;
   const size_t d_item_bytes;   /* sizeof(gr_complex), or 4 for sc16 items */
   doa_cuda_handle* d_cuda;
+  bool d_multi;                /* several devices (DOA_CUDA_DEVICES): doa_cuda_multi_* instead of doa_cuda_chain_* */
   std::vector<const void*> d_ptrs;
 
  public:

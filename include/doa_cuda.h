@@ -119,6 +119,28 @@ int doa_cuda_calibrate_create(doa_cuda_handle** out, float norm_spacing, int num
 int doa_cuda_calibrate_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_host);
 int doa_cuda_calibrate_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_dev, void* cuda_stream);
 
+/* ---- the fused chain on several GPUs from one process --------------------------------------
+ * A GNU Radio flowgraph is one process; this form lets one block instance use every GPU of the box.  Frames are independent
+ * in all four reference blocks (lib/autocorrelate_impl.cc:92, lib/MUSIC_lin_array_impl.cc:121,
+ * lib/rootMUSIC_linear_array_impl.cc:105, lib/find_local_max_impl.cc:179), so a batch of independent frames ([nframes][M][N]
+ * host memory, as doa_cuda_chain_run) is cut into contiguous blocks, one per entry of `devices` (sizes differ by at most one
+ * frame; doa_cuda_multi_block reports them).  Each device copies and processes its block concurrently (one host thread per
+ * device inside the call) and writes its peaks into the caller's output arrays at the block's offset -- that is the whole
+ * gather, so per-frame results are bit-identical to doa_cuda_chain_run on one device.  A device may be listed more than once
+ * (that many independent stream sets on it).  set_channel_gains / set_input_format apply to every device.
+ * The one-process-per-GPU form (torchrun, NCCL gather of device-resident peaks) lives in gr_doa_b200/sharding.py. */
+int doa_cuda_multi_create(doa_cuda_handle** h, int inputs, int snapshot_size, int overlap_size, int avg_method,
+                          float norm_spacing, int num_targets, int pspectrum_len, int num_max_vals, float x_min, float x_max,
+                          const int* devices, int ndevices, int max_frames_per_device);
+int doa_cuda_multi_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_val_host, void* out_loc_host,
+                       void* out_bin_host /* may be NULL */);
+/* Streaming form, arguments as doa_cuda_chain_run_streams (`inputs` channel pointers, frame i at hop*i): each device reads
+ * its block of frames from the same host streams, overlap samples included. */
+int doa_cuda_multi_run_streams(doa_cuda_handle* h, const void* const* in_host, int nframes, void* out_val_host,
+                               void* out_loc_host, void* out_bin_host /* may be NULL */);
+int doa_cuda_multi_device_count(const doa_cuda_handle* h);
+int doa_cuda_multi_block(const doa_cuda_handle* h, int nframes, int index, int* first, int* count);
+
 /* ---- channel gains in front of the covariance ---------------------------------------------
  * Replaces the antenna_correction block (lib/antenna_correction_impl.cc:47-99: out_k[i] = g_k * in_k[i]) and
  * python/phase_correct_hier.py:91-102 (g_k = e^{j phi_k}) when they feed autocorrelate: instead of two more passes over the

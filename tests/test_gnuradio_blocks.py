@@ -130,3 +130,30 @@ def test_fake_scheduler_music_chain_fed_sc16_items(tmp_path):
     ref = [np.fromfile(str(tmp_path / "out") + ext, np.float32).reshape(n, K) for ext in (".cval.f32", ".cloc.f32")]
     assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
     assert np.abs(got[1] - 60.0).max() < 2.0
+
+
+@pytest.mark.gpu
+def test_fake_scheduler_music_chain_over_a_device_list(tmp_path):
+    """DOA_CUDA_DEVICES: one doa.music_chain instance spreads each work() call's frames over the listed devices
+    (doa_cuda_multi_run_streams: every device reads its block, overlap included, from the scheduler's buffers).  Same
+    scheduler calls, same peaks, bit for bit, as on one device.  (A device listed twice = two independent stream sets on it,
+    which is how a one-GPU box exercises the sharding.)"""
+    import torch
+    from gr_doa_b200 import synth
+    exe = harness()
+    M, N, overlap, avg, T, P, K, n = 8, 256, 32, 0, 2, 1024, 2, 200
+    x = synth.stream_numpy(n, M, N, overlap, [50.0, 110.0], seed=17)
+    inp = tmp_path / "in.c64"
+    x.astype(np.complex64).tofile(inp)
+    outs = {}
+    nd = torch.cuda.device_count()
+    lists = {"one": "0", "twice": "0,0", "all": ",".join(str(i) for i in range(nd)) + ",0"}
+    for tag, devs in lists.items():
+        env = dict(os.environ, DOA_CUDA_DEVICES=devs)
+        r = subprocess.run([exe, str(inp), str(M), str(N), str(overlap), str(avg), "0.5", str(T), str(P), str(K), str(tmp_path / tag)],
+                           capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr + r.stdout
+        outs[tag] = [np.fromfile(str(tmp_path / tag) + ext, np.float32).reshape(n, K) for ext in (".cval.f32", ".cloc.f32")]
+    for tag in ("twice", "all"):
+        assert np.array_equal(outs[tag][0], outs["one"][0]) and np.array_equal(outs[tag][1], outs["one"][1])
+    assert np.abs(np.sort(outs["one"][1], 1) - np.array([50.0, 110.0])[None, :]).max() < 2.0
