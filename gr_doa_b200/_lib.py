@@ -44,6 +44,10 @@ SYMBOLS = {
     "doa_cuda_set_channel_gains": (_i, [_vp, _vp]),
     "doa_cuda_antenna_gains_from_file": (_i, [C.c_char_p, _i, _vp]),
     "doa_cuda_set_input_format": (_i, [_vp, _i, _f]),
+    "doa_cuda_rootchain_create": (_i, [_hp, _i, _i, _i, _i, _f, _i, _i, _i]),
+    "doa_cuda_rootchain_run_device": (_i, [_vp, _vp, _ll, _ll, _i, _vp, _vp]),
+    "doa_cuda_rootchain_run": (_i, [_vp, _vp, _i, _vp]),
+    "doa_cuda_rootchain_run_streams": (_i, [_vp, _hp, _i, _vp]),
     "doa_cuda_multi_create": (_i, [_hp, _i, _i, _i, _i, _f, _i, _i, _i, _f, _f, C.POINTER(_i), _i, _i]),
     "doa_cuda_multi_run": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "doa_cuda_multi_run_streams": (_i, [_vp, _hp, _i, _vp, _vp, _vp]),

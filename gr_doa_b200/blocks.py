@@ -410,3 +410,38 @@ class DoaChainMulti(_Block):
         check(self._L.doa_cuda_multi_run_streams(self._h, ptrs, nframes, val.ctypes.data, loc.ctypes.data, bins.ctypes.data),
               self._h)
         return val, loc, bins
+
+
+class RootMusicChain(_Block):
+    """autocorrelate -> rootMUSIC_linear_array in one call (doa_cuda_rootchain_*): samples in, num_targets ascending angles
+    per frame out; the covariance never leaves the device."""
+
+    def __init__(self, inputs, snapshot_size, overlap_size, avg_method, norm_spacing, num_targets, device=0, max_frames=4096):
+        super().__init__()
+        self.inputs, self.snapshot_size, self.overlap_size = inputs, snapshot_size, overlap_size
+        self.hop, self.T, self.max_frames = snapshot_size - overlap_size, num_targets, max_frames
+        self._created(self._L.doa_cuda_rootchain_create(C.byref(self._h), inputs, snapshot_size, overlap_size, int(avg_method),
+                                                        C.c_float(norm_spacing), num_targets, device, max_frames))
+
+    def run_device(self, x, frame_stride=None, chan_stride=None, nframes=None):
+        import torch
+        if frame_stride is None:
+            B, M, N = x.shape[:3]
+            frame_stride, chan_stride, nframes = M * N, N, B
+        out = torch.empty((nframes, self.T), dtype=torch.float32, device=x.device)
+        check(self._L.doa_cuda_rootchain_run_device(self._h, x.data_ptr(), frame_stride, chan_stride, nframes, out.data_ptr(),
+                                                    _stream_ptr()), self._h)
+        return out
+
+    def run_host(self, frames):
+        frames = self._samples(frames)
+        out = np.empty((frames.shape[0], self.T), np.float32)
+        check(self._L.doa_cuda_rootchain_run(self._h, frames.ctypes.data, frames.shape[0], out.ctypes.data), self._h)
+        return out
+
+    def run_streams(self, streams, nframes):
+        xs = [self._samples(x) for x in streams]
+        out = np.empty((nframes, self.T), np.float32)
+        ptrs = (C.c_void_p * self.inputs)(*[x.ctypes.data for x in xs])
+        check(self._L.doa_cuda_rootchain_run_streams(self._h, ptrs, nframes, out.ctypes.data), self._h)
+        return out

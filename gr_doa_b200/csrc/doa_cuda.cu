@@ -66,7 +66,8 @@ void build_x_axis(int len, float x_min, float x_max, std::vector<float>& x) {
 
 using namespace doa;
 
-enum Kind { K_AUTOCORR = 1, K_MUSIC, K_ROOTMUSIC, K_FLM, K_CHAIN, K_CALIB, K_MULTI };
+enum Kind { K_AUTOCORR = 1, K_MUSIC, K_ROOTMUSIC, K_FLM, K_CHAIN, K_CALIB, K_MULTI, K_ROOTCHAIN };
+static bool takes_samples(int kind) { return kind == K_AUTOCORR || kind == K_CHAIN || kind == K_ROOTCHAIN; }
 
 struct Lane {   // one stream's worth of buffers (the chain's host path double-buffers two of these)
   cudaStream_t stream = nullptr;
@@ -203,7 +204,7 @@ int doa_cuda_set_channel_gains(doa_cuda_handle* h, const float* gains) {
     }
     return DOA_CUDA_OK;
   }
-  if (!h || (h->kind != K_AUTOCORR && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
+  if (!h || !takes_samples(h->kind)) return DOA_CUDA_EINVAL;
   CK(h, cudaSetDevice(h->device));
   // runs already queued on the handle's streams may still read the old gains
   for (int i = 0; i < h->nlanes; ++i) if (h->lane[i].stream) CK(h, cudaStreamSynchronize(h->lane[i].stream));
@@ -225,7 +226,7 @@ int doa_cuda_set_input_format(doa_cuda_handle* h, int format, float scale) {
     h->fmt = h->children[0]->fmt;
     return DOA_CUDA_OK;
   }
-  if (!h || (h->kind != K_AUTOCORR && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
+  if (!h || !takes_samples(h->kind)) return DOA_CUDA_EINVAL;
   if (format != DOA_CUDA_FMT_FC32 && format != DOA_CUDA_FMT_SC16) return fail(h, DOA_CUDA_EINVAL, "unknown input format");
   if (format == DOA_CUDA_FMT_SC16 && !(std::isfinite(scale) && scale > 0.0f))
     return fail(h, DOA_CUDA_EINVAL, "sc16 scale must be finite and > 0");
@@ -676,6 +677,83 @@ int doa_cuda_chain_run_streams(doa_cuda_handle* h, const void* const* in_host, i
   CK(h, cudaMemcpyAsync(out_val_host, l.val, sizeof(float) * nk, cudaMemcpyDeviceToHost, l.stream));
   CK(h, cudaMemcpyAsync(out_loc_host, l.loc, sizeof(float) * nk, cudaMemcpyDeviceToHost, l.stream));
   if (out_bin_host) CK(h, cudaMemcpyAsync(out_bin_host, l.bin, sizeof(int) * nk, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaStreamSynchronize(l.stream));
+  return DOA_CUDA_OK;
+}
+
+// ---- autocorrelate -> rootMUSIC_linear_array without the covariance leaving the device (BASELINE configs[1]) ------------
+// The reference flowgraph's two blocks (lib/autocorrelate_impl.cc:82-118 -> lib/rootMUSIC_linear_array_impl.cc:90-152) as one
+// call: covariance, batched Jacobi + diagonal sums of the noise projector, polynomial roots, root selection; T angles per
+// frame come back.  Same kernels as the separate stages, hence the same bits.
+int doa_cuda_rootchain_create(doa_cuda_handle** out, int inputs, int snapshot_size, int overlap_size, int avg_method,
+                              float norm_spacing, int num_targets, int device, int max_frames) {
+  if (inputs < 2 || inputs > 64) return fail(nullptr, DOA_CUDA_EINVAL, "inputs must be in [2, 64]");
+  if (snapshot_size < 1) return fail(nullptr, DOA_CUDA_EINVAL, "snapshot_size must be > 0");
+  if (overlap_size < 0 || overlap_size >= snapshot_size) return fail(nullptr, DOA_CUDA_EINVAL, "need 0 <= overlap_size < snapshot_size");
+  if (avg_method != 0 && avg_method != 1) return fail(nullptr, DOA_CUDA_EINVAL, "avg_method must be 0 or 1");
+  int rc = check_array(norm_spacing, num_targets, inputs);
+  if (rc) return rc;
+  doa_cuda_handle* h = nullptr;
+  rc = begin_create(out, h, K_ROOTCHAIN, device, max_frames);
+  if (rc) return rc;
+  h->M = inputs; h->N = snapshot_size; h->overlap = overlap_size; h->hop = snapshot_size - overlap_size; h->avg = avg_method;
+  h->d = norm_spacing; h->T = num_targets;
+  Lane& l = h->lane[0];
+  const size_t mm = (size_t)h->M * h->M, n = 2 * (size_t)h->M - 2;
+  const size_t Lpad = (((size_t)(max_frames - 1) * h->hop + h->N) + 1) & ~(size_t)1;
+  l.in_elems = std::max(Lpad * h->M, (size_t)max_frames * h->M * h->N);     // streams or independent frames
+  bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess && dalloc(&l.in, l.in_elems) &&
+            dalloc(&l.R, max_frames * mm) && dalloc(&l.u, (size_t)max_frames * h->M) &&
+            dalloc(&l.aoa, (size_t)max_frames * h->T) && dalloc(&l.scratch, n * n * (size_t)max_frames);
+  return finish_create(out, h, ok);
+}
+
+int doa_cuda_rootchain_run_device(doa_cuda_handle* h, const void* in_dev, long long frame_stride, long long chan_stride,
+                                  int nframes, void* out_aoa_dev, void* cuda_stream) {
+  if (!h || h->kind != K_ROOTCHAIN) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  Lane& l = h->lane[0];
+  int a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains, h->fmt);
+  if (a < 0) return fail(h, a, "covariance launch rejected");
+  int b = launch_noise_subspace(l.R, h->M, h->T, nframes, nullptr, l.u, nullptr, st);
+  if (b < 0) return fail(h, b, "eigendecomposition launch rejected");
+  int c = launch_rootmusic_scratch(l.u, h->M, h->T, h->d, nframes, l.scratch, h->max_frames, (float*)out_aoa_dev, st);
+  if (c < 0) return fail(h, c, "root finder launch rejected");
+  h->launches = a + b + c;
+  CK(h, cudaGetLastError());
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_rootchain_run_streams(doa_cuda_handle* h, const void* const* in_host, int nframes, void* out_aoa_host) {
+  if (!h || h->kind != K_ROOTCHAIN) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  Lane& l = h->lane[0];
+  size_t Lpad = 0;
+  int rc = stage_streams(h, l, in_host, nframes, &Lpad);
+  if (rc) return rc;
+  rc = doa_cuda_rootchain_run_device(h, l.in, h->hop, (long long)Lpad, nframes, l.aoa, l.stream);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(out_aoa_host, l.aoa, sizeof(float) * (size_t)nframes * h->T, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaStreamSynchronize(l.stream));
+  return DOA_CUDA_OK;
+}
+
+int doa_cuda_rootchain_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_aoa_host) {
+  if (!h || h->kind != K_ROOTCHAIN) return DOA_CUDA_EINVAL;
+  if (nframes == 0) return DOA_CUDA_OK;
+  if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  CK(h, cudaSetDevice(h->device));
+  Lane& l = h->lane[0];
+  const size_t fe = (size_t)h->M * h->N;
+  CK(h, cudaMemcpyAsync(l.in, in_host, h->sample_bytes() * fe * nframes, cudaMemcpyHostToDevice, l.stream));
+  int rc = doa_cuda_rootchain_run_device(h, l.in, (long long)fe, h->N, nframes, l.aoa, l.stream);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(out_aoa_host, l.aoa, sizeof(float) * (size_t)nframes * h->T, cudaMemcpyDeviceToHost, l.stream));
   CK(h, cudaStreamSynchronize(l.stream));
   return DOA_CUDA_OK;
 }

@@ -12,7 +12,7 @@ OUT = os.path.join(HERE, "_build", "fake_scheduler")
 def build(force=False):
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     srcs = [os.path.join(HERE, "lib", f) for f in ("autocorrelate_impl.cc", "MUSIC_lin_array_impl.cc",
-                                                   "rootMUSIC_linear_array_impl.cc", "find_local_max_impl.cc", "music_chain_impl.cc", "calibrate_lin_array_impl.cc")]
+                                                   "rootMUSIC_linear_array_impl.cc", "find_local_max_impl.cc", "music_chain_impl.cc", "rootmusic_chain_impl.cc", "calibrate_lin_array_impl.cc")]
     srcs.append(os.path.join(HERE, "harness", "fake_scheduler.cc"))
     deps = srcs + [os.path.join(PKG, "libdoa_cuda.so")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps if os.path.exists(d)):

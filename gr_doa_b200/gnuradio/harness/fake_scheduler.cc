@@ -14,6 +14,7 @@
 #include <doa/MUSIC_lin_array.h>
 #include <doa/autocorrelate.h>
 #include <doa/music_chain.h>
+#include <doa/rootmusic_chain.h>
 #include <doa/find_local_max.h>
 #include <doa/rootMUSIC_linear_array.h>
 
@@ -63,6 +64,14 @@ int main(int argc, char** argv) {
     return 3;
   }
 
+  /* autocorrelate + rootMUSIC_linear_array in one block: autocorrelate's inputs, rootMUSIC's port 0 */
+  gr::doa::rootmusic_chain::sptr rc = gr::doa::rootmusic_chain::make(M, N, overlap, avg, d, T);
+  if (std::getenv("DOA_HARNESS_ANTENNA_CFG")) rc->set_antenna_config(std::getenv("DOA_HARNESS_ANTENNA_CFG"));
+  if (rc->input_signature()->min_streams() != M || rc->output_signature()->sizeof_stream_item(0) != (int)sizeof(float) * T ||
+      (int)rc->history() != overlap + 1) {
+    std::fprintf(stderr, "rootmusic_chain io signature mismatch\n");
+    return 3;
+  }
   /* optional: the sc16-fed fused block next to it */
   gr::doa::music_chain::sptr mc16;
   std::vector<char> raw16;
@@ -88,7 +97,7 @@ int main(int argc, char** argv) {
   /* GNU Radio pre-fills history()-1 zeros in front of the stream; gr-doa's QA vectors are laid out so that the first
    * snapshot starts at sample 0, i.e. the scheduler view is: read pointer at sample 0, `overlap` samples of look-ahead
    * required beyond hop*n.  Emulate exactly that: available = L, a call may produce n frames iff hop*n + overlap <= avail. */
-  std::vector<gr_complex> Rbuf; std::vector<float> spec, val, loc, aoa, cval, cloc, sval, sloc;
+  std::vector<gr_complex> Rbuf; std::vector<float> spec, val, loc, aoa, cval, cloc, sval, sloc, caoa;
   size_t rd = 0;                       /* read pointer (samples) shared by all channels */
   unsigned lcg = 12345;
   size_t frames_total = 0;
@@ -116,6 +125,11 @@ int main(int argc, char** argv) {
       if (need2[0] != need[0]) { std::fprintf(stderr, "music_chain forecast differs from autocorrelate\n"); return 3; }
       gr_vector_void_star out_c(2); out_c[0] = cval.data() + frames_total * (size_t)K; out_c[1] = cloc.data() + frames_total * (size_t)K;
       if (mc->general_work(n, nin, ins, out_c) != n || mc->last_consumed() != hop * n) { std::fprintf(stderr, "music_chain produced/consumed mismatch\n"); return 3; }
+    }
+    {   /* and so does the Root-MUSIC chain block */
+      caoa.resize((frames_total + n) * (size_t)T);
+      gr_vector_void_star out_r(1, caoa.data() + frames_total * (size_t)T);
+      if (rc->general_work(n, nin, ins, out_r) != n || rc->last_consumed() != hop * n) { std::fprintf(stderr, "rootmusic_chain produced/consumed mismatch\n"); return 3; }
     }
     if (mc16) {
       sval.resize((frames_total + n) * (size_t)K); sloc.resize(sval.size());
@@ -147,6 +161,7 @@ int main(int argc, char** argv) {
   dump(prefix + ".aoa.f32", aoa.data(), aoa.size() * sizeof(float));
   dump(prefix + ".cval.f32", cval.data(), cval.size() * sizeof(float));
   dump(prefix + ".cloc.f32", cloc.data(), cloc.size() * sizeof(float));
+  dump(prefix + ".caoa.f32", caoa.data(), caoa.size() * sizeof(float));
   if (mc16) {
     dump(prefix + ".sval.f32", sval.data(), sval.size() * sizeof(float));
     dump(prefix + ".sloc.f32", sloc.data(), sloc.size() * sizeof(float));

@@ -18,6 +18,7 @@
 #include "doa/rootMUSIC_linear_array.h"
 #include "doa/find_local_max.h"
 #include "doa/music_chain.h"
+#include "doa/rootmusic_chain.h"
 #include "doa/calibrate_lin_array.h"
 %}
 %include "doa/autocorrelate.h"
@@ -30,5 +31,7 @@ GR_SWIG_BLOCK_MAGIC2(doa, rootMUSIC_linear_array);
 GR_SWIG_BLOCK_MAGIC2(doa, find_local_max);
 %include "doa/music_chain.h"
 GR_SWIG_BLOCK_MAGIC2(doa, music_chain);   /* not in gr-doa: the three blocks above in one GPU call */
+%include "doa/rootmusic_chain.h"
+GR_SWIG_BLOCK_MAGIC2(doa, rootmusic_chain);   /* not in gr-doa: autocorrelate + rootMUSIC_linear_array in one GPU call */
 %include "doa/calibrate_lin_array.h"
 GR_SWIG_BLOCK_MAGIC2(doa, calibrate_lin_array);

@@ -119,6 +119,18 @@ int doa_cuda_calibrate_create(doa_cuda_handle** out, float norm_spacing, int num
 int doa_cuda_calibrate_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_host);
 int doa_cuda_calibrate_run_device(doa_cuda_handle* h, const void* in_dev, int nframes, void* out_dev, void* cuda_stream);
 
+/* ---- autocorrelate -> rootMUSIC_linear_array in one call (the Root-MUSIC flowgraph, BASELINE configs[1]) ---------------
+ * lib/autocorrelate_impl.cc:82-118 followed by lib/rootMUSIC_linear_array_impl.cc:90-152 with the covariance staying on the
+ * device: samples in (the three layouts of the chain: device strides, host frames [n][M][N], host channel streams),
+ * num_targets ascending angles per frame out.  Same kernels as the two separate stages: identical bits.
+ * doa_cuda_set_channel_gains / doa_cuda_set_input_format apply. */
+int doa_cuda_rootchain_create(doa_cuda_handle** h, int inputs, int snapshot_size, int overlap_size, int avg_method,
+                              float norm_spacing, int num_targets, int device, int max_frames);
+int doa_cuda_rootchain_run_device(doa_cuda_handle* h, const void* in_dev, long long frame_stride, long long chan_stride,
+                                  int nframes, void* out_aoa_dev, void* cuda_stream);
+int doa_cuda_rootchain_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_aoa_host);
+int doa_cuda_rootchain_run_streams(doa_cuda_handle* h, const void* const* in_host, int nframes, void* out_aoa_host);
+
 /* ---- the fused chain on several GPUs from one process --------------------------------------
  * A GNU Radio flowgraph is one process; this form lets one block instance use every GPU of the box.  Frames are independent
  * in all four reference blocks (lib/autocorrelate_impl.cc:92, lib/MUSIC_lin_array_impl.cc:121,
@@ -144,8 +156,8 @@ int doa_cuda_multi_block(const doa_cuda_handle* h, int nframes, int index, int* 
 /* ---- channel gains in front of the covariance ---------------------------------------------
  * Replaces the antenna_correction block (lib/antenna_correction_impl.cc:47-99: out_k[i] = g_k * in_k[i]) and
  * python/phase_correct_hier.py:91-102 (g_k = e^{j phi_k}) when they feed autocorrelate: instead of two more passes over the
- * sample stream the gains are folded into the covariance, R' = D R D^H, D = diag(g).  Valid on an autocorrelate or a chain
- * handle; `gains` = `inputs` complex floats (re, im interleaved, host memory), NULL restores "no gains".  Takes effect for
+ * sample stream the gains are folded into the covariance, R' = D R D^H, D = diag(g).  Valid on an autocorrelate, chain or
+ * rootchain handle; `gains` = `inputs` complex floats (re, im interleaved, host memory), NULL restores "no gains".  Takes effect for
  * the following runs. */
 int doa_cuda_set_channel_gains(doa_cuda_handle* h, const float* gains);
 /* The reference constructor's config-file reader (lib/antenna_correction_impl.cc:54-74): one "gain phase" pair per
@@ -155,8 +167,8 @@ int doa_cuda_antenna_gains_from_file(const char* config_filename, int num_ant_el
 
 /* ---- sample format of the covariance input -------------------------------------------------
  * The reference's flowgraphs ask UHD for cpu_format "fc32" (python/twinrx_usrp_source.py:57): the host converts the
- * radio's int16 I/Q pairs to gr_complex before autocorrelate reads them.  With DOA_CUDA_FMT_SC16 an autocorrelate or a
- * chain handle reads the int16 pairs directly (UHD cpu_format "sc16": one little-endian 32-bit word per complex sample,
+ * radio's int16 I/Q pairs to gr_complex before autocorrelate reads them.  With DOA_CUDA_FMT_SC16 an autocorrelate, chain,
+ * rootchain or multi handle reads the int16 pairs directly (UHD cpu_format "sc16": one little-endian 32-bit word per complex sample,
  * I in the low half), converts exactly inside the covariance kernel, and the value of a sample is int16 * scale (UHD's
  * converter uses 1/32767; 1/32768 is a power of two).  That halves the bytes the chain moves over PCIe and HBM.
  * Every `in` pointer of the run functions (host and device) is then read as sc16; strides stay in complex samples.

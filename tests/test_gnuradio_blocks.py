@@ -75,6 +75,9 @@ def test_fake_scheduler_flowgraph_matches_oracle(oracle, tmp_path, M, N, overlap
     worst, near = parity.root_angles_ok(aoa, a64, d64)
     assert worst <= parity.ROOT_DEG and near <= 6
     assert np.abs(np.sort(loc, 1) - np.sort(np.array(thetas))[None, :]).max() < 2.0     # the reference QA's own bound
+    # doa.rootmusic_chain (autocorrelate + rootMUSIC_linear_array in one block): same kernels on the same covariance = same bits
+    caoa = np.fromfile(tmp_path / "out.caoa.f32", np.float32).reshape(nframes, T)
+    assert np.array_equal(caoa, aoa)
     # the fused block (doa.music_chain: same inputs as autocorrelate, same outputs as find_local_max) under the same scheduler
     cval = np.fromfile(tmp_path / "out.cval.f32", np.float32).reshape(nframes, K)
     cloc = np.fromfile(tmp_path / "out.cloc.f32", np.float32).reshape(nframes, K)
