@@ -53,6 +53,8 @@ SYMBOLS = {
     "doa_cuda_multi_run_streams": (_i, [_vp, _hp, _i, _vp, _vp, _vp]),
     "doa_cuda_multi_device_count": (_i, [_vp]),
     "doa_cuda_multi_block": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "doa_cuda_pin_host_buffer": (_i, [_vp, C.c_ulonglong]),
+    "doa_cuda_unpin_host_buffer": (_i, [_vp]),
     "doa_cuda_destroy": (None, [_vp]),
 }
 

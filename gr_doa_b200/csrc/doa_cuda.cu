@@ -195,6 +195,21 @@ int doa_cuda_dev_set(const char* key, int value) {
   return 0;
 }
 
+// ---- page-locking a caller's host buffer -----------------------------------------------------------------------------
+int doa_cuda_pin_host_buffer(void* p, unsigned long long bytes) {
+  if (!p || bytes == 0) return fail(nullptr, DOA_CUDA_EINVAL, "null or empty host range");
+  const cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return DOA_CUDA_OK; }
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, DOA_CUDA_ECUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+  return DOA_CUDA_OK;
+}
+int doa_cuda_unpin_host_buffer(void* p) {
+  if (!p) return fail(nullptr, DOA_CUDA_EINVAL, "null host pointer");
+  const cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, DOA_CUDA_ECUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
+  return DOA_CUDA_OK;
+}
+
 // ---- channel gains ------------------------------------------------------------------------------------------------
 int doa_cuda_set_channel_gains(doa_cuda_handle* h, const float* gains) {
   if (h && h->kind == K_MULTI) {

@@ -179,6 +179,15 @@ int doa_cuda_antenna_gains_from_file(const char* config_filename, int num_ant_el
 #define DOA_CUDA_FMT_SC16 1
 int doa_cuda_set_input_format(doa_cuda_handle* h, int format, float scale);
 
+/* ---- page-locking the caller's buffers -------------------------------------------------------------------------------
+ * The *_run entry points accept any host memory.  Out of pageable memory (a GNU Radio scheduler's buffers) the host->device
+ * copy is staged by the driver and runs at a fraction of the PCIe rate; a flowgraph's circular buffers live as long as the
+ * flowgraph, so a maintainer who knows their extent (gr::buffer base and size) can page-lock them once with this wrapper
+ * around cudaHostRegister and release them before the buffers are freed.  Registering a range twice is not an error.
+ * No handle needed; errors are reported through doa_cuda_last_error(NULL). */
+int doa_cuda_pin_host_buffer(void* p, unsigned long long bytes);
+int doa_cuda_unpin_host_buffer(void* p);
+
 void doa_cuda_destroy(doa_cuda_handle* h);
 
 #ifdef __cplusplus

@@ -72,3 +72,16 @@ def test_create_fails_loudly_without_a_gpu():
     assert ei.value.code == _lib.ECUDA and "no CPU fallback" in str(ei.value)
     with pytest.raises(_lib.DoaCudaError):
         doa.DoaChain(8, 2048, 0, 0, 0.5, 3, 4096, 3)
+
+
+def test_pin_host_buffer_rejects_bad_arguments():
+    from gr_doa_b200 import _lib
+    L = _lib.lib()
+    assert L.doa_cuda_pin_host_buffer(None, 4096) == _lib.EINVAL
+    import numpy as np
+    a = np.zeros(1024, np.float32)
+    assert L.doa_cuda_pin_host_buffer(a.ctypes.data, 0) == _lib.EINVAL
+    assert L.doa_cuda_unpin_host_buffer(None) == _lib.EINVAL
+    if not has_cuda():       # no device: the CUDA error comes back as a code and a text, nothing is pinned
+        assert L.doa_cuda_pin_host_buffer(a.ctypes.data, a.nbytes) == _lib.ECUDA
+        assert b"cudaHostRegister" in L.doa_cuda_last_error(None)

@@ -408,3 +408,21 @@ def test_rootmusic_aberth_path_agrees_with_the_qr_path(doa, oracle, torch_cuda, 
     away = np.nanmin(d64, axis=1) >= parity.ROOT_NEAR_CIRCLE
     both = np.isfinite(got[0]) & np.isfinite(got[1]) & away[:, None]
     assert np.abs(got[0] - got[1])[both].max() <= parity.ROOT_DEG
+
+
+def test_page_locked_caller_buffers_change_nothing_but_speed(doa):
+    """doa_cuda_pin_host_buffer / unpin: the run entry points give the same bits from a page-locked caller buffer; pinning the
+    same range twice is accepted; unpinning something never pinned is an error."""
+    from gr_doa_b200 import synth, _lib
+    L = _lib.lib()
+    M, N, T, P, K, B = 8, 512, 3, 1024, 3, 64
+    fr, _ = synth.frames_numpy(B, M, N, [40.0, 90.0, 140.0], snr_db=10.0, seed=5)
+    ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
+    ref = [a.copy() for a in ch.run_host(fr)]
+    assert L.doa_cuda_pin_host_buffer(fr.ctypes.data, fr.nbytes) == 0
+    assert L.doa_cuda_pin_host_buffer(fr.ctypes.data, fr.nbytes) == 0
+    got = ch.run_host(fr)
+    assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    assert L.doa_cuda_unpin_host_buffer(fr.ctypes.data) == 0
+    assert L.doa_cuda_unpin_host_buffer(fr.ctypes.data) != 0
+    assert all(np.array_equal(a, b) for a, b in zip(ch.run_host(fr), ref))

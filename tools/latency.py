@@ -29,6 +29,11 @@ for name, (M, N, T, P, K, th) in {"cfg1 shape": (4, 2048, 1, 2048, 1, [60.0]), "
         t_mu = med(lambda: mu.work(R))
         t_fl = med(lambda: fl.work(S))
         t_ch = med(lambda: ch.run_host(fr))
+        # the same call with the caller's buffer page-locked once (doa_cuda_pin_host_buffer), as a flowgraph could do for its ring buffers
+        from gr_doa_b200 import _lib
+        pinned = _lib.lib().doa_cuda_pin_host_buffer(fr.ctypes.data, fr.nbytes) == 0
+        t_chp = med(lambda: ch.run_host(fr)) if pinned else float("nan")
+        if pinned: _lib.lib().doa_cuda_unpin_host_buffer(fr.ctypes.data)
         t_cpu = med(lambda: O.chain_frames(fr, 0, 0.5, T, P, K, nthreads=1), n=20, warm=2)
-        print(f"{name}, {n:2d} frames per call: autocorrelate {t_ac:7.1f} us  MUSIC {t_mu:7.1f} us  find_local_max {t_fl:7.1f} us  |  fused chain call {t_ch:7.1f} us"
+        print(f"{name}, {n:2d} frames per call: autocorrelate {t_ac:7.1f} us  MUSIC {t_mu:7.1f} us  find_local_max {t_fl:7.1f} us  |  fused chain call {t_ch:7.1f} us (buffer page-locked: {t_chp:7.1f} us)"
               f"  |  CPU restatement, 1 core {t_cpu:8.1f} us", flush=True)
