@@ -10,7 +10,11 @@
  *     doa_cuda_S_run         the body of work()/general_work(): HOST pointers, synchronous
  *     doa_cuda_S_run_device  the same on DEVICE pointers, asynchronous on the caller's stream
  *     doa_cuda_S_destroy
- * plus doa_cuda_chain_* = autocorrelate -> MUSIC_lin_array -> find_local_max fused, peaks only.
+ * plus doa_cuda_chain_*     = autocorrelate -> MUSIC_lin_array -> find_local_max fused, peaks only;
+ *      doa_cuda_rootchain_* = autocorrelate -> rootMUSIC_linear_array, angles only;
+ *      doa_cuda_multi_*     = the fused chain over several GPUs from one process;
+ *      doa_cuda_calibrate_*, doa_cuda_set_channel_gains, doa_cuda_set_input_format (sc16 samples),
+ *      doa_cuda_pin_host_buffer = the steps either side of the path.
  *
  * Reference interfaces replaced (paths relative to the gr-doa tree):
  *     autocorrelate::make / general_work / forecast     include/doa/autocorrelate.h:56, lib/autocorrelate_impl.cc:47-118
