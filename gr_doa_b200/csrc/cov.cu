@@ -166,10 +166,17 @@ cov16_kernel(const S* __restrict__ in, long long frame_stride, long long chan_st
 constexpr int C16_STAGES = 5;
 
 // One role's whole loop (the two roles are separate instantiations so that each only carries its own 128 accumulators).
-template <int ROLE>
-__device__ __forceinline__ void cov16_ring_role(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N,
+// S = float2: fc32 samples, float4 ring slots; S = unsigned: sc16 samples, uint2 ring slots (the same two samples per lane).
+template <typename S> struct Ring16Slot { typedef float4 type; };
+template <> struct Ring16Slot<unsigned> { typedef uint2 type; };
+
+template <int ROLE, typename S>
+__device__ __forceinline__ void cov16_ring_role(const S* __restrict__ in, long long frame_stride, long long chan_stride, int N,
                                                 int nframes, float2* __restrict__ out, float scale, float bscale, int avg_method,
-                                                const float2* __restrict__ gains, float4* ring, float* red, int slot, int lane) {
+                                                const float2* __restrict__ gains, typename Ring16Slot<S>::type* ring, float* red,
+                                                int slot, int lane) {
+  typedef typename Ring16Slot<S>::type Slot;
+  constexpr bool SC16 = sizeof(S) == 4;
   constexpr int M = 16, CNT = 256, NP16 = 120;
   const int bar_id = 1 + slot;
   const int nslots = gridDim.x * C16_FRAMES;
@@ -178,14 +185,17 @@ __device__ __forceinline__ void cov16_ring_role(const float2* __restrict__ in, l
   const int NCH = (N + 63) / 64;                      // 64-sample chunks per frame (2 samples per lane)
   const int total = nfw * NCH;
   // issue cursor: this warp loads channels 8 ROLE .. 8 ROLE + 7 of every chunk
-  const float2* ibase = in + (long long)first * frame_stride + (long long)(8 * ROLE) * chan_stride;
+  const S* ibase = in + (long long)first * frame_stride + (long long)(8 * ROLE) * chan_stride;
   int ic = 0, istage = 0, issued = 0;
   auto issue = [&]() {
     const int t = ic * 64 + lane * 2;
-    const int nbytes = (t < N) ? 16 : 0;
-    float4* dst = ring + ((size_t)istage * 16 + 8 * ROLE) * 32 + lane;
+    const int nbytes = (t < N) ? (int)sizeof(Slot) : 0;
+    Slot* dst = ring + ((size_t)istage * 16 + 8 * ROLE) * 32 + lane;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) cp_async16(dst + k * 32, ibase + (long long)k * chan_stride + (nbytes ? t : 0), nbytes);
+    for (int k = 0; k < 8; ++k) {
+      if constexpr (SC16) cp_async8(dst + k * 32, ibase + (long long)k * chan_stride + (nbytes ? t : 0), nbytes);
+      else cp_async16(dst + k * 32, ibase + (long long)k * chan_stride + (nbytes ? t : 0), nbytes);
+    }
     if (++ic == NCH) { ic = 0; ibase += (long long)nslots * frame_stride; }
     if (++istage == C16_STAGES) istage = 0;
     ++issued;
@@ -211,11 +221,15 @@ __device__ __forceinline__ void cov16_ring_role(const float2* __restrict__ in, l
     cp_async_commit();
     cp_async_wait<C16_STAGES - 2>();
     asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");      // both halves of this chunk have landed
-    const float4* src = ring + (size_t)rstage * 16 * 32 + lane;
+    const Slot* src = ring + (size_t)rstage * 16 * 32 + lane;
     if (++rstage == C16_STAGES) rstage = 0;
     float2 x[2][16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { const float4 v = src[k * 32]; x[0][k] = make_float2(v.x, v.y); x[1][k] = make_float2(v.z, v.w); }
+    for (int k = 0; k < 16; ++k) {
+      const Slot v = src[k * 32];
+      if constexpr (SC16) { x[0][k] = sc16_to_c64(v.x); x[1][k] = sc16_to_c64(v.y); }
+      else { x[0][k] = make_float2(v.x, v.y); x[1][k] = make_float2(v.z, v.w); }
+    }
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       if constexpr (ROLE == 0) {
@@ -303,41 +317,35 @@ __device__ __forceinline__ void cov16_ring_role(const float2* __restrict__ in, l
   }
 }
 
+template <typename S>
 __global__ void __launch_bounds__(C16_FRAMES * 64, 1)
-cov16_ring_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
+cov16_ring_kernel(const S* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
                   float2* __restrict__ out, float scale, float bscale, int avg_method, const float2* __restrict__ gains) {
-  extern __shared__ float4 ring_s[];                 // [C16_FRAMES][C16_STAGES][16][32]
+  typedef typename Ring16Slot<S>::type Slot;
+  extern __shared__ float4 ring_s[];                 // [C16_FRAMES][C16_STAGES][16][32] slots
   __shared__ float red_s[C16_FRAMES][256];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5, slot = warp >> 1;
-  float4* ring = ring_s + (size_t)slot * C16_STAGES * 16 * 32;
-  if ((warp & 1) == 0) cov16_ring_role<0>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, gains, ring, red_s[slot], slot, lane);
-  else cov16_ring_role<1>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, gains, ring, red_s[slot], slot, lane);
+  Slot* ring = reinterpret_cast<Slot*>(ring_s) + (size_t)slot * C16_STAGES * 16 * 32;
+  if ((warp & 1) == 0) cov16_ring_role<0, S>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, gains, ring, red_s[slot], slot, lane);
+  else cov16_ring_role<1, S>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, gains, ring, red_s[slot], slot, lane);
 }
 
-// sc16 input: the LDG kernel (bit-identical to the ring kernel; a ring of 8-byte cp.async is the obvious next step).
-int launch_cov16_sc16(const unsigned* in, long long fs, long long cs, int N, int nframes, float2* out, float scale, float bscale,
-                      int avg, cudaStream_t st, const float2* gains) {
-  const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 7u) == 0);
-  const int blocks = (nframes + C16_FRAMES - 1) / C16_FRAMES;
-  if (vec2) cov16_kernel<2, unsigned><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
-  else cov16_kernel<1, unsigned><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
-  return 1;
-}
-
-int launch_cov16(const float2* in, long long fs, long long cs, int N, int nframes, float2* out, float scale, float bscale,
+template <typename S>
+int launch_cov16(const S* in, long long fs, long long cs, int N, int nframes, float2* out, float scale, float bscale,
                  int avg, cudaStream_t st, const float2* gains) {
-  const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
+  // two samples per ring slot / load: 16 bytes of fc32, 8 bytes of sc16
+  const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & (2 * sizeof(S) - 1)) == 0);
   const int blocks = (nframes + C16_FRAMES - 1) / C16_FRAMES;
   if (vec2 && dev_option("cov16_ring", 1)) {
-    const size_t smem = (size_t)C16_FRAMES * C16_STAGES * 16 * 32 * sizeof(float4);
-    cudaFuncSetAttribute(cov16_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)C16_FRAMES * C16_STAGES * 16 * 32 * sizeof(typename Ring16Slot<S>::type);
+    cudaFuncSetAttribute(cov16_ring_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = std::min(blocks, num_sms());
-    cov16_ring_kernel<<<grid, C16_FRAMES * 64, smem, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+    cov16_ring_kernel<S><<<grid, C16_FRAMES * 64, smem, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
     return 1;
   }
-  if (vec2) cov16_kernel<2, float2><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
-  else cov16_kernel<1, float2><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+  if (vec2) cov16_kernel<2, S><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
+  else cov16_kernel<1, S><<<blocks, C16_FRAMES * 64, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
   return 1;
 }
 
@@ -495,7 +503,7 @@ int launch_covariance(const void* in_v, long long frame_stride, long long chan_s
       case 2: return launch_small<2>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
       case 4: return launch_small<4>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
       case 8: return launch_small<8>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
-      case 16: return launch_cov16_sc16(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
+      case 16: return launch_cov16(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
       default: return launch_tiled(in, frame_stride, chan_stride, M, N, nframes, out, scale, bscale, avg_method, st, gains);
     }
   }

@@ -30,6 +30,27 @@ def chain_case(name, M, T, N, overlap, P, K, thetas, avg, nframes, seed, d=0.5, 
     print(name, {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
+def sc16_case(name, M, T, N, overlap, P, K, thetas, avg, nframes, seed, scale, d=0.5, stream=True):
+    """Samples as a radio delivers them (UHD "sc16": int16 I, Q) + what the reference computes after UHD's host-side
+    conversion to gr_complex, float(int16) * scale."""
+    if stream:
+        x = synth.stream_numpy(nframes, M, N, overlap, thetas, d=d, snr_db=10.0, seed=seed)
+    else:
+        x, _ = synth.frames_numpy(nframes, M, N, thetas, d=d, snr_db=10.0, jitter_deg=3.0, seed=seed)
+    q = np.clip(np.rint(np.stack([x.real, x.imag], axis=-1) * 8192.0), -32768, 32767).astype(np.int16)
+    f = q.astype(np.float32) * np.float32(scale)
+    xc = (f[..., 0] + 1j * f[..., 1]).astype(np.complex64)
+    R = O.autocorrelate(xc, N, overlap, avg) if stream else O.autocorrelate_frames(xc, avg)
+    spec = O.music(R, d, T, M, P)
+    val, loc, bins = O.find_local_max(spec, K, 0.0, 180.0)
+    out = dict(q=q, scale=np.float32(scale), R=R, spec=spec, val=val, loc=loc, bins=bins, q32=O.music_q(R, d, T, M, P),
+               q64=O.music_f64(R, d, T, M, P), aoa64=O.rootmusic_f64(R, d, T, M),
+               params=np.array([M, T, N, overlap, P, K, avg, nframes, int(stream)], np.int64), d=np.float32(d),
+               thetas=np.array(thetas, np.float64))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
 def flm_case():
     rng = np.random.Generator(np.random.Philox(key=0x0D0A))
     vecs = []
@@ -62,3 +83,6 @@ if __name__ == "__main__":
     # configs[4]: 16-element frames x 1024 snapshots
     chain_case("cfg5_m16", 16, 3, 1024, 0, 4096, 3, [40.0, 90.0, 140.0], 0, 3, S + 5, stream=False)
     flm_case()
+    # sc16 wire format in front of the same path (the int16 samples are the fixture; the reference sees them converted)
+    sc16_case("sc16_cfg1_fb", 4, 1, 2048, 512, 2048, 1, [60.0], 1, 4, S + 11, 1.0 / 32768)
+    sc16_case("sc16_cfg3_batch", 8, 3, 2048, 0, 4096, 3, [40.0, 90.0, 140.0], 0, 3, S + 13, 1.0 / 32767, stream=False)

@@ -195,3 +195,56 @@ def test_channel_major_ring_fills_change_nothing(M, T, P, K, N):
             assert all(torch.equal(a, b) for a, b in zip(got, ref)), fmt
     finally:
         L.doa_cuda_dev_set(b"ws_fill", 0)
+
+
+# ---- committed golden fixtures (tests/golden/sc16_*.npz, written by tests/golden/make_golden.py) -----------------------
+SC16_CASES = ["sc16_cfg1_fb", "sc16_cfg3_batch"]
+
+
+def _load_sc16(name):
+    import os
+    from tests.test_golden import GOLDEN
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    M, T, N, overlap, P, K, avg, nframes, stream = [int(v) for v in z["params"]]
+    return z, dict(M=M, T=T, N=N, overlap=overlap, P=P, K=K, avg=avg, nframes=nframes, stream=bool(stream), d=float(z["d"]),
+                   scale=float(z["scale"]))
+
+
+@pytest.mark.parametrize("name", SC16_CASES)
+def test_oracle_reproduces_sc16_golden(oracle, name):
+    """CPU: the oracle on float(int16) * scale (what UHD's converter hands the reference) against the committed fixture."""
+    z, p = _load_sc16(name)
+    xc = to_fc32(z["q"], p["scale"])
+    R = oracle.autocorrelate(xc, p["N"], p["overlap"], p["avg"]) if p["stream"] else oracle.autocorrelate_frames(xc, p["avg"])
+    assert parity.rel_fro(R, z["R"]) < 1e-6
+    val, loc, bins = oracle.find_local_max(oracle.music(z["R"], p["d"], p["T"], p["M"], p["P"]), p["K"], 0.0, 180.0)
+    assert np.array_equal(bins, z["bins"])
+    assert np.abs(np.sort(z["loc"], axis=1) - np.sort(z["thetas"])[None, :]).max() < 4.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SC16_CASES)
+def test_gpu_sc16_against_golden(name):
+    """GPU: int16 samples in, the fixture's covariance (1e-5), peak bins (near-ties classified) and Root-MUSIC angles (1e-4
+    degree against the float64 twin) out -- through autocorrelate, the fused chain and the Root-MUSIC chain."""
+    import gr_doa_b200 as doa
+    z, p = _load_sc16(name)
+    M, T, N, ov, P, K, avg, n = p["M"], p["T"], p["N"], p["overlap"], p["P"], p["K"], p["avg"], p["nframes"]
+    ac = doa.autocorrelate(M, N, ov, avg, max_frames=n)
+    ac.set_input_format("sc16", p["scale"])
+    ch = doa.DoaChain(M, N, ov, avg, p["d"], T, P, K, max_frames=n)
+    ch.set_input_format("sc16", p["scale"])
+    rc = doa.RootMusicChain(M, N, ov, avg, p["d"], T, max_frames=n)
+    rc.set_input_format("sc16", p["scale"])
+    if p["stream"]:
+        R = ac.work(z["q"])
+        val, loc, bins = ch.run_streams(list(z["q"]), n)
+        aoa = rc.run_streams(list(z["q"]), n)
+    else:
+        R = ac.work(np.ascontiguousarray(z["q"].transpose(1, 0, 2, 3)).reshape(M, n * N, 2))
+        val, loc, bins = ch.run_host(z["q"])
+        aoa = rc.run_host(z["q"])
+    assert parity.rel_fro(R, z["R"]) <= parity.COV_REL_FRO
+    ndiff, unexplained = parity.classify_bins(bins, z["bins"], z["q64"], z["q32"])
+    assert unexplained == []
+    assert np.abs(aoa - z["aoa64"]).max() <= parity.ROOT_DEG

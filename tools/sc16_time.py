@@ -19,7 +19,11 @@ S15 = 1.0 / 32768
 SHAPES = {
     "cfg3 (M8 T3 N2048 P4096 K3)": dict(B=65536, M=8, N=2048, T=3, P=4096, K=3, th=[40.0, 90.0, 140.0]),
     "cfg1 (M4 T1 N2048 P2048 K1)": dict(B=131072, M=4, N=2048, T=1, P=2048, K=1, th=[60.0]),
+    "cfg5 shard (M16 T3 N1024 P4096 K3)": dict(B=65536, M=16, N=1024, T=3, P=4096, K=3, th=[40.0, 90.0, 140.0]),
 }
+only = [a for a in sys.argv[1:] if not a.startswith("--")]
+if only:
+    SHAPES = {k: v for k, v in SHAPES.items() if any(o in k for o in only)}
 
 
 def timed(fn, iters):
