@@ -10,7 +10,10 @@
 #include <fstream>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -79,6 +82,60 @@ struct Lane {   // one stream's worth of buffers (the chain's host path double-b
   int frames = 0;
 };
 
+// Host threads of a multi-device handle: device 0 is driven by the calling thread, every further device by one persistent
+// worker (a GNU Radio work() call is short: spawning threads per call would cost as much as the call).  One run at a time,
+// like every handle (a block's work() is called serially).
+struct MultiPool {
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  const std::function<int(int)>* job = nullptr;
+  unsigned long long epoch = 0;
+  int pending = 0;
+  bool stop = false;
+  std::vector<int> rcs;
+  std::vector<std::thread> threads;
+  explicit MultiPool(int G) : rcs(G, 0) {
+    for (int g = 1; g < G; ++g) threads.emplace_back([this, g] { loop(g); });
+  }
+  void loop(int g) {
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::function<int(int)>* j = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_job.wait(lk, [&] { return stop || epoch != seen; });
+        if (stop) return;
+        seen = epoch;
+        j = job;
+      }
+      const int rc = (*j)(g);
+      std::lock_guard<std::mutex> lk(mu);
+      rcs[g] = rc;
+      if (--pending == 0) cv_done.notify_one();
+    }
+  }
+  void run(const std::function<int(int)>& j) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      job = &j;
+      pending = (int)threads.size();
+      ++epoch;
+    }
+    cv_job.notify_all();
+    rcs[0] = j(0);
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+  ~MultiPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv_job.notify_all();
+    for (auto& t : threads) t.join();
+  }
+};
+
 struct doa_cuda_handle {
   int kind = 0, device = 0, max_frames = 0;
   int M = 0, N = 0, overlap = 0, hop = 0, avg = 0, T = 0, P = 0, K = 0;
@@ -94,6 +151,7 @@ struct doa_cuda_handle {
   int launches = 0;
   bool profiling = false;
   std::vector<doa_cuda_handle*> children;   // K_MULTI: one chain handle per listed device
+  std::unique_ptr<MultiPool> pool;          // K_MULTI: its host threads
   std::vector<cudaEvent_t> ev;   // profiling: 4 events per recorded chain call (ring of PROF_SETS calls)
   int prof_calls = 0;
 };
@@ -121,6 +179,7 @@ static void free_lane(Lane& l) {
 
 extern "C" void doa_cuda_destroy(doa_cuda_handle* h) {
   if (!h) return;
+  h->pool.reset();                          // workers are idle between runs; join them before their devices' handles go
   for (doa_cuda_handle* c : h->children) doa_cuda_destroy(c);
   h->children.clear();
   cudaSetDevice(h->device);
@@ -797,6 +856,7 @@ int doa_cuda_multi_create(doa_cuda_handle** out, int inputs, int snapshot_size, 
     h->children.push_back(c);
   }
   h->max_frames = max_frames_per_device * ndevices;
+  h->pool.reset(new MultiPool(ndevices));
   *out = h;
   return DOA_CUDA_OK;
 }
@@ -816,6 +876,18 @@ int doa_cuda_multi_block(const doa_cuda_handle* h, int nframes, int index, int* 
   return DOA_CUDA_OK;
 }
 
+// Run job(g) for every device of the handle (device 0 on the calling thread, the others on the handle's workers) and fold
+// the return codes and launch counts.
+static int multi_finish(doa_cuda_handle* h, const std::function<int(int)>& job) {
+  h->pool->run(job);
+  h->launches = 0;
+  for (size_t g = 0; g < h->children.size(); ++g) {
+    if (h->pool->rcs[g]) return fail(h, h->pool->rcs[g], "device " + std::to_string(h->children[g]->device) + ": " + h->children[g]->err);
+    h->launches += h->children[g]->launches;
+  }
+  return DOA_CUDA_OK;
+}
+
 int doa_cuda_multi_run(doa_cuda_handle* h, const void* in_host, int nframes, void* out_val_host, void* out_loc_host,
                        void* out_bin_host) {
   if (!h || h->kind != K_MULTI) return DOA_CUDA_EINVAL;
@@ -823,26 +895,16 @@ int doa_cuda_multi_run(doa_cuda_handle* h, const void* in_host, int nframes, voi
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames_per_device * ndevices");
   const int G = (int)h->children.size();
   const size_t frame_bytes = (size_t)h->M * h->N * h->children[0]->sample_bytes();
-  std::vector<int> rcs(G, DOA_CUDA_OK);
-  auto work = [&](int g) {
+  const std::function<int(int)> work = [&](int g) -> int {
     int first = 0, count = 0;
     multi_block(nframes, G, g, &first, &count);
-    if (count == 0) return;
+    if (count == 0) { h->children[g]->launches = 0; return DOA_CUDA_OK; }
     const size_t off = (size_t)first * h->K;
-    rcs[g] = doa_cuda_chain_run(h->children[g], (const char*)in_host + (size_t)first * frame_bytes, count,
-                                (float*)out_val_host + off, (float*)out_loc_host + off,
-                                out_bin_host ? (void*)((int*)out_bin_host + off) : nullptr);
+    return doa_cuda_chain_run(h->children[g], (const char*)in_host + (size_t)first * frame_bytes, count,
+                              (float*)out_val_host + off, (float*)out_loc_host + off,
+                              out_bin_host ? (void*)((int*)out_bin_host + off) : nullptr);
   };
-  std::vector<std::thread> th;
-  for (int g = 1; g < G; ++g) th.emplace_back(work, g);   // one host thread per additional device; the caller's drives device 0
-  work(0);
-  for (auto& t : th) t.join();
-  h->launches = 0;
-  for (int g = 0; g < G; ++g) {
-    if (rcs[g]) return fail(h, rcs[g], "device " + std::to_string(h->children[g]->device) + ": " + h->children[g]->err);
-    h->launches += h->children[g]->launches;
-  }
-  return DOA_CUDA_OK;
+  return multi_finish(h, work);
 }
 
 // Streaming form (what a GNU Radio general_work() holds: `inputs` channel pointers, frame i at hop * i): device g gets the
@@ -855,27 +917,17 @@ int doa_cuda_multi_run_streams(doa_cuda_handle* h, const void* const* in_host, i
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames_per_device * ndevices");
   const int G = (int)h->children.size();
   const size_t sb = h->children[0]->sample_bytes();
-  std::vector<int> rcs(G, DOA_CUDA_OK);
-  auto work = [&](int g) {
+  const std::function<int(int)> work = [&](int g) -> int {
     int first = 0, count = 0;
     multi_block(nframes, G, g, &first, &count);
-    if (count == 0) return;
+    if (count == 0) { h->children[g]->launches = 0; return DOA_CUDA_OK; }
     std::vector<const void*> ptrs(h->M);
     for (int k = 0; k < h->M; ++k) ptrs[k] = (const char*)in_host[k] + (size_t)first * h->hop * sb;
     const size_t off = (size_t)first * h->K;
-    rcs[g] = doa_cuda_chain_run_streams(h->children[g], ptrs.data(), count, (float*)out_val_host + off, (float*)out_loc_host + off,
-                                        out_bin_host ? (void*)((int*)out_bin_host + off) : nullptr);
+    return doa_cuda_chain_run_streams(h->children[g], ptrs.data(), count, (float*)out_val_host + off, (float*)out_loc_host + off,
+                                      out_bin_host ? (void*)((int*)out_bin_host + off) : nullptr);
   };
-  std::vector<std::thread> th;
-  for (int g = 1; g < G; ++g) th.emplace_back(work, g);
-  work(0);
-  for (auto& t : th) t.join();
-  h->launches = 0;
-  for (int g = 0; g < G; ++g) {
-    if (rcs[g]) return fail(h, rcs[g], "device " + std::to_string(h->children[g]->device) + ": " + h->children[g]->err);
-    h->launches += h->children[g]->launches;
-  }
-  return DOA_CUDA_OK;
+  return multi_finish(h, work);
 }
 
 int doa_cuda_set_profiling(doa_cuda_handle* h, int on) {

@@ -140,8 +140,8 @@ int doa_cuda_rootchain_run_streams(doa_cuda_handle* h, const void* const* in_hos
  * in all four reference blocks (lib/autocorrelate_impl.cc:92, lib/MUSIC_lin_array_impl.cc:121,
  * lib/rootMUSIC_linear_array_impl.cc:105, lib/find_local_max_impl.cc:179), so a batch of independent frames ([nframes][M][N]
  * host memory, as doa_cuda_chain_run) is cut into contiguous blocks, one per entry of `devices` (sizes differ by at most one
- * frame; doa_cuda_multi_block reports them).  Each device copies and processes its block concurrently (one host thread per
- * device inside the call) and writes its peaks into the caller's output arrays at the block's offset -- that is the whole
+ * frame; doa_cuda_multi_block reports them).  Each device copies and processes its block concurrently (the calling thread
+ * drives the first device, persistent worker threads owned by the handle the others) and writes its peaks into the caller's output arrays at the block's offset -- that is the whole
  * gather, so per-frame results are bit-identical to doa_cuda_chain_run on one device.  A device may be listed more than once
  * (that many independent stream sets on it).  set_channel_gains / set_input_format apply to every device.
  * The one-process-per-GPU form (torchrun, NCCL gather of device-resident peaks) lives in gr_doa_b200/sharding.py. */
