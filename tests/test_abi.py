@@ -85,3 +85,33 @@ def test_pin_host_buffer_rejects_bad_arguments():
     if not has_cuda():       # no device: the CUDA error comes back as a code and a text, nothing is pinned
         assert L.doa_cuda_pin_host_buffer(a.ctypes.data, a.nbytes) == _lib.ECUDA
         assert b"cudaHostRegister" in L.doa_cuda_last_error(None)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/doa_cuda.h compiles as strict C99 (no C++ types in any signature) and a C program that
+    only uses the header links against libdoa_cuda.so and runs (without a device it gets the documented error code back)."""
+    import subprocess
+    from gr_doa_b200 import _lib
+    src = tmp_path / "c_client.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "doa_cuda.h"
+int main(void) {
+  doa_cuda_handle* h = 0;
+  int rc;
+  if (doa_cuda_abi_version() != 1) return 10;
+  rc = doa_cuda_autocorrelate_create(&h, 4, 2048, 2048, 0, 0, 16);          /* overlap must be < snapshot */
+  if (rc != DOA_CUDA_EINVAL || h != 0) return 11;
+  rc = doa_cuda_autocorrelate_create(&h, 4, 2048, 512, 0, 0, 16);
+  if (doa_cuda_device_count() == 0) { if (rc != DOA_CUDA_ECUDA || h != 0) return 12; }
+  else { if (rc != DOA_CUDA_OK || doa_cuda_autocorrelate_forecast(h, 3) != 3 * 1536) return 13; doa_cuda_destroy(h); }
+  printf("c client ok\n");
+  return 0;
+}
+''')
+    exe = tmp_path / "c_client"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L", libdir, "-ldoa_cuda", "-Wl,-rpath," + libdir])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "c client ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
