@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libdoa_cuda.so")
-SOURCES = ["doa_cuda.cu", "cov.cu", "eig.cu", "scan.cu", "root.cu", "fused.cu", "herk_tc.cu"]
+SOURCES = ["doa_cuda.cu", "cov.cu", "eig.cu", "scan.cu", "root.cu", "fused.cu", "herk_tc.cu", "scan_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
 

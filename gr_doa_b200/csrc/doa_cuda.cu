@@ -142,7 +142,7 @@ struct doa_cuda_handle {
   float d = 0.f, x_min = 0.f, x_max = 0.f;
   Lane lane[2];
   int nlanes = 1;
-  float2* d_z = nullptr; float2* d_V = nullptr; float* d_x = nullptr; float* d_zpair = nullptr;
+  float2* d_z = nullptr; float2* d_V = nullptr; float* d_x = nullptr; float* d_zpair = nullptr; float* d_tctab = nullptr;
   float2* d_gains = nullptr;     // per-channel complex gains folded into the covariance (null: none)
   InputFormat fmt;               // sample format of the covariance input (fc32 unless doa_cuda_set_input_format said sc16)
   size_t sample_bytes() const { return fmt.sc16 ? 4 : sizeof(float2); }
@@ -184,7 +184,7 @@ extern "C" void doa_cuda_destroy(doa_cuda_handle* h) {
   h->children.clear();
   cudaSetDevice(h->device);
   for (int i = 0; i < 2; ++i) free_lane(h->lane[i]);
-  cudaFree(h->d_z); cudaFree(h->d_V); cudaFree(h->d_x); cudaFree(h->d_zpair); cudaFree(h->d_gains);
+  cudaFree(h->d_z); cudaFree(h->d_V); cudaFree(h->d_x); cudaFree(h->d_zpair); cudaFree(h->d_tctab); cudaFree(h->d_gains);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
 }
@@ -228,6 +228,12 @@ static bool upload_scan_tables(doa_cuda_handle* h, bool need_steering, bool need
       ok = cudaMemcpy(h->d_z, h->h_z.data(), sizeof(float2) * h->P, cudaMemcpyHostToDevice) == cudaSuccess &&
            cudaMemcpy(h->d_V, h->h_V.data(), sizeof(float2) * (size_t)h->P * h->M, cudaMemcpyHostToDevice) == cudaSuccess;
     }
+    if (ok && need_x && scan_tc_covers(h->M, h->P, h->K)) {   // peak-picking plans only: the tensor-core scan's table
+      std::vector<float> tc;
+      build_scan_tc_table(h->d, h->M, h->P, h->h_theta, tc);
+      ok = dalloc(&h->d_tctab, tc.size()) &&
+           cudaMemcpy(h->d_tctab, tc.data(), sizeof(float) * tc.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
   }
   if (need_x && ok) {
     const int len = h->P;
@@ -239,7 +245,7 @@ static bool upload_scan_tables(doa_cuda_handle* h, bool need_steering, bool need
 }
 
 static ScanTables tables_of(const doa_cuda_handle* h) {
-  ScanTables t; t.M = h->M; t.P = h->P; t.z = h->d_z; t.zpair = h->d_zpair; t.V = h->d_V; t.xaxis = h->d_x; return t;
+  ScanTables t; t.M = h->M; t.P = h->P; t.z = h->d_z; t.zpair = h->d_zpair; t.V = h->d_V; t.xaxis = h->d_x; t.tctab = reinterpret_cast<const uint8_t*>(h->d_tctab); return t;
 }
 
 extern "C" {
@@ -687,7 +693,8 @@ static int chain_on_lane(doa_cuda_handle* h, Lane& l, const void* in_dev, long l
   int b = launch_noise_subspace(l.R, h->M, h->T, nframes, l.G, l.u, nullptr, st);
   if (b < 0) return fail(h, b, "eigendecomposition launch rejected");
   if (prof) CK(h, cudaEventRecord(ev[2], st));
-  int c = launch_scan_peaks(l.u, l.G, tables_of(h), nframes, h->K, val, loc, bin, st);
+  int c = dev_option("scan_tc", 1) ? launch_scan_peaks_tc(l.u, l.G, tables_of(h), nframes, h->K, val, loc, bin, st) : 0;
+  if (c == 0) c = launch_scan_peaks(l.u, l.G, tables_of(h), nframes, h->K, val, loc, bin, st);
   if (c < 0) return fail(h, c, "scan launch rejected (pspectrum_len too large for shared memory?)");
   if (prof) CK(h, cudaEventRecord(ev[3], st));
   h->launches += a + b + c;

@@ -45,12 +45,21 @@ struct ScanTables {
   const float* zpair = nullptr;   // the same z in the scan kernels' per-lane pair layout (scan_device.cuh: ZTab)
   const float2* V = nullptr;      // [P][M] steering table exactly as the reference constructor builds it
   const float* xaxis = nullptr;   // [P]   find_local_max x-axis (float-accumulated)
+  const uint8_t* tctab = nullptr; // tensor-core scan: tf32 hi / lo images of the steering-power table (scan_tc.cu), or null
 };
 
 // Stage 2b+4 fused: coarse null-spectrum scan (ULA polynomial form) + local-minimum pick + refinement of the
 // picked bins with the reference's own v^H G v arithmetic + dB conversion.  Outputs per frame K values/locs/bins.
 int launch_scan_peaks(const float2* u, const float2* G, const ScanTables& tb, int nframes, int K, float* out_val,
                       float* out_loc, int* out_bin, cudaStream_t st);
+
+// The same stage on the tensor cores (scan_tc.cu): the scan as a [frames x 2M-1] x [2M-1 x P] contraction (tcgen05, 3xTF32),
+// peak picking out of TMEM, the same refinement.  Returns 1 if launched, 0 if the shape is not covered (M <= 16, P a
+// multiple of 128, K <= 4, table present).
+int launch_scan_peaks_tc(const float2* u, const float2* G, const ScanTables& tb, int nframes, int K, float* out_val,
+                         float* out_loc, int* out_bin, cudaStream_t st);
+bool scan_tc_covers(int M, int P, int K);
+void build_scan_tc_table(float norm_spacing, int M, int P, const std::vector<float>& theta, std::vector<float>& out);
 
 // The whole chain in one persistent kernel (fused.cu).  Returns 1 if launched, 0 if the shape is not covered (the caller
 // then runs the three stage kernels), <0 on error.  Bit-identical to the three-kernel path.

@@ -43,7 +43,8 @@ __device__ __forceinline__ cplx csqrt_(cplx a) {
 }
 
 // Root selection with the float arithmetic of the reference (:122-141): dist = 1 - |z| in float, strictly inside only, the T
-// closest to the circle, angle = 180*acos(arg(z)/(2 pi d))/pi with the double math of :136, ascending sort (NaNs last).
+// closest to the circle, angle = 180*acos(arg(z)/(2 pi d))/pi with the double math of :136, slots beyond the roots found = 90
+// degrees, ascending sort (NaNs -- no root inside at all -- last).
 template <class GetRoot>
 __device__ __forceinline__ void emit_angles(GetRoot root, int n, int T, bool failed, float norm_spacing, float* of) {
   unsigned long long used0 = 0ull, used1 = 0ull;
@@ -60,7 +61,11 @@ __device__ __forceinline__ void emit_angles(GetRoot root, int n, int T, bool fai
         if (dist > 0.0f && dist < best) { best = dist; bk = k; bre = re; bim = im; }
       }
     }
-    float aoa = __int_as_float(0x7fc00000);   // NaN: fewer than T roots strictly inside (reference undefined there)
+    // No root strictly inside the unit circle at all: the reference's index_min() runs on an empty vector (Armadillo throws) --
+    // NaN.  Fewer than T inside: a consumed root is overwritten with (inf, 0) and its distance with inf (:139-140), index_min of
+    // an all-inf vector returns entry 0, arg(inf + 0j) = 0 and acos(0) = pi/2: every further slot is 90 degrees (:136).
+    float aoa = (ii == 0 || failed) ? __int_as_float(0x7fc00000) : 90.0f;
+    if (bk < 0 && ii > 0 && of[0] != of[0]) aoa = __int_as_float(0x7fc00000);   // the empty set stays NaN in every slot
     if (bk >= 0) {
       if (bk < 64) used0 |= 1ull << bk; else used1 |= 1ull << (bk - 64);
       aoa = (float)(180.0 * acos((double)atan2f(bim, bre) / two_pi_d) / 3.14159265358979323846);

@@ -160,6 +160,38 @@ __device__ __forceinline__ float q_faithful(const float2* __restrict__ G, const 
   return qx;
 }
 
+// The same arithmetic with compile-time M: the steering row is loaded once into registers and the loops are unrolled, so the
+// M columns' row sums are independent instruction streams; GS = the projector is in shared memory (explicit LDS).  Operation
+// for operation q_faithful: identical bits.
+template <int MT, bool GS>
+__device__ __forceinline__ float q_faithful_t(const float2* __restrict__ G, const float2* __restrict__ v, int M) {
+  if constexpr (MT == 0) {
+    return q_faithful(G, v, M);
+  } else {
+    float2 vr[MT];
+#pragma unroll
+    for (int r = 0; r < MT; ++r) vr[r] = v[r];
+    const unsigned gs = GS ? (unsigned)__cvta_generic_to_shared(G) : 0u;
+    float qx = 0.0f;
+#pragma unroll
+    for (int c = 0; c < MT; ++c) {
+      float rx = 0.0f, ry = 0.0f;
+#pragma unroll
+      for (int r = 0; r < MT; ++r) {
+        float2 g;
+        if constexpr (GS) asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(g.x), "=f"(g.y) : "r"(gs + (unsigned)(c * MT + r) * 8u));
+        else g = G[c * MT + r];
+        const float px = __fsub_rn(__fmul_rn(vr[r].x, g.x), __fmul_rn(-vr[r].y, g.y));
+        const float py = __fadd_rn(__fmul_rn(vr[r].x, g.y), __fmul_rn(-vr[r].y, g.x));
+        rx = __fadd_rn(rx, px); ry = __fadd_rn(ry, py);
+      }
+      const float px = __fsub_rn(__fmul_rn(rx, vr[c].x), __fmul_rn(ry, vr[c].y));
+      qx = __fadd_rn(qx, px);
+    }
+    return qx;
+  }
+}
+
 __device__ __forceinline__ float db_value(float q, float qmin_global) {
   // out = 1.0/Q (double divide narrowed to float == correctly rounded float divide), out/max, 10*log10  (:140-142)
   const float y = __fdiv_rn(1.0f, q), ymax = __fdiv_rn(1.0f, qmin_global);
@@ -225,6 +257,27 @@ __device__ __forceinline__ ZTab ztab_fill(float* smem, const float* __restrict__
   return ztab_view(smem, P);
 }
 
+// K == 1, second half: refine around the coarse arg-min `bi` with the reference arithmetic and write the outputs.
+template <int MT = 0, bool GS = false>
+__device__ __forceinline__ void argmax_refine_emit(int bi, const float2* __restrict__ Gf, const float2* __restrict__ Vtab,
+                                                   const float* __restrict__ xaxis, int M, int P, int lane,
+                                                   float* __restrict__ o_val, float* __restrict__ o_loc, int* __restrict__ o_bin) {
+  constexpr unsigned FULLM = 0xffffffffu;
+  const int b = bi + lane - REFINE_W;
+  float qf = INFINITY; int qb = 0x7fffffff;
+  if (lane <= 2 * REFINE_W && b >= 0 && b < P) { qf = q_faithful_t<MT, GS>(Gf, Vtab + (size_t)b * M, M); qb = b; }
+#pragma unroll
+  for (int o = 4; o >= 1; o >>= 1) {
+    const float ov = __shfl_xor_sync(FULLM, qf, o); const int ob = __shfl_xor_sync(FULLM, qb, o);
+    if (ov < qf || (ov == qf && ob < qb)) { qf = ov; qb = ob; }
+  }
+  if (lane == 0) {
+    o_val[0] = db_value(qf, qf);
+    o_loc[0] = xaxis[qb];
+    if (o_bin) o_bin[0] = qb;
+  }
+}
+
 // K == 1 (index_max, find_local_max_impl.h:53-56): the global arg-max of one frame by one warp -- coarse arg-min of Q over
 // interleaved bins, refinement around it with the reference arithmetic, outputs.  ztab: plain z[P] table (global memory).
 template <int MT>
@@ -252,19 +305,95 @@ __device__ __forceinline__ void scan_frame_argmax(const float2* __restrict__ uf,
     const float ov = __shfl_xor_sync(FULLM, bv, o); const int oi = __shfl_xor_sync(FULLM, bi, o);
     if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
   }
-  // refine around the coarse arg-min with the reference arithmetic
-  const int b = bi + lane - REFINE_W;
-  float qf = INFINITY; int qb = 0x7fffffff;
-  if (lane <= 2 * REFINE_W && b >= 0 && b < P) { qf = q_faithful(Gf, Vtab + (size_t)b * M, M); qb = b; }
+  argmax_refine_emit(bi, Gf, Vtab, xaxis, M, P, lane, o_val, o_loc, o_bin);
+}
+
+// Second half of the peak search, shared by the Horner scan below and the tensor-core scan (scan_tc.cu): from the merged
+// coarse candidates (lane r < K holds entry r) to the K outputs.  q0 / qe: coarse values of the two end bins (never local
+// peaks, but either may hold the global minimum); q_at(bin): coarse value of any bin, used only when the frame has no local
+// minimum at all.
+template <int MT = 0, bool GS = false, typename QAT>
+__device__ __forceinline__ void peaks_refine_emit(const Merged& m, float q0, float qe, QAT&& q_at, const float2* __restrict__ Gf,
+                                                  const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int M, int P,
+                                                  int K, int lane, float* __restrict__ o_val, float* __restrict__ o_loc,
+                                                  int* __restrict__ o_bin) {
+  const int nref = min(K, m.nvalid);
+  // Global minimum of the coarse spectrum (it sets the 0 dB level): the deepest local minimum or one of the two end
+  // bins, which are never local peaks.  With no local minimum at all (a monotone spectrum) take the exact first arg-min.
+  int gbest_bin;
+  {
+    float gv = q0; gbest_bin = 0;
+    if (m.nvalid > 0) {
+      const float bv = __shfl_sync(FULL, m.val, 0); const int bb = __shfl_sync(FULL, m.bin, 0);
+      if (bv < gv) { gv = bv; gbest_bin = bb; }
+    } else {
+      float lv = INFINITY; int li = 0x7fffffff;
+      for (int i = lane; i < P; i += 32) { const float q = q_at(i); if (q < lv) { lv = q; li = i; } }
 #pragma unroll
-  for (int o = 4; o >= 1; o >>= 1) {
-    const float ov = __shfl_xor_sync(FULLM, qf, o); const int ob = __shfl_xor_sync(FULLM, qb, o);
-    if (ov < qf || (ov == qf && ob < qb)) { qf = ov; qb = ob; }
+      for (int o = 16; o >= 1; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, lv, o); const int oi = __shfl_xor_sync(FULL, li, o);
+        if (ov < lv || (ov == lv && oi < li)) { lv = ov; li = oi; }
+      }
+      gv = lv; gbest_bin = li;
+    }
+    if (qe < gv) { gv = qe; gbest_bin = P - 1; }
   }
-  if (lane == 0) {
-    o_val[0] = db_value(qf, qf);
-    o_loc[0] = xaxis[qb];
-    if (o_bin) o_bin[0] = qb;
+  // the reference's fill-in rule (find_local_max_impl.cc:145-163): global arg-max when no peak exists, otherwise
+  // all_pks_sorted_indx(0) -- the POSITION of the best peak in the peak list, used as a bin (reference bug, kept)
+  const int pad_bin = (m.nvalid == 0) ? gbest_bin : m.best_ord;
+
+  // Refinement with the reference's arithmetic.  Slot 0 = the global minimum (it sets the 0 dB level), slot 1+r =
+  // output entry r.  Eight lanes per slot, bin offset = sub-lane - REFINE_W (sub-lanes > 2W idle); entries that
+  // are fill-ins (r >= nref) are evaluated at their single bin only.
+  float fin_q = 0.f; int fin_bin = 0;     // lane r: refined entry r
+  float gmin_q = 0.f; int gmin_bin = 0;
+  for (int base = 0; base <= K; base += 4) {
+    const int slot = base + (lane >> 3), sub = lane & 7;
+    const int entry = slot - 1;
+    const int cb = __shfl_sync(FULL, m.bin, max(0, min(entry, 31)));
+    int centre = 0; bool refine = false, used = false;
+    if (slot == 0) { used = true; refine = true; centre = gbest_bin; }
+    else if (entry < K) { used = true; refine = entry < nref; centre = refine ? cb : pad_bin; }
+    const int b = centre + (refine ? sub - REFINE_W : 0);
+    const bool valid = used && b >= 0 && b < P && (refine ? sub <= 2 * REFINE_W : sub == 0);
+    float qf = INFINITY; int qb = 0x7fffffff;
+    if (valid) { qf = q_faithful_t<MT, GS>(Gf, Vtab + (size_t)b * M, M); qb = b; }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+      const float ov = __shfl_xor_sync(FULL, qf, o); const int ob = __shfl_xor_sync(FULL, qb, o);
+      if (ov < qf || (ov == qf && ob < qb)) { qf = ov; qb = ob; }
+    }
+    // hand slot results to their owner lanes
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float sv = __shfl_sync(FULL, qf, g * 8); const int sb = __shfl_sync(FULL, qb, g * 8);
+      const int sl = base + g;
+      if (sl == 0) { gmin_q = sv; gmin_bin = sb; }
+      else if (sl - 1 < K && lane == sl - 1) { fin_q = sv; fin_bin = sb; }
+    }
+  }
+  if (m.nvalid == 0) { fin_q = gmin_q; fin_bin = gmin_bin; }   // no local peak at all: every entry is the arg-max (:149-150)
+  fin_bin = min(fin_bin, P - 1);
+  {   // the 0 dB level is the smallest refined value anywhere (two nulls of near-equal depth can swap order on refinement)
+    float mq = (lane < K) ? fin_q : INFINITY;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) mq = fminf(mq, __shfl_xor_sync(FULL, mq, o));
+    gmin_q = fminf(gmin_q, mq);
+  }
+  float val = (lane < K) ? db_value(fin_q, gmin_q) : -INFINITY;
+  // entries 0..nref-1 are real peaks: order them by height like sort_index(..., "descend"); fill-ins stay behind
+  int slot = lane;
+  {
+    const float key = (lane < nref) ? val : -INFINITY;
+    const int rk = rank_desc(key, nref, lane);
+    if (lane < nref) slot = rk;
+  }
+  const float loc = (lane < K) ? xaxis[fin_bin] : -INFINITY;
+  const int lrank = rank_desc(loc, K, lane);      // sort(x_axis(pk), "descend")  find_local_max_impl.cc:188
+  if (lane < K) {
+    o_val[slot] = val;
+    o_loc[lrank] = loc;
+    if (o_bin) o_bin[slot] = fin_bin;
   }
 }
 
@@ -370,85 +499,7 @@ __device__ __forceinline__ void scan_frame_peaks(const float2* __restrict__ uf, 
     for (; k < s1 - s0; ++k) { const float q = q_at(s0 + k); w.step(prev, q, s0 + k, q_at); prev = q; }
   }
   Merged m = stitch_and_merge<KL, false>(w, K, lane, q_at);
-  const int nref = min(K, m.nvalid);
-  // Global minimum of the coarse spectrum (it sets the 0 dB level): the deepest local minimum or one of the two end
-  // bins, which are never local peaks.  With no local minimum at all (a monotone spectrum) take the exact first arg-min.
-  int gbest_bin;
-  {
-    const float q0 = q_at(0), qe = q_at(P - 1);
-    float gv = q0; gbest_bin = 0;
-    if (m.nvalid > 0) {
-      const float bv = __shfl_sync(FULL, m.val, 0); const int bb = __shfl_sync(FULL, m.bin, 0);
-      if (bv < gv) { gv = bv; gbest_bin = bb; }
-    } else {
-      float lv = INFINITY; int li = 0x7fffffff;
-      for (int i = lane; i < P; i += 32) { const float q = q_at(i); if (q < lv) { lv = q; li = i; } }
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        const float ov = __shfl_xor_sync(FULL, lv, o); const int oi = __shfl_xor_sync(FULL, li, o);
-        if (ov < lv || (ov == lv && oi < li)) { lv = ov; li = oi; }
-      }
-      gv = lv; gbest_bin = li;
-    }
-    if (qe < gv) { gv = qe; gbest_bin = P - 1; }
-  }
-  // the reference's fill-in rule (find_local_max_impl.cc:145-163): global arg-max when no peak exists, otherwise
-  // all_pks_sorted_indx(0) -- the POSITION of the best peak in the peak list, used as a bin (reference bug, kept)
-  const int pad_bin = (m.nvalid == 0) ? gbest_bin : m.best_ord;
-
-  // Refinement with the reference's arithmetic.  Slot 0 = the global minimum (it sets the 0 dB level), slot 1+r =
-  // output entry r.  Eight lanes per slot, bin offset = sub-lane - REFINE_W (sub-lanes > 2W idle); entries that
-  // are fill-ins (r >= nref) are evaluated at their single bin only.
-  float fin_q = 0.f; int fin_bin = 0;     // lane r: refined entry r
-  float gmin_q = 0.f; int gmin_bin = 0;
-  for (int base = 0; base <= K; base += 4) {
-    const int slot = base + (lane >> 3), sub = lane & 7;
-    const int entry = slot - 1;
-    const int cb = __shfl_sync(FULL, m.bin, max(0, min(entry, 31)));
-    int centre = 0; bool refine = false, used = false;
-    if (slot == 0) { used = true; refine = true; centre = gbest_bin; }
-    else if (entry < K) { used = true; refine = entry < nref; centre = refine ? cb : pad_bin; }
-    const int b = centre + (refine ? sub - REFINE_W : 0);
-    const bool valid = used && b >= 0 && b < P && (refine ? sub <= 2 * REFINE_W : sub == 0);
-    float qf = INFINITY; int qb = 0x7fffffff;
-    if (valid) { qf = q_faithful(Gf, Vtab + (size_t)b * M, M); qb = b; }
-#pragma unroll
-    for (int o = 4; o >= 1; o >>= 1) {
-      const float ov = __shfl_xor_sync(FULL, qf, o); const int ob = __shfl_xor_sync(FULL, qb, o);
-      if (ov < qf || (ov == qf && ob < qb)) { qf = ov; qb = ob; }
-    }
-    // hand slot results to their owner lanes
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const float sv = __shfl_sync(FULL, qf, g * 8); const int sb = __shfl_sync(FULL, qb, g * 8);
-      const int sl = base + g;
-      if (sl == 0) { gmin_q = sv; gmin_bin = sb; }
-      else if (sl - 1 < K && lane == sl - 1) { fin_q = sv; fin_bin = sb; }
-    }
-  }
-  if (m.nvalid == 0) { fin_q = gmin_q; fin_bin = gmin_bin; }   // no local peak at all: every entry is the arg-max (:149-150)
-  fin_bin = min(fin_bin, P - 1);
-  {   // the 0 dB level is the smallest refined value anywhere (two nulls of near-equal depth can swap order on refinement)
-    float mq = (lane < K) ? fin_q : INFINITY;
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) mq = fminf(mq, __shfl_xor_sync(FULL, mq, o));
-    gmin_q = fminf(gmin_q, mq);
-  }
-  float val = (lane < K) ? db_value(fin_q, gmin_q) : -INFINITY;
-  // entries 0..nref-1 are real peaks: order them by height like sort_index(..., "descend"); fill-ins stay behind
-  int slot = lane;
-  {
-    const float key = (lane < nref) ? val : -INFINITY;
-    const int rk = rank_desc(key, nref, lane);
-    if (lane < nref) slot = rk;
-  }
-  const float loc = (lane < K) ? xaxis[fin_bin] : -INFINITY;
-  const int lrank = rank_desc(loc, K, lane);      // sort(x_axis(pk), "descend")  find_local_max_impl.cc:188
-  if (lane < K) {
-    o_val[slot] = val;
-    o_loc[lrank] = loc;
-    if (o_bin) o_bin[slot] = fin_bin;
-  }
+  peaks_refine_emit(m, q_at(0), q_at(P - 1), q_at, Gf, Vtab, xaxis, M, P, K, lane, o_val, o_loc, o_bin);
 }
 
 }  // namespace

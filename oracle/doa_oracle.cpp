@@ -279,14 +279,29 @@ void rootmusic_one(const cf* R, int M, int T, float norm_spacing, float* out, cf
   noise_projector_f32(R, M, T, G.data(), A, w, ws);
   const int n = 2 * M - 2;
   std::vector<cf> u(2 * M - 1);
-  for (int ii = -M + 1; ii < 0; ++ii) {          // :74-78  sum(A.diag(ii)), ii<0: sub-diagonals (row = col - ii)
-    cf sacc(0.0f, 0.0f);
-    for (int c = 0; c < M + ii; ++c) sacc += G[(c - ii) + (size_t)c * M];
+  // sum(A.diag(ii)) is Armadillo's accu() of a vector-like view: two interleaved partial sums (even / odd positions), added at the end
+  auto diag_sum = [&](int ii) {                    // ii <= 0: sub-diagonal (row = col - ii)
+    const int n = M + ii;
+    cf v1(0.0f, 0.0f), v2(0.0f, 0.0f);
+    int i = 0, j = 1;
+    for (; j < n; i += 2, j += 2) { v1 += G[(i - ii) + (size_t)i * M]; v2 += G[(j - ii) + (size_t)j * M]; }
+    if (i < n) v1 += G[(i - ii) + (size_t)i * M];
+    return v1 + v2;
+  };
+  for (int ii = -M + 1; ii < 0; ++ii) {          // :74-78
+    const cf sacc = diag_sum(ii);
     u[ii + M - 1] = sacc;
     u[M - 1 - ii] = std::conj(sacc);
   }
-  { cf sacc(0.0f, 0.0f); for (int c = 0; c < M; ++c) sacc += G[c + (size_t)c * M]; u[M - 1] = sacc; }   // :79
-  const cf scale = cf(-1.0f, 0.0f) / u[2 * M - 2];                                                     // :80
+  u[M - 1] = diag_sum(0);                          // :79
+  // :80  gr_complex(-1, 0) / u(2M-2).  This file is built with -fcx-limited-range; the reference is not, so its complex<float>
+  // division is libgcc's __divsc3, which (GCC >= 11) evaluates (ac + bd) / (cc + dd), (bc - ad) / (cc + dd) in double and narrows.
+  cf scale;
+  {
+    const double a = -1.0, b = 0.0, c = u[2 * M - 2].real(), d = u[2 * M - 2].imag();
+    const double denom = (c * c) + (d * d);
+    scale = cf((float)(((a * c) + (b * d)) / denom), (float)(((b * c) - (a * d)) / denom));
+  }
   for (auto& x : u) x = scale * x;
   std::vector<cf> comp((size_t)n * n, cf(0.0f, 0.0f));
   for (int i = 0; i + 1 < n; ++i) comp[(i + 1) + (size_t)i * n] = cf(1.0f, 0.0f);                       // :55-58
@@ -301,12 +316,13 @@ void rootmusic_one(const cf* R, int M, int T, float norm_spacing, float* out, cf
   }
   std::vector<float> aoa(T, std::numeric_limits<float>::quiet_NaN());
   for (int ii = 0; ii < T; ++ii) {                                                                     // :131-141
-    if (din.empty()) break;   // reference would index an empty vector here (undefined) -> NaN, documented
-    size_t mi = 0;
+    if (din.empty()) break;   // no root strictly inside the unit circle: the reference's index_min() throws (Armadillo: "object has no elements") -> NaN
+    size_t mi = 0;            // index_min keeps the FIRST smallest value; once every entry is inf that is entry 0
     for (size_t k = 1; k < din.size(); ++k) if (din[k] < din[mi]) mi = k;
-    if (std::isinf(din[mi])) break;
+    // a consumed root is (inf, 0) (:140): arg = 0, acos(0) = pi/2 -> 90 degrees for every slot beyond the roots found
     aoa[ii] = (float)(180.0 * std::acos((double)std::arg(rin[mi]) / (2 * kPi * (double)norm_spacing)) / kPi);   // :136
     din[mi] = std::numeric_limits<float>::infinity();
+    rin[mi] = cf(std::numeric_limits<float>::infinity(), 0.0f);
   }
   std::sort(aoa.begin(), aoa.end(), [](float a, float b) { return a < b; });                            // :144 (NaN unordered; only hit when undefined)
   for (int i = 0; i < T; ++i) out[i] = aoa[i];
