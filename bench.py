@@ -4,19 +4,28 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
 
-Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 65,536 independent 8-element ULA frames
-x 2048 snapshots (8 GiB of complex64, resident in HBM before the timed region), 3 sources at 10 dB SNR, 4096-point angle
-scan, K = 3 peaks.  A step = one pass of the whole chain over that batch.  For N > 1 every rank owns a batch of the same
-size (weak scaling; frames are independent, no data-path collective) and ONE gather of the per-frame peaks to rank 0
-closes each step.  Inputs (8 GiB) are far larger than L2 (126 MB), so no flush is needed between iterations.
+Headline workload (BASELINE.json configs[2], the configuration the metric is quoted on): 65,536 independent 8-element ULA
+frames x 2048 snapshots (8 GiB of complex64, resident in HBM before the timed region), 3 sources at 10 dB SNR, 4096-point
+angle scan, K = 3 peaks.  A step = one pass of the whole chain over that batch.  For N > 1 every rank owns a batch of the same
+size (weak scaling; frames are independent, no data-path collective) and ONE gather of the per-frame peaks to rank 0 closes
+each step.  Inputs (8 GiB) are far larger than L2 (126 MB), so no flush is needed between iterations.
 
-JSON keys beyond the base contract: roofline (the covariance kernel -- the dominant one -- against measured HBM copy
-bandwidth, plus the whole chain's algorithmic bytes / step time), cpu_baseline (the CPU oracle = LAPACK restatement of
-the reference, timed on this box's host cores on a bounded sample of the same frames), e2e (the same chain through the
-host-pointer C-ABI call, H2D/D2H inside the timed region), clocks, gpu_launches.
+JSON keys beyond the base contract:
+  roofline      the chain kernel against measured HBM copy bandwidth (algorithmic bytes / CUDA-event launch time)
+  sustained     the same step back to back for >= 2 s (the headline's K steps last tens of milliseconds): ms/step, roofline
+                fraction, the time course in slices, SM / memory clocks, power and temperature sampled through NVML
+  cpu_baseline  the reference's CPU path on this box's host cores, bounded sample of the same frames: the reference's own
+                block sources (oracle/_ref, kind "reference") when that build is present, and the port (oracle/doa_oracle.cpp)
+  parity        exemption rates measured on that sample: frames whose peak bins differ from the CPU arm, how many of them
+                are near-ties, and how many are unexplained (must be 0)
+  e2e           the same chain through the host-pointer C-ABI call, H2D/D2H inside the timed region, per-rank H2D GB/s
+  other_configs the other BASELINE.json configs (N = 1: cfg1 streaming with overlap 512 and both averaging methods, cfg2
+                Root-MUSIC chain, cfg4 large array; every N: cfg5 = 1,048,576 16-element frames x 1024 snapshots STRONG-scaled
+                over the ranks, one peak gather per step), each with ms, frames/s, roofline fraction and (N = 1) its CPU arm
+  clocks, gpu_launches
 
---impl reference times the reference arm: the reference's CPU algorithm (oracle port; the reference itself needs GNU
-Radio + Armadillo and cannot be built here) on all host cores, bounded sample per step.
+--impl reference times the reference arm on the host cores: oracle/_ref (the reference's unmodified lib/*_impl.cc compiled
+against the Armadillo / GNU Radio stand-ins, oracle/build_ref.py) when present, else the port; bounded sample per step.
 """
 import argparse
 import json
@@ -31,8 +40,14 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(frames=65536, M=8, N=2048, T=3, P=4096, K=3, d=0.5, thetas=[40.0, 90.0, 140.0], jitter=5.0, snr_db=10.0)
 METRIC, UNIT = "doa_frames_per_s", "frames/s"
-ALG_BYTES_CHAIN = lambda w: 8 * w["M"] * w["N"] + 8 * w["K"]              # samples in once + K (value, location) out
-ALG_BYTES_COV = lambda w: 8 * w["M"] * w["N"] + 8 * w["M"] * w["M"]       # autocorrelate stage: samples in + M*M complex out
+ALG_BYTES_CHAIN = lambda w: 8 * w["M"] * (w["hop"] if "hop" in w else w["N"]) + 8 * w["K"]     # unique samples in once + K (value, location) out
+ALG_BYTES_COV = lambda w: 8 * w["M"] * w["N"] + 8 * w["M"] * w["M"]            # autocorrelate stage: samples in + M*M complex out
+
+# the other BASELINE.json configs (SURVEY 8(d) shapes); cfg5's T, P, K are not given by BASELINE.json: T3, P4096, K3 assumed
+CFG1 = dict(name="cfg1", M=4, N=2048, overlap=512, T=1, P=2048, K=1, thetas=[60.0], frames=262144)
+CFG2 = dict(name="cfg2", M=4, N=2048, overlap=512, T=2, thetas=[50.0, 110.0], frames=262144, avg=1)
+CFG4 = dict(name="cfg4", M=64, N=16384, T=8, P=16384, K=8, thetas=[30.0 + 120.0 * i / 7 for i in range(8)], frames=512)
+CFG5 = dict(name="cfg5", M=16, N=1024, T=3, P=4096, K=3, thetas=[40.0, 90.0, 140.0], frames=1048576)
 
 
 def workload_text(w):
@@ -49,13 +64,14 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    """Samples SM / memory clocks, power, temperature and throttle reasons of one GPU through NVML while a timed region runs."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake"}
 
-    def __init__(self, index, period=0.004):
+    def __init__(self, index, period=0.004, detailed=False):
         super().__init__(daemon=True)
-        self.index, self.period = index, period
+        self.index, self.period, self.detailed = index, period, detailed
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.mem, self.power, self.temp, self.stamps = [], [], [], []
         self._stop_evt = threading.Event()
         self.ok = False
         try:
@@ -71,13 +87,19 @@ class ClockSampler(threading.Thread):
     def run(self):
         if not self.ok:
             return
+        nv = self.nv
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.stamps.append(time.perf_counter())
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for bit, name in self.REASONS.items():
                     if mask & bit:
                         self.reasons.add(name)
+                if self.detailed:
+                    self.mem.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM))
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                    self.temp.append(nv.nvmlDeviceGetTemperature(self.h, nv.NVML_TEMPERATURE_GPU))
             except Exception:
                 pass
             time.sleep(self.period)
@@ -87,41 +109,98 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        out = {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(self.samples)}
+        if self.detailed and self.power:
+            n = len(self.samples)
+            q = max(1, n // 4)
+            out.update({"sm_mhz_min": min(self.samples), "mem_mhz": statistics.median(self.mem), "mem_mhz_min": min(self.mem),
+                        "power_w_first_quarter": statistics.mean(self.power[:q]), "power_w_last_quarter": statistics.mean(self.power[-q:]),
+                        "power_w_max": max(self.power), "temp_c_first": self.temp[0], "temp_c_last": self.temp[-1],
+                        "sample_period_ms": 1e3 * (self.stamps[-1] - self.stamps[0]) / max(1, n - 1)})
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU arm
+def cpu_arm():
+    """(module, kind): the reference's own sources when oracle/_ref is built (here or prebuilt), else the port."""
+    try:
+        from oracle import reference as REF
+        if REF.available():
+            REF.lib()
+            return REF, "reference"
+    except Exception:
+        pass
+    from oracle import oracle as O
+    return O, "port"
+
+
+def cpu_chain(mod, kind, frames, avg, d, T, P, K, cores, root=False):
+    """One timed pass of the CPU arm over `frames`: (values, locations, bins or None, seconds).  The reference build runs as
+    `cores` single-threaded worker processes (its thousands of tiny BLAS calls per frame serialise the threads of one process on
+    OpenBLAS's buffer lock: oracle/ref_worker.py), the port as OpenMP threads over frames."""
+    if kind == "reference":
+        outs, sec = mod.chain_frames_procs(frames, avg, d, T, P, K, cores, root=root)
+        return (outs[0], None, None, sec) if root else (outs[0], outs[1], None, sec)
+    t0 = time.perf_counter()
+    if root:
+        aoa = mod.rootmusic(mod.autocorrelate_frames(frames, avg, nthreads=cores), d, T, frames.shape[1], nthreads=cores)
+        return aoa, None, None, time.perf_counter() - t0
+    val, loc, bins = mod.chain_frames(frames, avg, d, T, P, K, nthreads=cores)
+    return val, loc, bins, time.perf_counter() - t0
 
 
 def run_reference(args, w):
-    """Reference arm: the reference's CPU algorithm (oracle port) on all host cores; each step = a bounded sample."""
+    """Reference arm: the reference's CPU implementation on all host cores; each step = a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import numpy as np
-    from oracle import oracle as O
     from gr_doa_b200 import synth
-    cores = O.max_threads()
-    per_step = 128 * cores                      # ~0.7 ms/frame/core -> ~0.1 s per step
+    mod, kind = cpu_arm()
+    cores = mod.max_threads()
+    per_step = (64 if kind == "reference" else 128) * cores     # ~2 ms (reference build) / ~0.5 ms (port) per frame and core
     fr, _ = synth.frames_numpy(per_step, w["M"], w["N"], w["thetas"], d=w["d"], snr_db=w["snr_db"], jitter_deg=w["jitter"],
                                seed=synth.SEED_BASE + 3)
-    for _ in range(args.warmup):
-        O.chain_frames(fr, 0, w["d"], w["T"], w["P"], w["K"], nthreads=cores)
-    t0 = time.perf_counter()
+    for _ in range(min(args.warmup, 1)):
+        cpu_chain(mod, kind, fr, 0, w["d"], w["T"], w["P"], w["K"], cores)
+    dt = 0.0
     for _ in range(args.steps):
-        O.chain_frames(fr, 0, w["d"], w["T"], w["P"], w["K"], nthreads=cores)
-    dt = time.perf_counter() - t0
+        dt += cpu_chain(mod, kind, fr, 0, w["d"], w["T"], w["P"], w["K"], cores)[3]
     value = per_step * args.steps / dt
+    what = ("gr-doa's unmodified lib/{autocorrelate,MUSIC_lin_array,find_local_max}_impl.cc (oracle/_ref: Armadillo / GNU Radio stand-ins, OpenBLAS), "
+            "one single-threaded worker process per core (oracle/ref_worker.py), timed pass of the slowest worker" if kind == "reference" else "oracle port (oracle/doa_oracle.cpp), OpenMP over frames")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_text(w), "sample_frames_per_step": per_step},
         "msamples_per_s_per_stream": value * w["N"] / 1e6,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step} frames of the workload per step x {args.steps} steps, OpenMP over frames, BLAS single-threaded"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{per_step} frames of the workload per step x {args.steps} steps; {what}; BLAS single-threaded"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------- helpers
+def classify_against_cpu(np, O, sub, bins_gpu, bins_cpu, w, cores):
+    """Exemption rates on a CPU-checked sample: frames whose sorted peak bins differ, how many are near-ties (one bin apart and
+    closer, in the float64 null spectrum, than 8x the float32 CPU path's own distance from it: tests/parity.py), how many not."""
+    bg, bc = np.sort(bins_gpu, axis=1), np.sort(bins_cpu, axis=1)
+    diff = np.where((bg != bc).any(axis=1))[0]
+    near, unexplained = 0, 0
+    if len(diff):
+        R = O.autocorrelate_frames(sub[diff], 0, nthreads=cores)
+        q64 = O.music_f64(R, w["d"], w["T"], w["M"], w["P"], nthreads=cores)
+        q32 = O.music_q(R, w["d"], w["T"], w["M"], w["P"], nthreads=cores)
+        for i, f in enumerate(diff):
+            noise = float(np.abs(q32[i].astype(np.float64) - q64[i]).max())
+            ok = all(a == b or (abs(int(a) - int(b)) <= 1 and abs(q64[i, a] - q64[i, b]) <= 8.0 * noise) for a, b in zip(bg[f], bc[f]))
+            near += ok
+            unexplained += (not ok)
+    n = len(bins_gpu)
+    return {"frames_checked": n, "frames_with_different_bins": int(len(diff)), "near_tie_frac": near / n, "unexplained_bins": int(unexplained)}
 
 
 def main():
@@ -134,6 +213,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sc16", action="store_true", help="skip the informational sc16-input arm")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configs (cfg1, cfg2, cfg4, cfg5)")
+    ap.add_argument("--cfg5-frames", type=int, default=CFG5["frames"], help="total frames of the strong-scaled cfg5 run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = dict(WORKLOAD, frames=args.frames)
@@ -156,6 +238,20 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    peak, peak_src = measured_peaks()
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
 
     B, M, N, T, P, K = w["frames"], w["M"], w["N"], w["T"], w["P"], w["K"]
     x, _ = synth.frames_torch(B, M, N, w["thetas"], d=w["d"], snr_db=w["snr_db"], jitter_deg=w["jitter"],
@@ -167,8 +263,8 @@ def main():
     # NCCL: 8 GPUs 1.87-1.95 -> 1.74 ms per step, 4 GPUs no change, 2 GPUs 2-3 % slower (the reserved SMs)
     pipelined = os.environ.get("DOA_PIPELINE", "1" if world > 4 else "0") != "0"
     peaks = sharding.PeakExchange(B, K, dev, world=world, is_dst=(rank == 0), pipelined=pipelined)
-    if world > 1 and pipelined:
-        _lib.lib().doa_cuda_dev_set(b"chain_sms_reserve", int(os.environ.get("DOA_SMS_RESERVE", "2")))
+    reserve = int(os.environ.get("DOA_SMS_RESERVE", "2")) if (world > 1 and pipelined) else 0
+    chain.set_sms_reserve(reserve)
     out = peaks.bufs[0].outputs()
     total = B * world
 
@@ -177,12 +273,6 @@ def main():
         out = peaks.begin()
         chain.run_device(x, out=out)
         peaks.submit()
-
-    def fence():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         step()
@@ -204,13 +294,35 @@ def main():
     ms = e0.elapsed_time(e1)
     cov_ms, eig_ms, scan_ms = chain.stage_ms()
     chain.set_profiling(False)
-    fused = chain.launches() == 1          # one persistent kernel for the whole chain: the stage timers read (0, 0, total)
-    if world > 1:
-        t = torch.tensor([ms, cov_ms, eig_ms, scan_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, cov_ms, eig_ms, scan_ms = [float(v) for v in t.tolist()]
+    nlaunch = chain.launches()
+    fused = nlaunch == 1          # one persistent kernel for the whole chain: the stage timers read (0, 0, total)
+    ms, cov_ms, eig_ms, scan_ms = max_over_ranks([ms, cov_ms, eig_ms, scan_ms])
     ms_per_step = ms / args.steps
     value = total / (ms_per_step * 1e-3)
+
+    # ---- the sustained regime: the same step back to back for >= 2 s, time course in slices, NVML samples --------------------
+    sustained = None
+    if not args.no_sustained:
+        n_slices, slice_steps = 10, max(10, int(0.25 / (ms_per_step * 1e-3)))     # ~0.25 s per slice
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_slices + 1)]
+        fence()
+        smp = ClockSampler(local, period=0.001, detailed=True)
+        smp.start()
+        evs[0].record()
+        for s in range(n_slices):
+            for _ in range(slice_steps):
+                step()
+            peaks.drain()
+            evs[s + 1].record()
+        fence()
+        sclk = smp.stop()
+        course = [evs[s].elapsed_time(evs[s + 1]) / slice_steps for s in range(n_slices)]
+        course = [max_over_ranks([c])[0] for c in course]
+        sus_ms = sum(course) / n_slices
+        sustained = {"seconds": sum(course) * slice_steps * 1e-3, "steps": n_slices * slice_steps, "ms_per_step": sus_ms,
+                     "value": total / (sus_ms * 1e-3), "unit": UNIT,
+                     "roofline_frac_chain": ALG_BYTES_CHAIN(w) * B / (sus_ms * 1e-3) / 1e9 / peak,
+                     "ms_per_step_by_slice": [round(c, 4) for c in course], "vs_burst": sus_ms / ms_per_step, "nvml": sclk}
 
     # ---- end to end through the host-pointer C-ABI call (pinned host buffers, copies inside the timed region) ----
     e2e = None
@@ -226,20 +338,39 @@ def main():
         esteps = max(3, min(args.steps, 10))
         for _ in range(2):
             chain.run_host(hx, out=hout)
+        # bare copy rate of this rank while every rank copies (what the platform gives; the chain call cannot beat it)
+        dbuf = torch.empty((min(eb, 8192), M, N), dtype=torch.complex64, device=dev)
+        fence()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(0, eb - dbuf.shape[0] + 1, dbuf.shape[0]):
+            dbuf.copy_(hx[i:i + dbuf.shape[0]], non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        bare_gbps = (eb // dbuf.shape[0]) * dbuf.numel() * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del dbuf
         fence()
         t0 = time.perf_counter()
         for _ in range(esteps):
             chain.run_host(hx, out=hout)      # synchronous: returns when the peaks are in host memory
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        dt_local = time.perf_counter() - t0
+        dt = max_over_ranks([dt_local])[0]
+        h2d = eb * M * N * 8
+        rates = [h2d * esteps / dt_local / 1e9, bare_gbps]
         if world > 1:
-            tt = torch.tensor([dt], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        e2e = {"value": eb * world * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": eb * M * N * 8, "d2h_bytes_per_step": eb * K * 12,
+            gl = [torch.zeros(2, device=dev, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(gl, torch.tensor(rates, device=dev, dtype=torch.float64))
+            per_rank = [[round(float(v), 2) for v in g.tolist()] for g in gl]
+        else:
+            per_rank = [[round(v, 2) for v in rates]]
+        e2e = {"value": eb * world * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": eb * K * 12,
                "frames_per_step_per_gpu": eb, "steps": esteps, "ms_per_step": dt / esteps * 1e3,
+               "h2d_GBps_per_rank": [p[0] for p in per_rank], "bare_pinned_memcpy_GBps_per_rank": [p[1] for p in per_rank],
+               "h2d_GBps_aggregate": sum(p[0] for p in per_rank),
                "api": "doa_cuda_chain_run (host pointers, chunked H2D overlapped with kernels, synchronous)",
-               "timer": "host wall clock around the synchronous calls, max over ranks"}
+               "timer": "host wall clock around the synchronous calls, max over ranks",
+               "note": "PCIe-bound: the chain call moves its input at the rate a bare cudaMemcpyAsync loop from the same pinned buffer reaches on this rank while all ranks copy"}
         assert torch.equal(hout[2].cuda(), out[2][:eb]), "host path and device path disagree"
         del hx
 
@@ -284,8 +415,8 @@ def main():
         finally:
             chain.set_input_format("fc32")
 
-    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample of the same frames (rank 0, N = 1) ----
-    cpu = None
+    # ---- CPU baseline + exemption rates: the reference's CPU path on this box's host cores, bounded sample of the same frames ----
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as O
         cores = O.max_threads()
@@ -294,14 +425,41 @@ def main():
         O.chain_frames(sub[:256], 0, w["d"], T, P, K, nthreads=cores)
         t0 = time.perf_counter()
         v_o, l_o, b_o = O.chain_frames(sub, 0, w["d"], T, P, K, nthreads=cores)
-        dt = time.perf_counter() - t0
-        same = float((np.sort(out[2][:ns].cpu().numpy(), 1) == np.sort(b_o, 1)).all(1).mean())
-        cpu = {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {ns} frames of the timed batch, OpenMP over frames ({cores} threads), BLAS single-threaded",
-               "peak_bins_identical_frac": same}
+        dt_port = time.perf_counter() - t0
+        bins_gpu = out[2][:ns].cpu().numpy()
+        parity = {"against_port": classify_against_cpu(np, O, sub, bins_gpu, b_o, w, cores)}
+        cpu = {"value": ns / dt_port, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {ns} frames of the timed batch, oracle port, OpenMP over frames ({cores} threads), BLAS single-threaded",
+               "peak_bins_identical_frac": 1.0 - parity["against_port"]["frames_with_different_bins"] / ns}
+        mod, kind = cpu_arm()
+        if kind == "reference":
+            nr = min(ns, 256 * cores)
+            v_r, l_r, _, dt_ref = cpu_chain(mod, kind, sub[:nr], 0, w["d"], T, P, K, cores)
+            bins_ref = np.rint(l_r.astype(np.float64) * P / 180.0).astype(np.int64)
+            parity["against_reference_build"] = classify_against_cpu(np, O, sub[:nr], bins_gpu[:nr], bins_ref, w, cores)
+            parity["port_vs_reference_build"] = classify_against_cpu(np, O, sub[:nr], b_o[:nr], bins_ref, w, cores)
+            cpu = {"value": nr / dt_ref, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"first {nr} frames of the timed batch through gr-doa's unmodified block sources (oracle/_ref), one single-threaded worker process per core ({cores}), BLAS single-threaded; timed pass of the slowest worker",
+                   "peak_bins_identical_frac": 1.0 - parity["against_reference_build"]["frames_with_different_bins"] / nr,
+                   "port": {"value": ns / dt_port, "sample_frames": ns, "threads": cores}}
+
+    del x, peaks
+    chain.close()
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs -------------------------------------------------------------------------------------
+    others = None
+    if not args.no_others:
+        others = {}
+        try:
+            if world == 1:
+                others.update(bench_small_configs(doa, synth, torch, np, dev, local, peak, args))
+            others["cfg5"] = bench_cfg5(doa, synth, sharding, torch, dist, np, dev, local, rank, world, peak, args, fence, max_over_ranks)
+        except Exception as ex:     # never lose the headline line to the additional configs
+            import traceback
+            others["error"] = repr(ex) + " | " + traceback.format_exc()[-600:]
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
         kern_ms = (cov_ms + eig_ms + scan_ms) if fused else cov_ms
         kern_bytes = (ALG_BYTES_CHAIN(w) if fused else ALG_BYTES_COV(w)) * B
         cov_gbs = kern_bytes / (kern_ms * 1e-3) / 1e9
@@ -319,7 +477,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_text(w), "frames_per_gpu": B, "parallelism": f"frames sharded x{world}, one peak gather per step" + (" (double-buffered on a side stream, under the next step's kernel; 2 SMs left to NCCL)" if (world > 1 and pipelined) else ""),
                        "l2": "inputs (8 GiB/GPU) larger than L2 (126 MB): no flush between iterations",
-                       "timer": "CUDA events on the launching stream, max over ranks"},
+                       "timer": "CUDA events on the launching stream, max over ranks",
+                       "regime": f"burst: {args.steps} steps = {ms:.0f} ms; see `sustained` for >= 2 s of back-to-back steps"},
             "msamples_per_s_per_stream": value * N / 1e6,
             "msamples_per_s_aggregate": value * N * M / 1e6,
             "roofline": {"bound": "hbm", "achieved": cov_gbs, "peak": peak, "unit": "GB/s", "frac": cov_gbs / peak,
@@ -330,9 +489,12 @@ def main():
                          "stage_ms": ({"fused_chain": kern_ms} if fused else {"cov": cov_ms, "eig": eig_ms, "scan_peaks": scan_ms}),
                          "chain": {"algorithmic_bytes_per_frame": ALG_BYTES_CHAIN(w), "achieved": chain_gbs,
                                    "frac": chain_gbs / peak, "note": "whole step (chain kernel" + ("" if fused else "s") + (" + peak gather" if world > 1 else "") + ") per GPU against the same HBM peak"}},
+            "sustained": sustained,
             "cpu_baseline": cpu,
+            "parity": parity,
             "e2e": e2e,
             "sc16_input": sc16,
+            "other_configs": others,
             "gpu_launches": launches,
             "clocks": clocks,
         }
@@ -341,6 +503,173 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def time_calls(torch, fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def bench_small_configs(doa, synth, torch, np, dev, local, peak, args):
+    """cfg1 (the reference's own app shape: streaming, overlap 512, both averaging methods), cfg2 (Root-MUSIC chain), cfg4 (large
+    array) on one GPU, inputs resident; each next to the CPU arm on a bounded sample of the same shape."""
+    res = {}
+    mod, kind = (None, None) if args.no_cpu else cpu_arm()
+    cores = mod.max_threads() if mod else 0
+
+    def cpu_rate(c, avg, n_per_core, root=False):
+        if mod is None:
+            return None
+        n = max(cores, n_per_core * cores)
+        fr, _ = synth.frames_numpy(n, c["M"], c["N"], c["thetas"], snr_db=10.0, jitter_deg=2.0, seed=synth.SEED_BASE + 50)
+        dt = cpu_chain(mod, kind, fr, avg, 0.5, c["T"], c.get("P", 0), c.get("K", 0), cores, root=root)[3]
+        return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{n} independent frames of this shape"}
+
+    # cfg1 / cfg2: M channel streams, frames overlap by 512 samples (hop 1536): the covariance reads them in place
+    for c in (CFG1, CFG2):
+        hop = c["N"] - c["overlap"]
+        Bc = c["frames"]
+        L = (Bc - 1) * hop + c["N"]
+        xs = synth.stream_torch(c["M"], L, c["thetas"], snr_db=10.0, seed=synth.SEED_BASE + 11, device=dev)     # [M][L]
+        wb = dict(M=c["M"], hop=hop, K=c.get("K", 0))
+        if c is CFG1:
+            for avg in (0, 1):
+                ch = doa.DoaChain(c["M"], c["N"], c["overlap"], avg, 0.5, c["T"], c["P"], c["K"], device=local, max_frames=Bc)
+                ms = time_calls(torch, lambda: ch.run_device(xs, frame_stride=hop, chan_stride=L, nframes=Bc), 10)
+                gbs = ALG_BYTES_CHAIN(wb) * Bc / (ms * 1e-3) / 1e9
+                res["cfg1_" + ("fb" if avg else "fwd")] = {
+                    "workload": f"{Bc} frames of 4 channel streams, snapshot 2048, overlap 512 (hop 1536), avg_method {avg}, 1 source, P 2048, K 1 (index_max)",
+                    "ms": ms, "frames_per_s": Bc / (ms * 1e-3), "msamples_per_s_per_stream": Bc * hop / (ms * 1e-3) / 1e6,
+                    "launches": ch.launches(), "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": ALG_BYTES_CHAIN(wb), "achieved": gbs, "frac": gbs / peak},
+                    "cpu_baseline": cpu_rate(c, avg, 64)}
+                ch.close()
+        else:
+            rc = doa.RootMusicChain(c["M"], c["N"], c["overlap"], 1, 0.5, c["T"], device=local, max_frames=Bc)
+            ms = time_calls(torch, lambda: rc.run_device(xs, frame_stride=hop, chan_stride=L, nframes=Bc), 10)
+            bytes_pf = 8 * c["M"] * hop + 4 * c["T"]
+            gbs = bytes_pf * Bc / (ms * 1e-3) / 1e9
+            aoa = rc.run_device(xs, frame_stride=hop, chan_stride=L, nframes=Bc)
+            res["cfg2_rootmusic"] = {
+                "workload": f"{Bc} frames of 4 channel streams, snapshot 2048, overlap 512, forward-backward averaging, 2 sources (autocorrelate -> rootMUSIC_linear_array)",
+                "ms": ms, "frames_per_s": Bc / (ms * 1e-3), "launches": rc.launches(), "nan_frac": float(torch.isnan(aoa).any(1).float().mean()),
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": bytes_pf, "achieved": gbs, "frac": gbs / peak},
+                "cpu_baseline": cpu_rate(c, 1, 128, root=True)}
+            if mod is not None:   # Root-MUSIC exemption rate: frames whose selected root is within 4e-4 of the unit circle (tests/parity.py)
+                from oracle import oracle as O
+                nchk = 4096
+                Rr = O.autocorrelate(xs[:, :(nchk - 1) * hop + c["N"]].cpu().numpy(), c["N"], c["overlap"], 1)
+                a64, d64 = O.rootmusic_f64(Rr, 0.5, c["T"], c["M"], nthreads=cores, return_dist=True)
+                good = np.nanmin(d64, axis=1) >= 4e-4
+                err = np.abs(aoa[:nchk].cpu().numpy() - a64)
+                res["cfg2_rootmusic"]["parity"] = {"frames_checked": nchk, "near_circle_frac": float((~good).mean()),
+                                                   "max_abs_err_deg_vs_float64_on_good_frames": float(err[good].max()) if good.any() else None}
+            rc.close()
+        del xs
+        torch.cuda.empty_cache()
+
+    # cfg4: 64-element array (tensor-core HERK covariance, block Jacobi, wide scan)
+    c = CFG4
+    Bc = c["frames"]
+    x4, _ = synth.frames_torch(Bc, c["M"], c["N"], c["thetas"], jitter_deg=2.0, device=dev, chunk=32, seed=synth.SEED_BASE + 4)
+    ch = doa.DoaChain(c["M"], c["N"], 0, 0, 0.5, c["T"], c["P"], c["K"], device=local, max_frames=Bc)
+    ms = time_calls(torch, lambda: ch.run_device(x4), 10)
+    ch.set_profiling(True)
+    for _ in range(5):
+        ch.run_device(x4)
+    torch.cuda.synchronize()
+    st = ch.stage_ms()
+    ch.set_profiling(False)
+    wb = dict(M=c["M"], N=c["N"], K=c["K"])
+    gbs = ALG_BYTES_CHAIN(wb) * Bc / (ms * 1e-3) / 1e9
+    herk_tflops = 3 * 2.0 * 128 * 64 * 2 * c["N"] * Bc / (st[0] * 1e-3) / 1e12        # 3xTF32 real MMA flops of [Z; W] Z^T
+    res["cfg4"] = {"workload": f"{Bc} independent 64-element frames x 16384 snapshots, 8 sources, 16384-point scan, K 8",
+                   "ms": ms, "frames_per_s": Bc / (ms * 1e-3), "stage_ms": {"cov_herk_tc": st[0], "jacobi": st[1], "scan_peaks": st[2]},
+                   "launches": ch.launches(),
+                   "roofline": {"bound": "tensor (covariance) / latency (Jacobi)", "algorithmic_bytes_per_frame": ALG_BYTES_CHAIN(wb),
+                                "achieved_GBps": gbs, "frac_hbm": gbs / peak, "herk_tf32_mma_TFLOPs": herk_tflops,
+                                "herk_input_GBps": 8.0 * c["M"] * c["N"] * Bc / (st[0] * 1e-3) / 1e9},
+                   "cpu_baseline": cpu_rate(c, 0, 1)}
+    ch.close()
+    del x4
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_cfg5(doa, synth, sharding, torch, dist, np, dev, local, rank, world, peak, args, fence, max_over_ranks):
+    """BASELINE configs[4]: 1,048,576 16-element frames x 1024 snapshots, STRONG-scaled: rank r owns frames
+    shard_range(total, r, world) (generated on its device, resident before the timed region), one gather of the peak indices per
+    step.  value = total frames / max-over-ranks step time."""
+    c = CFG5
+    total = args.cfg5_frames
+    lo, hi = sharding.shard_range(total, rank, world)
+    Bl = hi - lo
+    M, N, T, P, K = c["M"], c["N"], c["T"], c["P"], c["K"]
+    x5, _ = synth.frames_torch(Bl, M, N, c["thetas"], jitter_deg=5.0, device=dev, chunk=8192, seed=synth.SEED_BASE + 5 + 1000 * rank)
+    call = min(Bl, 262144)                                     # frames per chain call: bounds the per-call intermediates (R, G, u)
+    ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, device=local, max_frames=call)
+    longest = -(-total // world)
+    pk = sharding.PeakExchange(longest, K, dev, world=world, is_dst=(rank == 0), pipelined=False)
+
+    def step():
+        val, loc, bins = pk.begin()
+        for f0 in range(0, Bl, call):
+            n = min(call, Bl - f0)
+            ch.run_device(x5[f0:f0 + n], out=(val[f0:f0 + n], loc[f0:f0 + n], bins[f0:f0 + n]))
+        pk.submit()
+
+    steps = 5
+    for _ in range(3):
+        step()
+    pk.drain()
+    fence()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nl = 0
+    for _ in range(steps):
+        step()
+        nl += ch.launches() * (-(-Bl // call))
+    pk.drain()
+    e1.record()
+    fence()
+    ms = max_over_ranks([e0.elapsed_time(e1) / steps])[0]
+    # kernel-only time of this rank's shard (no gather), and the stage split
+    kms = time_calls(torch, lambda: [ch.run_device(x5[f0:f0 + min(call, Bl - f0)]) for f0 in range(0, Bl, call)], 3, warmup=1)
+    ch.set_profiling(True)
+    for _ in range(2):
+        ch.run_device(x5[:call])
+    torch.cuda.synchronize()
+    st = ch.stage_ms()
+    ch.set_profiling(False)
+    kms = max_over_ranks([kms])[0]
+    bytes_pf = 8 * M * N + 8 * K
+    res = {"workload": f"{total} independent 16-element frames x 1024 snapshots, 3 sources, 4096-point scan, K 3 (T, P, K assumed: BASELINE.json gives none), strong-scaled over {world} rank(s)",
+           "scaling": "strong", "n_ranks": world, "frames_total": total, "frames_per_gpu": Bl, "ms_per_step": ms,
+           "frames_per_s": total / (ms * 1e-3), "msamples_per_s_per_stream": total * N / (ms * 1e-3) / 1e6,
+           "kernel_ms_per_step_per_gpu": kms, "exposed_gather_ms": ms - kms, "launches_per_step": ch.launches() * (-(-Bl // call)),
+           "stage_ms_per_call": {"frames": call, "cov": st[0], "jacobi": st[1], "scan_peaks": st[2]},
+           "roofline": {"bound": "fp32 pipe (8.5 flop/B covariance + 16x16 Jacobi), reported against HBM", "algorithmic_bytes_per_frame": bytes_pf,
+                        "achieved_GBps_per_gpu": bytes_pf * Bl / (ms * 1e-3) / 1e9, "frac": bytes_pf * Bl / (ms * 1e-3) / 1e9 / peak,
+                        "frac_kernels_only": bytes_pf * Bl / (kms * 1e-3) / 1e9 / peak},
+           "timer": "CUDA events, max over ranks; inputs resident (generated per shard on the device); gather of the peaks inside the timed region"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        mod, kind = cpu_arm()
+        cores = mod.max_threads()
+        n = 16 * cores
+        fr = x5[:n].cpu().numpy()
+        dt = cpu_chain(mod, kind, fr, 0, 0.5, T, P, K, cores)[3]
+        res["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"first {n} frames of the shard"}
+    ch.close()
+    del x5, pk
+    torch.cuda.empty_cache()
+    return res
 
 
 if __name__ == "__main__":

@@ -5,7 +5,10 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdoa_cuda.so")
+DEV_LIB_PATH = os.path.join(_HERE, "libdoa_cuda_dev.so")      # -DDOA_DEV_KNOBS build: experimental kernel variants (tools/, tests)
 _lib = None
+_dev_lib = None
+_use_dev = False
 
 OK, EINVAL, ECUDA, ENOMEM, ECAPACITY = 0, -1, -2, -3, -4
 
@@ -55,6 +58,8 @@ SYMBOLS = {
     "doa_cuda_multi_block": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "doa_cuda_pin_host_buffer": (_i, [_vp, C.c_ulonglong]),
     "doa_cuda_unpin_host_buffer": (_i, [_vp]),
+    "doa_cuda_set_option": (_i, [_vp, C.c_char_p, _i]),
+    "doa_cuda_has_dev_knobs": (_i, []),
     "doa_cuda_destroy": (None, [_vp]),
 }
 
@@ -65,23 +70,45 @@ class DoaCudaError(RuntimeError):
         self.code = code
 
 
-def lib():
-    """Load libdoa_cuda.so (built in-tree by gr_doa_b200.build).  Raises if absent: no fallback exists."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} not found: build it with `python -m gr_doa_b200.build` "
+def _load(path):
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found: build it with `python -m gr_doa_b200.build" + (" --dev" if path == DEV_LIB_PATH else "") + "` "
                           "(libdoa_cuda is the only compute path; there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(L, name)   # AttributeError if the library does not export what the header declares
         fn.restype = res
         fn.argtypes = args
-    L.doa_cuda_dev_set.restype = _i
-    L.doa_cuda_dev_set.argtypes = [C.c_char_p, _i]
-    _lib = L
     return L
+
+
+def lib():
+    """libdoa_cuda.so (built in-tree by gr_doa_b200.build) -- or, inside a `dev_library()` block, libdoa_cuda_dev.so.
+    Raises if absent: no fallback exists."""
+    global _lib, _dev_lib
+    if _use_dev:
+        if _dev_lib is None:
+            _dev_lib = _load(DEV_LIB_PATH)
+        return _dev_lib
+    if _lib is None:
+        _lib = _load(LIB_PATH)
+    return _lib
+
+
+class dev_library:
+    """Context manager: blocks CREATED inside it are bound to libdoa_cuda_dev.so, the -DDOA_DEV_KNOBS build that also contains
+    the experimental kernel configurations (a block keeps the library it was created with)."""
+
+    def __enter__(self):
+        global _use_dev
+        self._prev = _use_dev
+        _use_dev = True
+        return lib()
+
+    def __exit__(self, *exc):
+        global _use_dev
+        _use_dev = self._prev
+        return False
 
 
 def check(rc, handle=None):

@@ -14,6 +14,7 @@ current stream.  torch is used for device memory and streams only.  DoaChain is 
 autocorrelate -> MUSIC_lin_array -> find_local_max path (peaks only).
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -25,9 +26,25 @@ def _np(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
-def _stream_ptr():
+def _stream_ptr(dev=None):
+    """torch's current stream ON THE TENSOR'S DEVICE (a handle's stream argument must belong to the handle's device)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+_live = weakref.WeakSet()
+_default_options = {}
+
+
+def set_default_option(key, value):
+    """Measurement scripts (tools/): set a per-handle option (doa_cuda_set_option) on every live block of this process and on
+    every block created from now on.  This convenience is Python-side state; the library itself has none."""
+    _default_options[key] = int(value)
+    for b in list(_live):
+        try:
+            b.set_option(key, value)
+        except _lib.DoaCudaError:
+            pass          # a product-library handle refusing a dev-only variant
 
 
 class _Block:
@@ -39,9 +56,32 @@ class _Block:
         if rc != 0:
             txt = self._L.doa_cuda_last_error(None)
             raise _lib.DoaCudaError(rc, txt.decode() if txt else "")
+        _live.add(self)
+        for k, v in _default_options.items():
+            if self._L.doa_cuda_set_option(self._h, k.encode(), v) != 0:
+                pass      # not applicable to this library build
 
     def launches(self):
         return int(self._L.doa_cuda_last_launch_count(self._h))
+
+    def set_option(self, key, value):
+        """Per-handle option (include/doa_cuda.h: doa_cuda_set_option): path selection for A/B measurements, SM reserve."""
+        rc = self._L.doa_cuda_set_option(self._h, key.encode() if isinstance(key, str) else key, int(value))
+        if rc != 0:
+            txt = self._L.doa_cuda_last_error(self._h)
+            raise _lib.DoaCudaError(rc, txt.decode() if txt else "")
+
+    def _stream_of(self, t):
+        """torch's current stream on the tensor's device, which must be the handle's device (include/doa_cuda.h, threading and
+        streams: a handle's scratch lives on its device; one call at a time per handle)."""
+        dev = getattr(self, "device", None)
+        if dev is not None and t.device.index != dev:
+            raise ValueError(f"tensor on cuda:{t.device.index}, handle created for cuda:{dev}")
+        return _stream_ptr(t.device)
+
+    def set_sms_reserve(self, n):
+        """SMs the persistent chain kernel leaves to a collective's kernel (multi-GPU runs)."""
+        self.set_option("sms_reserve", n)
 
     def set_channel_gains(self, gains):
         """Per-channel complex gains applied in front of the covariance as R' = D R D^H (autocorrelate and chain handles):
@@ -79,6 +119,18 @@ class _Block:
     def _nsamp(self, x):
         return x.size // 2 if self._sc16 else x.size
 
+    def _checked_streams(self, streams, nframes):
+        """M channel streams for nframes frames: each must hold hop * (nframes - 1) + snapshot_size samples (history included),
+        as general_work()'s input buffers do (lib/autocorrelate_impl.cc:74-80,95-100); a short array would be read past its end."""
+        xs = [self._samples(x) for x in streams]
+        if len(xs) != self.inputs:
+            raise ValueError(f"expected {self.inputs} channel streams, got {len(xs)}")
+        need = (nframes - 1) * self.hop + self.snapshot_size if nframes > 0 else 0
+        for x in xs:
+            if self._nsamp(x) < need:
+                raise ValueError("not enough input items for nframes")
+        return xs
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._L.doa_cuda_destroy(self._h)
@@ -114,6 +166,7 @@ class autocorrelate(_Block):
 
     def __init__(self, inputs, snapshot_size, overlap_size, avg_method, device=0, max_frames=4096):
         super().__init__()
+        self.device = device
         self.inputs, self.snapshot_size, self.overlap_size, self.avg_method = inputs, snapshot_size, overlap_size, int(avg_method)
         self.hop = snapshot_size - overlap_size
         self.max_frames = max_frames
@@ -160,7 +213,7 @@ class autocorrelate(_Block):
             frame_stride, chan_stride, nframes = M * N, N, B
         out = torch.empty((nframes, self.inputs * self.inputs), dtype=torch.complex64, device=x.device)
         check(self._L.doa_cuda_autocorrelate_run_device(self._h, x.data_ptr(), frame_stride, chan_stride, nframes,
-                                                        out.data_ptr(), _stream_ptr()), self._h)
+                                                        out.data_ptr(), self._stream_of(x)), self._h)
         return out
 
 
@@ -169,6 +222,7 @@ class MUSIC_lin_array(_Block):
 
     def __init__(self, norm_spacing, num_targets, num_ant_ele, pspectrum_len, device=0, max_frames=4096):
         super().__init__()
+        self.device = device
         self.norm_spacing, self.num_targets, self.num_ant_ele, self.pspectrum_len = norm_spacing, num_targets, num_ant_ele, pspectrum_len
         self.max_frames = max_frames
         self.nout_items_total = 0             # public counter of the reference block (lib/MUSIC_lin_array_impl.h:47)
@@ -189,7 +243,7 @@ class MUSIC_lin_array(_Block):
         u = torch.empty((n, M), dtype=torch.complex64, device=R.device)
         w = torch.empty((n, M), dtype=torch.float32, device=R.device)
         check(self._L.doa_cuda_music_noise_subspace_device(self._h, R.data_ptr(), n, G.data_ptr(), u.data_ptr(), w.data_ptr(),
-                                                           _stream_ptr()), self._h)
+                                                           self._stream_of(R)), self._h)
         return G, u, w
 
     def work(self, R):
@@ -206,7 +260,7 @@ class MUSIC_lin_array(_Block):
         import torch
         n = R.shape[0]
         out = torch.empty((n, self.pspectrum_len), dtype=torch.float32, device=R.device)
-        check(self._L.doa_cuda_music_run_device(self._h, R.data_ptr(), n, out.data_ptr(), _stream_ptr()), self._h)
+        check(self._L.doa_cuda_music_run_device(self._h, R.data_ptr(), n, out.data_ptr(), self._stream_of(R)), self._h)
         self.nout_items_total += n
         return out
 
@@ -216,6 +270,7 @@ class rootMUSIC_linear_array(_Block):
 
     def __init__(self, norm_spacing, num_targets, num_ant_ele, device=0, max_frames=4096):
         super().__init__()
+        self.device = device
         self.norm_spacing, self.num_targets, self.num_ant_ele = norm_spacing, num_targets, num_ant_ele
         self.max_frames = max_frames
         self._created(self._L.doa_cuda_rootmusic_create(C.byref(self._h), C.c_float(norm_spacing), num_targets, num_ant_ele,
@@ -234,7 +289,7 @@ class rootMUSIC_linear_array(_Block):
         import torch
         n = R.shape[0]
         out = torch.empty((n, self.num_targets), dtype=torch.float32, device=R.device)
-        check(self._L.doa_cuda_rootmusic_run_device(self._h, R.data_ptr(), n, out.data_ptr(), _stream_ptr()), self._h)
+        check(self._L.doa_cuda_rootmusic_run_device(self._h, R.data_ptr(), n, out.data_ptr(), self._stream_of(R)), self._h)
         return out
 
 
@@ -243,6 +298,7 @@ class find_local_max(_Block):
 
     def __init__(self, num_max_vals, vector_len, x_min, x_max, device=0, max_frames=4096):
         super().__init__()
+        self.device = device
         self.num_max_vals, self.vector_len, self.x_min, self.x_max = num_max_vals, vector_len, x_min, x_max
         self.max_frames = max_frames
         self._created(self._L.doa_cuda_find_local_max_create(C.byref(self._h), num_max_vals, vector_len, C.c_float(x_min),
@@ -265,7 +321,7 @@ class find_local_max(_Block):
         loc = torch.empty_like(val)
         bins = torch.empty((n, K), dtype=torch.int32, device=vecs.device)
         check(self._L.doa_cuda_find_local_max_run_device(self._h, vecs.data_ptr(), n, val.data_ptr(), loc.data_ptr(),
-                                                         bins.data_ptr(), _stream_ptr()), self._h)
+                                                         bins.data_ptr(), self._stream_of(vecs)), self._h)
         return val, loc, bins
 
 
@@ -276,6 +332,7 @@ class calibrate_lin_array(_Block):
 
     def __init__(self, norm_spacing, num_ant_ele, pilot_angle, device=0, max_frames=4096):
         super().__init__()
+        self.device = device
         self.num_ant_ele, self.inputs = num_ant_ele, num_ant_ele
         self._created(self._L.doa_cuda_calibrate_create(C.byref(self._h), C.c_float(norm_spacing), num_ant_ele, C.c_float(pilot_angle),
                                                         device, max_frames))
@@ -291,7 +348,7 @@ class calibrate_lin_array(_Block):
         import torch
         n, M = R.shape[0], self.num_ant_ele
         out = torch.empty((n, M), dtype=torch.complex64, device=R.device)
-        check(self._L.doa_cuda_calibrate_run_device(self._h, R.data_ptr(), n, out.data_ptr(), _stream_ptr()), self._h)
+        check(self._L.doa_cuda_calibrate_run_device(self._h, R.data_ptr(), n, out.data_ptr(), self._stream_of(R)), self._h)
         return out
 
 
@@ -301,6 +358,7 @@ class DoaChain(_Block):
     def __init__(self, inputs, snapshot_size, overlap_size, avg_method, norm_spacing, num_targets, pspectrum_len,
                  num_max_vals, x_min=0.0, x_max=180.0, device=0, max_frames=4096):
         super().__init__()
+        self.device = device
         self.inputs, self.snapshot_size, self.overlap_size = inputs, snapshot_size, overlap_size
         self.hop = snapshot_size - overlap_size
         self.K, self.max_frames = num_max_vals, max_frames
@@ -331,7 +389,7 @@ class DoaChain(_Block):
             out = (val, torch.empty_like(val), torch.empty((nframes, self.K), dtype=torch.int32, device=x.device))
         val, loc, bins = out
         check(self._L.doa_cuda_chain_run_device(self._h, x.data_ptr(), frame_stride, chan_stride, nframes, val.data_ptr(),
-                                                loc.data_ptr(), bins.data_ptr(), _stream_ptr()), self._h)
+                                                loc.data_ptr(), bins.data_ptr(), self._stream_of(x)), self._h)
         return val, loc, bins
 
     def run_host(self, frames, out=None):
@@ -350,7 +408,7 @@ class DoaChain(_Block):
         return val, loc, bins
 
     def run_streams(self, streams, nframes):
-        xs = [self._samples(x) for x in streams]
+        xs = self._checked_streams(streams, nframes)
         val, loc, bins = (np.empty((nframes, self.K), np.float32), np.empty((nframes, self.K), np.float32),
                           np.empty((nframes, self.K), np.int32))
         ptrs = (C.c_void_p * self.inputs)(*[x.ctypes.data for x in xs])
@@ -371,6 +429,7 @@ class DoaChainMulti(_Block):
             devices = list(range(int(self._L.doa_cuda_device_count())))
         self.devices = [int(d) for d in devices]
         self.inputs, self.snapshot_size, self.overlap_size = inputs, snapshot_size, overlap_size
+        self.hop = snapshot_size - overlap_size
         self.K, self.max_frames = num_max_vals, max_frames_per_device * max(1, len(self.devices))
         dv = (C.c_int * max(1, len(self.devices)))(*self.devices)
         self._created(self._L.doa_cuda_multi_create(C.byref(self._h), inputs, snapshot_size, overlap_size, int(avg_method),
@@ -403,7 +462,7 @@ class DoaChainMulti(_Block):
 
     def run_streams(self, streams, nframes):
         """streams: M channel arrays holding hop*(nframes-1)+snapshot_size samples each (a general_work() view)."""
-        xs = [self._samples(x) for x in streams]
+        xs = self._checked_streams(streams, nframes)
         val, loc, bins = (np.empty((nframes, self.K), np.float32), np.empty((nframes, self.K), np.float32),
                           np.empty((nframes, self.K), np.int32))
         ptrs = (C.c_void_p * self.inputs)(*[x.ctypes.data for x in xs])
@@ -418,6 +477,7 @@ class RootMusicChain(_Block):
 
     def __init__(self, inputs, snapshot_size, overlap_size, avg_method, norm_spacing, num_targets, device=0, max_frames=4096):
         super().__init__()
+        self.device = device
         self.inputs, self.snapshot_size, self.overlap_size = inputs, snapshot_size, overlap_size
         self.hop, self.T, self.max_frames = snapshot_size - overlap_size, num_targets, max_frames
         self._created(self._L.doa_cuda_rootchain_create(C.byref(self._h), inputs, snapshot_size, overlap_size, int(avg_method),
@@ -430,7 +490,7 @@ class RootMusicChain(_Block):
             frame_stride, chan_stride, nframes = M * N, N, B
         out = torch.empty((nframes, self.T), dtype=torch.float32, device=x.device)
         check(self._L.doa_cuda_rootchain_run_device(self._h, x.data_ptr(), frame_stride, chan_stride, nframes, out.data_ptr(),
-                                                    _stream_ptr()), self._h)
+                                                    self._stream_of(x)), self._h)
         return out
 
     def run_host(self, frames):
@@ -440,7 +500,7 @@ class RootMusicChain(_Block):
         return out
 
     def run_streams(self, streams, nframes):
-        xs = [self._samples(x) for x in streams]
+        xs = self._checked_streams(streams, nframes)
         out = np.empty((nframes, self.T), np.float32)
         ptrs = (C.c_void_p * self.inputs)(*[x.ctypes.data for x in xs])
         check(self._L.doa_cuda_rootchain_run_streams(self._h, ptrs, nframes, out.ctypes.data), self._h)

@@ -53,9 +53,6 @@ cov_small_kernel(const S* __restrict__ in, long long frame_stride, long long cha
 // frame's shared 256-float area in the layout folded_entry<16> reads; the pair then emits half of R each.
 constexpr int C16_FRAMES = 4;   // frames in flight per CTA (8 warps)
 
-__device__ const unsigned char kTri8Row[28] = {1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7};
-__device__ const unsigned char kTri8Col[28] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 6};
-
 template <int VEC, typename S>
 __device__ __forceinline__ void cov16_load(const S* __restrict__ base, long long chan_stride, int t, bool ok,
                                            float2 (&x)[VEC][16]) {
@@ -160,163 +157,6 @@ cov16_kernel(const S* __restrict__ in, long long frame_stride, long long chan_st
   }
 }
 
-// Ring-fed variant (16-byte aligned, even N): the two warps of a pair share ONE cp.async ring -- each loads 8 of the 16
-// channels, both read all 16 after the pair's barrier -- so a frame crosses L2 -> SM once instead of twice and the loads of
-// chunk q + STAGES - 2 are in flight while chunk q is accumulated (the LDG version stalls a 255-register warp on every load).
-constexpr int C16_STAGES = 5;
-
-// One role's whole loop (the two roles are separate instantiations so that each only carries its own 128 accumulators).
-// S = float2: fc32 samples, float4 ring slots; S = unsigned: sc16 samples, uint2 ring slots (the same two samples per lane).
-template <typename S> struct Ring16Slot { typedef float4 type; };
-template <> struct Ring16Slot<unsigned> { typedef uint2 type; };
-
-template <int ROLE, typename S>
-__device__ __forceinline__ void cov16_ring_role(const S* __restrict__ in, long long frame_stride, long long chan_stride, int N,
-                                                int nframes, float2* __restrict__ out, float scale, float bscale, int avg_method,
-                                                const float2* __restrict__ gains, typename Ring16Slot<S>::type* ring, float* red,
-                                                int slot, int lane) {
-  typedef typename Ring16Slot<S>::type Slot;
-  constexpr bool SC16 = sizeof(S) == 4;
-  constexpr int M = 16, CNT = 256, NP16 = 120;
-  const int bar_id = 1 + slot;
-  const int nslots = gridDim.x * C16_FRAMES;
-  const int first = blockIdx.x * C16_FRAMES + slot;
-  const int nfw = (first < nframes) ? (nframes - first + nslots - 1) / nslots : 0;    // frames of this pair
-  const int NCH = (N + 63) / 64;                      // 64-sample chunks per frame (2 samples per lane)
-  const int total = nfw * NCH;
-  // issue cursor: this warp loads channels 8 ROLE .. 8 ROLE + 7 of every chunk
-  const S* ibase = in + (long long)first * frame_stride + (long long)(8 * ROLE) * chan_stride;
-  int ic = 0, istage = 0, issued = 0;
-  auto issue = [&]() {
-    const int t = ic * 64 + lane * 2;
-    const int nbytes = (t < N) ? (int)sizeof(Slot) : 0;
-    Slot* dst = ring + ((size_t)istage * 16 + 8 * ROLE) * 32 + lane;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if constexpr (SC16) cp_async8(dst + k * 32, ibase + (long long)k * chan_stride + (nbytes ? t : 0), nbytes);
-      else cp_async16(dst + k * 32, ibase + (long long)k * chan_stride + (nbytes ? t : 0), nbytes);
-    }
-    if (++ic == NCH) { ic = 0; ibase += (long long)nslots * frame_stride; }
-    if (++istage == C16_STAGES) istage = 0;
-    ++issued;
-  };
-#pragma unroll
-  for (int q = 0; q < C16_STAGES - 2; ++q) { if (issued < total) issue(); cp_async_commit(); }
-
-  f32x2 od[64];                                       // ROLE 0: two CovAcc<8>-style diagonal blocks; ROLE 1: R[8 + i][j] at od[i * 8 + j]
-  float dg[ROLE == 0 ? 16 : 1];
-  auto clear = [&]() {
-#pragma unroll
-    for (int i = 0; i < 64; ++i) od[i] = 0ull;
-    if constexpr (ROLE == 0) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) dg[i] = 0.0f;
-    }
-  };
-  clear();
-  int c = 0, rstage = 0, f = first;
-  for (int q = 0; q < total; ++q) {
-    // the stage refilled here was read two iterations ago at the latest, before the barrier both warps passed last time
-    if (issued < total) issue();
-    cp_async_commit();
-    cp_async_wait<C16_STAGES - 2>();
-    asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");      // both halves of this chunk have landed
-    const Slot* src = ring + (size_t)rstage * 16 * 32 + lane;
-    if (++rstage == C16_STAGES) rstage = 0;
-    float2 x[2][16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const Slot v = src[k * 32];
-      if constexpr (SC16) { x[0][k] = sc16_to_c64(v.x); x[1][k] = sc16_to_c64(v.y); }
-      else { x[0][k] = make_float2(v.x, v.y); x[1][k] = make_float2(v.z, v.w); }
-    }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if constexpr (ROLE == 0) {
-        // diagonal blocks b = 0, 1: entry (r > c) of block b at od[32 b + r (r - 1) / 2 + c]  (28 of 32 used), diagonals in dg
-#pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const float2 xr = x[s][8 * b + r];
-            dg[8 * b + r] = fmaf(xr.x, xr.x, dg[8 * b + r]);
-            dg[8 * b + r] = fmaf(xr.y, xr.y, dg[8 * b + r]);
-            const f32x2 xp = pk2(xr.x, xr.y), xs = pk2(xr.y, -xr.x);
-#pragma unroll
-            for (int cc = 0; cc < r; ++cc) {
-              const float2 xc = x[s][8 * b + cc];
-              const int p = 32 * b + r * (r - 1) / 2 + cc;
-              od[p] = fma2(xp, pk2(xc.x, xc.x), od[p]);   // x_r conj(x_c), see CovAcc
-              od[p] = fma2(xs, pk2(xc.y, xc.y), od[p]);
-            }
-          }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 xr = x[s][8 + i];
-          const f32x2 xp = pk2(xr.x, xr.y), xs = pk2(xr.y, -xr.x);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 xc = x[s][j];
-            od[i * 8 + j] = fma2(xp, pk2(xc.x, xc.x), od[i * 8 + j]);
-            od[i * 8 + j] = fma2(xs, pk2(xc.y, xc.y), od[i * 8 + j]);
-          }
-        }
-      }
-    }
-    if (++c == NCH) {
-      c = 0;
-      float a[128];
-      if constexpr (ROLE == 0) {
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-#pragma unroll
-          for (int p = 0; p < 28; ++p) upk2(od[32 * b + p], a[64 * b + 2 * p], a[64 * b + 2 * p + 1]);
-#pragma unroll
-          for (int r = 0; r < 8; ++r) a[64 * b + 56 + r] = dg[8 * b + r];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) upk2(od[i], a[2 * i], a[2 * i + 1]);
-      }
-      clear();
-      warp_reduce_scatter<128, 16>(a, (unsigned)lane);   // lane L now holds the full sums of elements 4L .. 4L+3
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = lane * 4 + i;
-        int pos;
-        if constexpr (ROLE == 0) {
-          const int blk = k >> 6, kk = k & 63;
-          if (kk < 56) {
-            const int r = 8 * blk + kTri8Row[kk >> 1], cc = 8 * blk + kTri8Col[kk >> 1];
-            pos = 2 * (r * (r - 1) / 2 + cc) + (kk & 1);
-          } else {
-            pos = 2 * NP16 + 8 * blk + (kk - 56);
-          }
-        } else {
-          const int r = 8 + (k >> 4), cc = (k >> 1) & 7;
-          pos = 2 * (r * (r - 1) / 2 + cc) + (k & 1);
-        }
-        red[pos] = a[i];
-      }
-      asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");   // both roles' sums are in red
-      float2* o = out + (long long)f * CNT;
-      for (int e = ROLE * 32 + lane; e < CNT; e += 64) {
-        const int r = e % M, cc = e / M;
-        float2 v = apply_gain(folded_entry<M>(red, r, cc, scale), gains, r, cc);
-        if (avg_method == 1) {   // 0.5*R + (0.5/N) * J conj(R) J, lib/autocorrelate_impl.cc:108
-          const float2 wv = apply_gain(folded_entry<M>(red, M - 1 - r, M - 1 - cc, scale), gains, M - 1 - r, M - 1 - cc);
-          v.x = __fadd_rn(__fmul_rn(0.5f, v.x), __fmul_rn(bscale, wv.x));
-          v.y = __fadd_rn(__fmul_rn(0.5f, v.y), __fmul_rn(bscale, -wv.y));
-        }
-        o[e] = v;
-      }
-      f += nslots;
-      // red is rewritten only after the next frame's chunk barriers, which both warps pass after finishing this loop
-    }
-  }
-}
-
 template <typename S>
 __global__ void __launch_bounds__(C16_FRAMES * 64, 1)
 cov16_ring_kernel(const S* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
@@ -327,8 +167,18 @@ cov16_ring_kernel(const S* __restrict__ in, long long frame_stride, long long ch
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5, slot = warp >> 1;
   Slot* ring = reinterpret_cast<Slot*>(ring_s) + (size_t)slot * C16_STAGES * 16 * 32;
-  if ((warp & 1) == 0) cov16_ring_role<0, S>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, gains, ring, red_s[slot], slot, lane);
-  else cov16_ring_role<1, S>(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, gains, ring, red_s[slot], slot, lane);
+  const int nslots = gridDim.x * C16_FRAMES;
+  const int first = blockIdx.x * C16_FRAMES + slot;
+  const int nfw = (first < nframes) ? (nframes - first + nslots - 1) / nslots : 0;    // frames of this pair
+  if ((warp & 1) == 0) {
+    cov16_ring_role<0, S>(in, frame_stride, chan_stride, N, first, nslots, nfw, ring, red_s[slot], 1 + slot, lane, [&](int k, const float* red) {
+      cov16_pair_emit<0>(red, scale, bscale, avg_method, lane, out + ((long long)first + (long long)k * nslots) * 256, gains);
+    });
+  } else {
+    cov16_ring_role<1, S>(in, frame_stride, chan_stride, N, first, nslots, nfw, ring, red_s[slot], 1 + slot, lane, [&](int k, const float* red) {
+      cov16_pair_emit<1>(red, scale, bscale, avg_method, lane, out + ((long long)first + (long long)k * nslots) * 256, gains);
+    });
+  }
 }
 
 template <typename S>
@@ -337,7 +187,7 @@ int launch_cov16(const S* in, long long fs, long long cs, int N, int nframes, fl
   // two samples per ring slot / load: 16 bytes of fc32, 8 bytes of sc16
   const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & (2 * sizeof(S) - 1)) == 0);
   const int blocks = (nframes + C16_FRAMES - 1) / C16_FRAMES;
-  if (vec2 && dev_option("cov16_ring", 1)) {
+  if (vec2 && dev_option(OPT_COV16_RING, 1)) {
     const size_t smem = (size_t)C16_FRAMES * C16_STAGES * 16 * 32 * sizeof(typename Ring16Slot<S>::type);
     cudaFuncSetAttribute(cov16_ring_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = std::min(blocks, num_sms());
@@ -464,7 +314,7 @@ int launch_small(const S* in, long long fs, long long cs, int N, int nframes, fl
   // two samples per load (LDG.128 for fc32, LDG.64 for sc16) when the layout is aligned for it
   const bool vec2 = (N % 2 == 0) && (fs % 2 == 0) && (cs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & (2 * sizeof(S) - 1)) == 0);
   const int blocks = (nframes + COV_WARPS - 1) / COV_WARPS;
-  const int variant = dev_option("cov_groups", 1);   // 1: 128 regs, 2 CTAs/SM (6.4 TB/s at M=8); 2: 167 regs, 1 CTA/SM (5.9 TB/s)
+  const int variant = dev_option(OPT_COV_GROUPS, 1);   // 1: 128 regs, 2 CTAs/SM (6.4 TB/s at M=8); 2: 167 regs, 1 CTA/SM (5.9 TB/s)
   if (vec2) {
     if (variant == 1) cov_small_kernel<M, 2, 1, S><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
     else cov_small_kernel<M, 2, 2, S><<<blocks, COV_WARPS * 32, 0, st>>>(in, fs, cs, N, nframes, out, scale, bscale, avg, gains);
@@ -516,7 +366,7 @@ int launch_covariance(const void* in_v, long long frame_stride, long long chan_s
     case 16: return launch_cov16(in, frame_stride, chan_stride, N, nframes, out, scale, bscale, avg_method, st, gains);
     default: break;
   }
-  if (M == 64 && dev_option("herk_tc", 1)) {   // tensor-core complex HERK (3xTF32) when alignment allows
+  if (M == 64 && dev_option(OPT_HERK_TC, 1)) {   // tensor-core complex HERK (3xTF32) when alignment allows
     const int r = launch_covariance_tc(in, frame_stride, chan_stride, M, N, nframes, avg_method, out, st, gains);
     if (r != 0) return r;
   }

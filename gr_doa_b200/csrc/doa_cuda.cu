@@ -1,8 +1,10 @@
 // doa_cuda.cu -- the C ABI of libdoa_cuda (include/doa_cuda.h): handles, constructor tables, staging, stage plumbing.
 //
 // One handle = one GNU Radio block instance: it owns its CUDA stream(s), device buffers sized for max_frames and the
-// constructor tables.  cudaSetDevice() is called on entry to every function (GNU Radio may call work() from a thread
-// other than the constructor's).  There is no global mutable state besides the error text of a failed *_create.
+// constructor tables.  Every entry point makes the handle's device current for the duration of the call and restores the
+// caller's (GNU Radio may call work() from a thread other than the constructor's; torch or another library may own the thread's
+// current device).  There is no global mutable state: options live in the handle, the error text of a failed *_create is
+// thread-local.
 #include "doa_internal.h"
 
 #include <cmath>
@@ -12,20 +14,19 @@
 #include <cstring>
 #include <condition_variable>
 #include <functional>
-#include <map>
+#include <climits>
 #include <memory>
 #include <mutex>
 #include <thread>
 
 namespace doa {
 
-// ---- development knobs ---------------------------------------------------------------------------------------------
-static std::mutex g_opt_mu;
-static std::map<std::string, int> g_opts;
-int dev_option(const char* key, int dflt) {
-  std::lock_guard<std::mutex> lk(g_opt_mu);
-  auto it = g_opts.find(key);
-  return it == g_opts.end() ? dflt : it->second;
+// ---- per-handle options ---------------------------------------------------------------------------------------------
+// The calling thread's current option set: installed by Enter (below) for the duration of an ABI call.
+static thread_local const Tuning* tl_tune = nullptr;
+int dev_option(Opt key, int dflt) {
+  const Tuning* t = tl_tune;
+  return (t != nullptr && t->v[key] != OPT_UNSET) ? t->v[key] : dflt;
 }
 
 // ---- constructor tables (host) -----------------------------------------------------------------------------------
@@ -80,6 +81,7 @@ struct Lane {   // one stream's worth of buffers (the chain's host path double-b
   float* vecs = nullptr;
   double2* scratch = nullptr;
   int frames = 0;
+  char* pin = nullptr; size_t pin_bytes = 0;   // page-locked host staging for small host-pointer calls (allocated on first use)
 };
 
 // Host threads of a multi-device handle: device 0 is driven by the calling thread, every further device by one persistent
@@ -137,6 +139,7 @@ struct MultiPool {
 };
 
 struct doa_cuda_handle {
+  Tuning tune;
   int kind = 0, device = 0, max_frames = 0;
   int M = 0, N = 0, overlap = 0, hop = 0, avg = 0, T = 0, P = 0, K = 0;
   float d = 0.f, x_min = 0.f, x_max = 0.f;
@@ -159,6 +162,30 @@ static const int PROF_SETS = 256;
 
 static thread_local std::string g_create_err;
 
+// Scope of one ABI call on a handle: the handle's device becomes current (GNU Radio may call work() from a thread other than the
+// constructor's) and is put back on return, so a call never changes the calling thread's device under torch or another
+// library; the handle's options become the thread's current ones.
+struct Enter {
+  int prev_dev = -1; const Tuning* prev_tune; bool ok;
+  explicit Enter(doa_cuda_handle* h) : prev_tune(tl_tune) {
+    if (cudaGetDevice(&prev_dev) != cudaSuccess) prev_dev = -1;
+    ok = cudaSetDevice(h->device) == cudaSuccess;
+    tl_tune = &h->tune;
+  }
+  ~Enter() {
+    tl_tune = prev_tune;
+    if (prev_dev >= 0 && ok) cudaSetDevice(prev_dev);
+  }
+};
+struct DevSave {   // create / destroy: leave the calling thread's current device as it was
+  int prev = -1;
+  DevSave() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+  ~DevSave() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ENTER(h)                                                                  \
+  Enter enter_guard_(h);                                                          \
+  if (!enter_guard_.ok) return fail(h, DOA_CUDA_ECUDA, "cudaSetDevice failed")
+
 #define CK(h, call)                                                                                    \
   do {                                                                                                 \
     cudaError_t e_ = (call);                                                                           \
@@ -173,6 +200,7 @@ static int fail(doa_cuda_handle* h, int code, const std::string& msg) { if (h) h
 static void free_lane(Lane& l) {
   cudaFree(l.in); cudaFree(l.R); cudaFree(l.G); cudaFree(l.u); cudaFree(l.spec); cudaFree(l.val); cudaFree(l.loc);
   cudaFree(l.bin); cudaFree(l.aoa); cudaFree(l.vecs); cudaFree(l.scratch);
+  if (l.pin) cudaFreeHost(l.pin);
   if (l.stream) cudaStreamDestroy(l.stream);
   l = Lane();
 }
@@ -182,6 +210,7 @@ extern "C" void doa_cuda_destroy(doa_cuda_handle* h) {
   h->pool.reset();                          // workers are idle between runs; join them before their devices' handles go
   for (doa_cuda_handle* c : h->children) doa_cuda_destroy(c);
   h->children.clear();
+  DevSave dev_save_;
   cudaSetDevice(h->device);
   for (int i = 0; i < 2; ++i) free_lane(h->lane[i]);
   cudaFree(h->d_z); cudaFree(h->d_V); cudaFree(h->d_x); cudaFree(h->d_zpair); cudaFree(h->d_tctab); cudaFree(h->d_gains);
@@ -254,10 +283,31 @@ int doa_cuda_abi_version(void) { return 1; }
 const char* doa_cuda_last_error(const doa_cuda_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 int doa_cuda_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 int doa_cuda_last_launch_count(const doa_cuda_handle* h) { return h ? h->launches : 0; }
-int doa_cuda_dev_set(const char* key, int value) {
-  std::lock_guard<std::mutex> lk(g_opt_mu);
-  g_opts[key] = value;
+int doa_cuda_set_option(doa_cuda_handle* h, const char* key, int value) {
+  static const struct { const char* name; Opt opt; } kNames[] = {
+      {"fused", OPT_FUSED}, {"scan_tc", OPT_SCAN_TC}, {"sms_reserve", OPT_SMS_RESERVE}, {"cov_groups", OPT_COV_GROUPS},
+      {"cov16_ring", OPT_COV16_RING}, {"herk_tc", OPT_HERK_TC}, {"scan_wide", OPT_SCAN_WIDE}, {"spectrum_smem", OPT_SPECTRUM_SMEM},
+      {"root_aberth", OPT_ROOT_ABERTH}, {"jacobi_sweeps", OPT_JACOBI_SWEEPS}, {"ws_split", OPT_WS_SPLIT}, {"ws_stages", OPT_WS_STAGES},
+      {"ws_nbuf", OPT_WS_NBUF}, {"ws4", OPT_WS4}, {"ws_tma", OPT_WS_TMA}, {"ws_fill", OPT_WS_FILL}, {"scan_tc_dbg", OPT_SCAN_TC_DBG}, {"fused16", OPT_FUSED16}};
+  if (!h || !key) return DOA_CUDA_EINVAL;
+  for (const auto& n : kNames) {
+    if (std::strcmp(n.name, key) != 0) continue;
+#ifndef DOA_DEV_KNOBS
+    if ((int)n.opt >= OPT_FIRST_DEV_ONLY) return fail(h, DOA_CUDA_EINVAL, std::string("option '") + key + "' selects a kernel variant that only a -DDOA_DEV_KNOBS build contains");
+#endif
+    if (n.opt == OPT_SMS_RESERVE && (value < 0 || value > 64)) return fail(h, DOA_CUDA_EINVAL, "sms_reserve must be in [0, 64]");
+    h->tune.v[n.opt] = value;
+    for (doa_cuda_handle* c : h->children) c->tune.v[n.opt] = value;
+    return DOA_CUDA_OK;
+  }
+  return fail(h, DOA_CUDA_EINVAL, std::string("unknown option '") + key + "'");
+}
+int doa_cuda_has_dev_knobs(void) {
+#ifdef DOA_DEV_KNOBS
+  return 1;
+#else
   return 0;
+#endif
 }
 
 // ---- page-locking a caller's host buffer -----------------------------------------------------------------------------
@@ -285,7 +335,7 @@ int doa_cuda_set_channel_gains(doa_cuda_handle* h, const float* gains) {
     return DOA_CUDA_OK;
   }
   if (!h || !takes_samples(h->kind)) return DOA_CUDA_EINVAL;
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   // runs already queued on the handle's streams may still read the old gains
   for (int i = 0; i < h->nlanes; ++i) if (h->lane[i].stream) CK(h, cudaStreamSynchronize(h->lane[i].stream));
   if (gains == nullptr) { CK(h, cudaDeviceSynchronize()); cudaFree(h->d_gains); h->d_gains = nullptr; return DOA_CUDA_OK; }
@@ -310,7 +360,7 @@ int doa_cuda_set_input_format(doa_cuda_handle* h, int format, float scale) {
   if (format != DOA_CUDA_FMT_FC32 && format != DOA_CUDA_FMT_SC16) return fail(h, DOA_CUDA_EINVAL, "unknown input format");
   if (format == DOA_CUDA_FMT_SC16 && !(std::isfinite(scale) && scale > 0.0f))
     return fail(h, DOA_CUDA_EINVAL, "sc16 scale must be finite and > 0");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   for (int i = 0; i < h->nlanes; ++i) if (h->lane[i].stream) CK(h, cudaStreamSynchronize(h->lane[i].stream));
   h->fmt.sc16 = format == DOA_CUDA_FMT_SC16;
   h->fmt.scale = h->fmt.sc16 ? scale : 1.0f;
@@ -342,6 +392,7 @@ int doa_cuda_autocorrelate_create(doa_cuda_handle** out, int inputs, int snapsho
   if (overlap_size < 0 || overlap_size >= snapshot_size) return fail(nullptr, DOA_CUDA_EINVAL, "need 0 <= overlap_size < snapshot_size");
   if (avg_method != 0 && avg_method != 1) return fail(nullptr, DOA_CUDA_EINVAL, "avg_method must be 0 (forward) or 1 (forward-backward)");
   doa_cuda_handle* h = nullptr;
+  DevSave dev_save_;
   int rc = begin_create(out, h, K_AUTOCORR, device, max_frames);
   if (rc) return rc;
   h->M = inputs; h->N = snapshot_size; h->overlap = overlap_size; h->hop = snapshot_size - overlap_size; h->avg = avg_method;
@@ -362,7 +413,7 @@ int doa_cuda_autocorrelate_run_device(doa_cuda_handle* h, const void* in_dev, lo
                                       int nframes, void* out_dev, void* cuda_stream) {
   if (!h || (h->kind != K_AUTOCORR && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
   if (nframes < 0) return fail(h, DOA_CUDA_EINVAL, "nframes < 0");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   int n = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, (float2*)out_dev,
                             (cudaStream_t)cuda_stream, h->d_gains, h->fmt);
   if (n < 0) return fail(h, n, "covariance launch rejected");
@@ -371,15 +422,67 @@ int doa_cuda_autocorrelate_run_device(doa_cuda_handle* h, const void* in_dev, lo
   return DOA_CUDA_OK;
 }
 
+// ---- page-locked staging of small host-pointer calls --------------------------------------------------------------------
+// A GNU Radio scheduler hands work() pageable buffers and a handful of frames.  Copied straight out of pageable memory every
+// channel stream (and every output array) is its own driver-staged, blocking transfer; here the call's samples are first
+// gathered into the handle's page-locked buffer in the device layout, so that ONE asynchronous copy moves them, and the
+// outputs come back through the same buffer.  Large transfers (batch jobs; anything over PIN_STAGE_BYTES) keep the direct
+// route: a single host thread cannot memcpy faster than the driver's own pageable path.  Caller memory that already is
+// page-locked (cudaHostAlloc, doa_cuda_pin_host_buffer) is never staged.
+static const size_t PIN_STAGE_BYTES = 8u << 20;
+
+static bool is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+static char* pin_staging(Lane& l, size_t bytes) {
+  if (bytes > PIN_STAGE_BYTES) return nullptr;
+  if (l.pin == nullptr) {
+    if (cudaHostAlloc((void**)&l.pin, PIN_STAGE_BYTES, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); l.pin = nullptr; return nullptr; }
+    l.pin_bytes = PIN_STAGE_BYTES;
+  }
+  return l.pin;
+}
+
 // Copy `inputs` host channel streams into lane.in as [M][Lpad]; returns Lpad.
 static int stage_streams(doa_cuda_handle* h, Lane& l, const void* const* in_host, int nframes, size_t* Lpad_out) {
   const size_t L = (size_t)(nframes - 1) * h->hop + h->N;
   const size_t Lpad = (L + 1) & ~(size_t)1;
-  if (Lpad * h->M > l.in_elems) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
+  if (Lpad * h->M > l.in_elems) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds the staging capacity of this handle (max_frames)");
   const size_t sb = h->sample_bytes();
-  for (int k = 0; k < h->M; ++k)
-    CK(h, cudaMemcpyAsync((char*)l.in + (size_t)k * Lpad * sb, in_host[k], L * sb, cudaMemcpyHostToDevice, l.stream));
+  char* pin = is_pageable(in_host[0]) ? pin_staging(l, Lpad * h->M * sb) : nullptr;
+  if (pin != nullptr) {
+    CK(h, cudaStreamSynchronize(l.stream));                 // the previous call's copies out of the staging buffer are done
+    for (int k = 0; k < h->M; ++k) std::memcpy(pin + (size_t)k * Lpad * sb, in_host[k], L * sb);
+    CK(h, cudaMemcpyAsync(l.in, pin, Lpad * h->M * sb, cudaMemcpyHostToDevice, l.stream));
+  } else {
+    for (int k = 0; k < h->M; ++k)
+      CK(h, cudaMemcpyAsync((char*)l.in + (size_t)k * Lpad * sb, in_host[k], L * sb, cudaMemcpyHostToDevice, l.stream));
+  }
   *Lpad_out = Lpad;
+  return DOA_CUDA_OK;
+}
+
+// Peaks of one call back to the caller's arrays: through the staging buffer (one synchronisation, then plain copies) when the
+// destination is pageable and small, directly otherwise.  Synchronises the lane's stream.
+static int peaks_to_host(doa_cuda_handle* h, Lane& l, int nframes, void* out_val_host, void* out_loc_host, void* out_bin_host) {
+  const size_t nk = (size_t)nframes * h->K, bytes = sizeof(float) * nk;
+  char* pin = is_pageable(out_val_host) ? pin_staging(l, 3 * bytes) : nullptr;
+  if (pin != nullptr) {
+    CK(h, cudaMemcpyAsync(pin, l.val, bytes, cudaMemcpyDeviceToHost, l.stream));
+    CK(h, cudaMemcpyAsync(pin + bytes, l.loc, bytes, cudaMemcpyDeviceToHost, l.stream));
+    if (out_bin_host) CK(h, cudaMemcpyAsync(pin + 2 * bytes, l.bin, bytes, cudaMemcpyDeviceToHost, l.stream));
+    CK(h, cudaStreamSynchronize(l.stream));
+    std::memcpy(out_val_host, pin, bytes);
+    std::memcpy(out_loc_host, pin + bytes, bytes);
+    if (out_bin_host) std::memcpy(out_bin_host, pin + 2 * bytes, bytes);
+    return DOA_CUDA_OK;
+  }
+  CK(h, cudaMemcpyAsync(out_val_host, l.val, bytes, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaMemcpyAsync(out_loc_host, l.loc, bytes, cudaMemcpyDeviceToHost, l.stream));
+  if (out_bin_host) CK(h, cudaMemcpyAsync(out_bin_host, l.bin, bytes, cudaMemcpyDeviceToHost, l.stream));
+  CK(h, cudaStreamSynchronize(l.stream));
   return DOA_CUDA_OK;
 }
 
@@ -387,7 +490,7 @@ int doa_cuda_autocorrelate_run(doa_cuda_handle* h, const void* const* in_host, i
   if (!h || h->kind != K_AUTOCORR) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   Lane& l = h->lane[0];
   size_t Lpad = 0;
   int rc = stage_streams(h, l, in_host, nframes, &Lpad);
@@ -413,6 +516,7 @@ int doa_cuda_music_create(doa_cuda_handle** out, float norm_spacing, int num_tar
   if (rc) return rc;
   if (pspectrum_len < 2) return fail(nullptr, DOA_CUDA_EINVAL, "pspectrum_len must be >= 2");
   doa_cuda_handle* h = nullptr;
+  DevSave dev_save_;
   rc = begin_create(out, h, K_MUSIC, device, max_frames);
   if (rc) return rc;
   h->d = norm_spacing; h->T = num_targets; h->M = num_ant_ele; h->P = pspectrum_len;
@@ -436,7 +540,7 @@ int doa_cuda_music_noise_subspace_device(doa_cuda_handle* h, const void* in_dev,
                                          void* w_dev, void* cuda_stream) {
   if (!h || (h->kind != K_MUSIC && h->kind != K_ROOTMUSIC && h->kind != K_CHAIN)) return DOA_CUDA_EINVAL;
   if (nframes <= 0) return nframes == 0 ? DOA_CUDA_OK : fail(h, DOA_CUDA_EINVAL, "nframes < 0");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   int a = launch_noise_subspace((const float2*)in_dev, h->M, h->T, nframes, (float2*)G_dev, (float2*)u_dev, (float*)w_dev,
                                 (cudaStream_t)cuda_stream);
   if (a < 0) return fail(h, a, "eigendecomposition launch rejected");
@@ -449,7 +553,7 @@ int doa_cuda_music_run_device(doa_cuda_handle* h, const void* in_dev, int nframe
   if (!h || h->kind != K_MUSIC) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   Lane& l = h->lane[0];
   int a = launch_noise_subspace((const float2*)in_dev, h->M, h->T, nframes, nullptr, l.u, nullptr, st);
@@ -465,7 +569,7 @@ int doa_cuda_music_run(doa_cuda_handle* h, const void* in_host, int nframes, voi
   if (!h || h->kind != K_MUSIC) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   Lane& l = h->lane[0];
   const size_t mm = (size_t)h->M * h->M;
   CK(h, cudaMemcpyAsync(l.R, in_host, sizeof(float2) * nframes * mm, cudaMemcpyHostToDevice, l.stream));
@@ -482,6 +586,7 @@ int doa_cuda_rootmusic_create(doa_cuda_handle** out, float norm_spacing, int num
   int rc = check_array(norm_spacing, num_targets, num_ant_ele);
   if (rc) return rc;
   doa_cuda_handle* h = nullptr;
+  DevSave dev_save_;
   rc = begin_create(out, h, K_ROOTMUSIC, device, max_frames);
   if (rc) return rc;
   h->d = norm_spacing; h->T = num_targets; h->M = num_ant_ele;
@@ -497,7 +602,7 @@ int doa_cuda_rootmusic_run_device(doa_cuda_handle* h, const void* in_dev, int nf
   if (!h || h->kind != K_ROOTMUSIC) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   Lane& l = h->lane[0];
   int a = launch_noise_subspace((const float2*)in_dev, h->M, h->T, nframes, nullptr, l.u, nullptr, st);
@@ -513,7 +618,7 @@ int doa_cuda_rootmusic_run(doa_cuda_handle* h, const void* in_host, int nframes,
   if (!h || h->kind != K_ROOTMUSIC) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   Lane& l = h->lane[0];
   const size_t mm = (size_t)h->M * h->M;
   CK(h, cudaMemcpyAsync(l.R, in_host, sizeof(float2) * nframes * mm, cudaMemcpyHostToDevice, l.stream));
@@ -531,6 +636,7 @@ int doa_cuda_calibrate_create(doa_cuda_handle** out, float norm_spacing, int num
   if (rc) return rc;
   if (!std::isfinite(pilot_angle)) return fail(nullptr, DOA_CUDA_EINVAL, "pilot_angle must be finite");
   doa_cuda_handle* h = nullptr;
+  DevSave dev_save_;
   rc = begin_create(out, h, K_CALIB, device, max_frames);
   if (rc) return rc;
   h->d = norm_spacing; h->T = 1; h->M = num_ant_ele;
@@ -556,7 +662,7 @@ int doa_cuda_calibrate_run_device(doa_cuda_handle* h, const void* in_dev, int nf
   if (!h || h->kind != K_CALIB) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   Lane& l = h->lane[0];
   int a = launch_noise_subspace((const float2*)in_dev, h->M, 1, nframes, l.G, nullptr, nullptr, st);
@@ -572,7 +678,7 @@ int doa_cuda_calibrate_run(doa_cuda_handle* h, const void* in_host, int nframes,
   if (!h || h->kind != K_CALIB) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   Lane& l = h->lane[0];
   const size_t mm = (size_t)h->M * h->M;
   CK(h, cudaMemcpyAsync(l.R, in_host, sizeof(float2) * nframes * mm, cudaMemcpyHostToDevice, l.stream));
@@ -589,6 +695,7 @@ int doa_cuda_find_local_max_create(doa_cuda_handle** out, int num_max_vals, int 
   if (num_max_vals < 1 || num_max_vals > 16) return fail(nullptr, DOA_CUDA_EINVAL, "num_max_vals must be in [1, 16]");
   if (vector_len < 2) return fail(nullptr, DOA_CUDA_EINVAL, "vector_len must be >= 2");
   doa_cuda_handle* h = nullptr;
+  DevSave dev_save_;
   int rc = begin_create(out, h, K_FLM, device, max_frames);
   if (rc) return rc;
   h->K = num_max_vals; h->P = vector_len; h->x_min = x_min; h->x_max = x_max;
@@ -605,7 +712,7 @@ int doa_cuda_find_local_max_run_device(doa_cuda_handle* h, const void* in_dev, i
   if (!h || h->kind != K_FLM) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0) return fail(h, DOA_CUDA_EINVAL, "nframes < 0");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   int a = launch_find_local_max((const float*)in_dev, h->P, nframes, h->K, h->d_x, (float*)out_val_dev, (float*)out_loc_dev,
                                 (int*)out_bin_dev, (cudaStream_t)cuda_stream);
   if (a < 0) return fail(h, a, "find_local_max launch rejected (vector_len too large for shared memory?)");
@@ -619,7 +726,7 @@ int doa_cuda_find_local_max_run(doa_cuda_handle* h, const void* in_host, int nfr
   if (!h || h->kind != K_FLM) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   Lane& l = h->lane[0];
   CK(h, cudaMemcpyAsync(l.vecs, in_host, sizeof(float) * (size_t)nframes * h->P, cudaMemcpyHostToDevice, l.stream));
   int rc = doa_cuda_find_local_max_run_device(h, l.vecs, nframes, l.val, l.loc, l.bin, l.stream);
@@ -647,6 +754,7 @@ int doa_cuda_chain_create(doa_cuda_handle** out, int inputs, int snapshot_size, 
   if (pspectrum_len < 2) return fail(nullptr, DOA_CUDA_EINVAL, "pspectrum_len must be >= 2");
   if (num_max_vals < 1 || num_max_vals > 16) return fail(nullptr, DOA_CUDA_EINVAL, "num_max_vals must be in [1, 16]");
   doa_cuda_handle* h = nullptr;
+  DevSave dev_save_;
   rc = begin_create(out, h, K_CHAIN, device, max_frames);
   if (rc) return rc;
   h->M = inputs; h->N = snapshot_size; h->overlap = overlap_size; h->hop = snapshot_size - overlap_size; h->avg = avg_method;
@@ -661,7 +769,10 @@ int doa_cuda_chain_create(doa_cuda_handle** out, int inputs, int snapshot_size, 
     // lane 0 carries the intermediates for a full device-resident batch; lane 1 only ever sees host chunks
     const size_t nf = (i == 0) ? (size_t)max_frames : (size_t)chunk;
     l.frames = (int)nf;
-    l.in_elems = (size_t)chunk * h->M * h->N + 2 * (size_t)h->M;   // host staging (frames layout or [M][Lpad] streams)
+    // host staging: a chunk of independent frames, or -- lane 0, doa_cuda_chain_run_streams -- the [M][Lpad] channel streams of
+    // up to max_frames frames (hop <= snapshot_size, so that never exceeds max_frames * M * N samples)
+    const size_t Lpad_max = (((size_t)(max_frames - 1) * h->hop + h->N) + 1) & ~(size_t)1;
+    l.in_elems = std::max((size_t)chunk * h->M * h->N + 2 * (size_t)h->M, i == 0 ? Lpad_max * h->M : (size_t)0);
     ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess && dalloc(&l.in, l.in_elems) &&
          dalloc(&l.R, nf * mm) && dalloc(&l.G, nf * mm) && dalloc(&l.u, nf * h->M) && dalloc(&l.val, nf * h->K) &&
          dalloc(&l.loc, nf * h->K) && dalloc(&l.bin, nf * h->K);
@@ -674,7 +785,7 @@ static int chain_on_lane(doa_cuda_handle* h, Lane& l, const void* in_dev, long l
   cudaEvent_t* ev = nullptr;
   if (prof) { ev = &h->ev[(size_t)(h->prof_calls % PROF_SETS) * 4]; ++h->prof_calls; }
   if (prof) CK(h, cudaEventRecord(ev[0], st));
-  if (dev_option("fused", 1)) {
+  if (dev_option(OPT_FUSED, 1)) {
     // one persistent kernel for the whole chain when the shape allows it; stage events collapse to (0, 0, total)
     if (prof) { CK(h, cudaEventRecord(ev[1], st)); CK(h, cudaEventRecord(ev[2], st)); }
     int f = launch_chain_fused(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, h->T, tables_of(h), h->K, val,
@@ -687,13 +798,26 @@ static int chain_on_lane(doa_cuda_handle* h, Lane& l, const void* in_dev, long l
       return DOA_CUDA_OK;
     }
   }
-  int a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains, h->fmt);
-  if (a < 0) return fail(h, a, "covariance launch rejected");
-  if (prof) CK(h, cudaEventRecord(ev[1], st));
-  int b = launch_noise_subspace(l.R, h->M, h->T, nframes, l.G, l.u, nullptr, st);
-  if (b < 0) return fail(h, b, "eigendecomposition launch rejected");
-  if (prof) CK(h, cudaEventRecord(ev[2], st));
-  int c = dev_option("scan_tc", 1) ? launch_scan_peaks_tc(l.u, l.G, tables_of(h), nframes, h->K, val, loc, bin, st) : 0;
+  // 16 elements: covariance and eigendecomposition are both bound by the FP32 pipe and by registers (255 per covariance thread,
+  // 125 per Jacobi thread): sharing the SMs in one persistent kernel (fused16.cu) leaves each side too few warps and measured
+  // 4.9 ms against 1.7 + 2.3 ms for the two stage kernels (65,536 frames).  The experiment stays in the -DDOA_DEV_KNOBS build.
+  int a = 0;
+#ifdef DOA_DEV_KNOBS
+  if (dev_option(OPT_FUSED16, 0))
+    a = launch_cov_eig_fused16(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, h->T, l.G, l.u, st, h->d_gains, h->fmt);
+#endif
+  int b = 0;
+  if (a > 0) {
+    if (prof) { CK(h, cudaEventRecord(ev[1], st)); CK(h, cudaEventRecord(ev[2], st)); }
+  } else {
+    a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains, h->fmt);
+    if (a < 0) return fail(h, a, "covariance launch rejected");
+    if (prof) CK(h, cudaEventRecord(ev[1], st));
+    b = launch_noise_subspace(l.R, h->M, h->T, nframes, l.G, l.u, nullptr, st);
+    if (b < 0) return fail(h, b, "eigendecomposition launch rejected");
+    if (prof) CK(h, cudaEventRecord(ev[2], st));
+  }
+  int c = dev_option(OPT_SCAN_TC, 1) ? launch_scan_peaks_tc(l.u, l.G, tables_of(h), nframes, h->K, val, loc, bin, st) : 0;
   if (c == 0) c = launch_scan_peaks(l.u, l.G, tables_of(h), nframes, h->K, val, loc, bin, st);
   if (c < 0) return fail(h, c, "scan launch rejected (pspectrum_len too large for shared memory?)");
   if (prof) CK(h, cudaEventRecord(ev[3], st));
@@ -707,7 +831,7 @@ int doa_cuda_chain_run_device(doa_cuda_handle* h, const void* in_dev, long long 
   if (!h || h->kind != K_CHAIN) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   h->launches = 0;
   return chain_on_lane(h, h->lane[0], in_dev, frame_stride, chan_stride, nframes, (float*)out_val_dev,
                        (float*)out_loc_dev, (int*)out_bin_dev, (cudaStream_t)cuda_stream, h->profiling);
@@ -718,12 +842,24 @@ int doa_cuda_chain_run(doa_cuda_handle* h, const void* in_host, int nframes, voi
   if (!h || h->kind != K_CHAIN) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   h->launches = 0;
   const size_t fe = (size_t)h->M * h->N;
   const int chunk = h->lane[1].frames;
   const size_t sb = h->sample_bytes();
   const char* src = (const char*)in_host;
+  if (nframes <= chunk && is_pageable(in_host)) {   // a small call out of pageable memory: one staged copy in, one synchronisation out
+    Lane& l = h->lane[0];
+    char* pin = pin_staging(l, sb * nframes * fe);
+    if (pin != nullptr) {
+      CK(h, cudaStreamSynchronize(l.stream));
+      std::memcpy(pin, src, sb * nframes * fe);
+      CK(h, cudaMemcpyAsync(l.in, pin, sb * nframes * fe, cudaMemcpyHostToDevice, l.stream));
+      int rc = chain_on_lane(h, l, l.in, (long long)fe, h->N, nframes, l.val, l.loc, l.bin, l.stream, false);
+      if (rc) return rc;
+      return peaks_to_host(h, l, nframes, out_val_host, out_loc_host, out_bin_host);
+    }
+  }
   int c = 0;
   for (int f0 = 0; f0 < nframes; f0 += chunk, ++c) {
     Lane& l = h->lane[c & 1];
@@ -746,7 +882,7 @@ int doa_cuda_chain_run_streams(doa_cuda_handle* h, const void* const* in_host, i
   if (!h || h->kind != K_CHAIN) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   h->launches = 0;
   Lane& l = h->lane[0];
   size_t Lpad = 0;
@@ -754,12 +890,7 @@ int doa_cuda_chain_run_streams(doa_cuda_handle* h, const void* const* in_host, i
   if (rc) return rc;
   rc = chain_on_lane(h, l, l.in, h->hop, (long long)Lpad, nframes, l.val, l.loc, l.bin, l.stream, false);
   if (rc) return rc;
-  const size_t nk = (size_t)nframes * h->K;
-  CK(h, cudaMemcpyAsync(out_val_host, l.val, sizeof(float) * nk, cudaMemcpyDeviceToHost, l.stream));
-  CK(h, cudaMemcpyAsync(out_loc_host, l.loc, sizeof(float) * nk, cudaMemcpyDeviceToHost, l.stream));
-  if (out_bin_host) CK(h, cudaMemcpyAsync(out_bin_host, l.bin, sizeof(int) * nk, cudaMemcpyDeviceToHost, l.stream));
-  CK(h, cudaStreamSynchronize(l.stream));
-  return DOA_CUDA_OK;
+  return peaks_to_host(h, l, nframes, out_val_host, out_loc_host, out_bin_host);
 }
 
 // ---- autocorrelate -> rootMUSIC_linear_array without the covariance leaving the device (BASELINE configs[1]) ------------
@@ -775,6 +906,7 @@ int doa_cuda_rootchain_create(doa_cuda_handle** out, int inputs, int snapshot_si
   int rc = check_array(norm_spacing, num_targets, inputs);
   if (rc) return rc;
   doa_cuda_handle* h = nullptr;
+  DevSave dev_save_;
   rc = begin_create(out, h, K_ROOTCHAIN, device, max_frames);
   if (rc) return rc;
   h->M = inputs; h->N = snapshot_size; h->overlap = overlap_size; h->hop = snapshot_size - overlap_size; h->avg = avg_method;
@@ -794,7 +926,7 @@ int doa_cuda_rootchain_run_device(doa_cuda_handle* h, const void* in_dev, long l
   if (!h || h->kind != K_ROOTCHAIN) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   Lane& l = h->lane[0];
   int a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains, h->fmt);
@@ -812,7 +944,7 @@ int doa_cuda_rootchain_run_streams(doa_cuda_handle* h, const void* const* in_hos
   if (!h || h->kind != K_ROOTCHAIN) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   Lane& l = h->lane[0];
   size_t Lpad = 0;
   int rc = stage_streams(h, l, in_host, nframes, &Lpad);
@@ -828,7 +960,7 @@ int doa_cuda_rootchain_run(doa_cuda_handle* h, const void* in_host, int nframes,
   if (!h || h->kind != K_ROOTCHAIN) return DOA_CUDA_EINVAL;
   if (nframes == 0) return DOA_CUDA_OK;
   if (nframes < 0 || nframes > h->max_frames) return fail(h, DOA_CUDA_ECAPACITY, "nframes exceeds max_frames");
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   Lane& l = h->lane[0];
   const size_t fe = (size_t)h->M * h->N;
   CK(h, cudaMemcpyAsync(l.in, in_host, h->sample_bytes() * fe * nframes, cudaMemcpyHostToDevice, l.stream));
@@ -852,6 +984,7 @@ int doa_cuda_multi_create(doa_cuda_handle** out, int inputs, int snapshot_size, 
   *out = nullptr;
   if (!devices || ndevices < 1 || ndevices > 64) return fail(nullptr, DOA_CUDA_EINVAL, "need 1 <= ndevices <= 64 and a device list");
   doa_cuda_handle* h = nullptr;
+  DevSave dev_save_;
   int rc = begin_create(out, h, K_MULTI, devices[0], max_frames_per_device);
   if (rc) return rc;
   h->M = inputs; h->N = snapshot_size; h->K = num_max_vals; h->overlap = overlap_size; h->hop = snapshot_size - overlap_size;
@@ -939,7 +1072,7 @@ int doa_cuda_multi_run_streams(doa_cuda_handle* h, const void* const* in_host, i
 
 int doa_cuda_set_profiling(doa_cuda_handle* h, int on) {
   if (!h || h->kind != K_CHAIN) return DOA_CUDA_EINVAL;
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   if (on && h->ev.empty()) {
     h->ev.assign((size_t)PROF_SETS * 4, nullptr);
     for (auto& e : h->ev) CK(h, cudaEventCreate(&e));
@@ -953,7 +1086,7 @@ int doa_cuda_set_profiling(doa_cuda_handle* h, int on) {
 // (the last PROF_SETS of them); returns the number of calls averaged, or a negative error.
 int doa_cuda_chain_stage_ms(doa_cuda_handle* h, float* cov_ms, float* eig_ms, float* scan_ms) {
   if (!h || h->kind != K_CHAIN || h->ev.empty()) return DOA_CUDA_EINVAL;
-  CK(h, cudaSetDevice(h->device));
+  ENTER(h);
   const int n = std::min(h->prof_calls, PROF_SETS);
   double a = 0, b = 0, c = 0;
   for (int i = 0; i < n; ++i) {

@@ -67,6 +67,12 @@ int launch_chain_fused(const void* in, long long frame_stride, long long chan_st
                        int avg_method, int T, const ScanTables& tb, int K, float* out_val, float* out_loc, int* out_bin,
                        cudaStream_t st, const float2* gains = nullptr, InputFormat fmt = InputFormat());
 
+// 16-element arrays: covariance + eigendecomposition in one persistent warp-specialised kernel (fused16.cu); G and u as from
+// launch_noise_subspace.  Returns 1 if launched, 0 if the shape is not covered.  Bit-identical to the two stage kernels and
+// SLOWER than them (measured, tools/fused16_exp.py): an experiment kept in the -DDOA_DEV_KNOBS build only.
+int launch_cov_eig_fused16(const void* in, long long frame_stride, long long chan_stride, int M, int N, int nframes, int avg_method,
+                           int T, float2* G, float2* u, cudaStream_t st, const float2* gains = nullptr, InputFormat fmt = InputFormat());
+
 // Stage 2b standalone: the full dB pseudo-spectrum [nframes][P].
 int launch_scan_spectrum(const float2* u, const float2* G, const ScanTables& tb, int nframes, float* out,
                          cudaStream_t st);
@@ -80,8 +86,24 @@ int launch_find_local_max(const float* in, int len, int nframes, int K, const fl
 int launch_rootmusic_scratch(const float2* u, int M, int T, float norm_spacing, int nframes, double2* scratch,
                              long long stride, float* out, cudaStream_t st);
 
-// Development knobs (doa_cuda_dev_set): kernel-variant selection for A/B measurements; defaults are the shipped path.
-int dev_option(const char* key, int dflt);
+// Per-handle options (doa_cuda_set_option, include/doa_cuda.h): kernel-path selection for A/B measurements and the multi-GPU
+// SM reserve; the defaults are the shipped path.  The values live in the handle; an ABI entry point makes its handle's set
+// the calling thread's current one for the duration of the call (doa_cuda.cu: Enter), the launchers read it with dev_option():
+// no global mutable state, no lock, no lookup on the launch path.
+enum Opt {
+  OPT_FUSED, OPT_SCAN_TC, OPT_SMS_RESERVE, OPT_COV_GROUPS, OPT_COV16_RING, OPT_HERK_TC, OPT_SCAN_WIDE, OPT_SPECTRUM_SMEM,
+  OPT_ROOT_ABERTH, OPT_JACOBI_SWEEPS,
+  // kernel variants that only exist in a -DDOA_DEV_KNOBS build (libdoa_cuda_dev.so, used by tools/ and the bit-identity tests)
+  OPT_WS_SPLIT, OPT_WS_STAGES, OPT_WS_NBUF, OPT_WS4, OPT_WS_TMA, OPT_WS_FILL, OPT_SCAN_TC_DBG, OPT_FUSED16,
+  OPT_COUNT
+};
+constexpr int OPT_FIRST_DEV_ONLY = OPT_WS_SPLIT;
+constexpr int OPT_UNSET = -2147483647 - 1;
+struct Tuning {
+  int v[OPT_COUNT];
+  Tuning() { for (int i = 0; i < OPT_COUNT; ++i) v[i] = OPT_UNSET; }
+};
+int dev_option(Opt key, int dflt);
 
 // Host-side table construction (reference constructor arithmetic).
 void build_music_tables(float norm_spacing, int M, int P, std::vector<float>& array_loc, std::vector<float>& theta,

@@ -246,7 +246,7 @@ template <int M>
 int launch_group(const float2* R, int T, int nframes, float2* G, float2* u, float* w, cudaStream_t st) {
   constexpr int per_block = JG_WARPS * (32 / M);
   const int blocks = (nframes + per_block - 1) / per_block;
-  jacobi_group_kernel<M><<<blocks, JG_WARPS * 32, 0, st>>>(R, T, nframes, G, u, w, dev_option("jacobi_sweeps", M <= 8 ? 12 : 16));
+  jacobi_group_kernel<M><<<blocks, JG_WARPS * 32, 0, st>>>(R, T, nframes, G, u, w, dev_option(OPT_JACOBI_SWEEPS, M <= 8 ? 12 : 16));
   return 1;
 }
 

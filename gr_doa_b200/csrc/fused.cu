@@ -253,7 +253,7 @@ int launch_ws_cfg2(const S* in, long long fs, long long cs, int N, int nframes, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // Multi-GPU runs leave a few SMs to the peak gather's NCCL kernel so that it overlaps the next step's chain kernel
   // (a persistent CTA owns a whole SM's registers and shared memory: nothing else can co-reside).
-  sms = std::max(1, sms - std::max(0, dev_option("chain_sms_reserve", 0)));
+  sms = std::max(1, sms - std::max(0, dev_option(OPT_SMS_RESERVE, 0)));
   // small batches (a GNU Radio work() call): spread over the SMs down to one consumer warp's worth of frames per CTA
   constexpr int GRP = 32 / M;
   const int grid = std::max(1, std::min(sms, (nframes + GRP - 1) / GRP));
@@ -270,15 +270,17 @@ int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nfram
   // Bulk (TMA) ring fills, measured at cfg3: 1.99 ms against 1.67 ms with per-lane cp.async -- a 512-byte copy per channel and
   // chunk is too small for the bulk-copy engine (16.8 M copies per launch) and larger ones do not fit per-warp rings.  Kept
   // selectable (dev knob ws_tma) for the default configuration only.
+#ifdef DOA_DEV_KNOBS
   if constexpr (WS_P == 8 && WS_C == 8 && WS_STAGES == 2 && WS_NBUF == 4) {
-    if (N % 64 == 0 && dev_option("ws_tma", 0))
+    if (N % 64 == 0 && dev_option(OPT_WS_TMA, 0))
       return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 1>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
   }
   // channel-major fills (FILL 2): instantiated for the shipped configurations only
   if constexpr ((M == 8 && WS_P == 8 && WS_C == 8 && WS_STAGES == 2 && WS_NBUF == 4) || (M == 4 && WS_P == 8 && WS_C == 8 && WS_STAGES == 6 && WS_NBUF == 4)) {
-    if (dev_option("ws_fill", 0) == 2)
+    if (dev_option(OPT_WS_FILL, 0) == 2)
       return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 2>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
   }
+#endif
   return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 0>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
 }
 
@@ -300,12 +302,13 @@ int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_
     // shared memory.  Not tuned separately yet.
     const unsigned* in = static_cast<const unsigned*>(in_v);
     const float s2 = fmt.scale * fmt.scale;
-    const bool f2 = dev_option("ws_fill", 0) == 2;
-    if (M == 4) {
-      if (f2) return launch_ws_cfg2<4, 8, 8, 6, 4, 2>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
-      return launch_ws_cfg2<4, 8, 8, 6, 4, 0>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
+#ifdef DOA_DEV_KNOBS
+    if (dev_option(OPT_WS_FILL, 0) == 2) {
+      if (M == 4) return launch_ws_cfg2<4, 8, 8, 6, 4, 2>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
+      return launch_ws_cfg2<8, 8, 8, 3, 4, 2>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
     }
-    if (f2) return launch_ws_cfg2<8, 8, 8, 3, 4, 2>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
+#endif
+    if (M == 4) return launch_ws_cfg2<4, 8, 8, 6, 4, 0>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
     return launch_ws_cfg2<8, 8, 8, 3, 4, 0>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
   }
   const float2* in = static_cast<const float2*>(in_v);
@@ -318,7 +321,10 @@ int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_
   // feeds consumer w through a private ring of 4-frame slots and mbarriers, no CTA-wide barrier) measured the same 1.67 ms.
 #define WS_ARGS in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains
   if (M == 4) {   // covariance-dominated (80 % of the step): the consumers only have to hide 0.1 + 0.7 ms under 2.6 ms of streaming
-    switch (dev_option("ws4", 5)) {
+#ifndef DOA_DEV_KNOBS
+    return launch_ws_cfg<4, 8, 8, 6, 4>(WS_ARGS);
+#else
+    switch (dev_option(OPT_WS4, 5)) {
       case 0: return 0;
       case 1: return launch_ws_cfg<4, 8, 8, 2, 4>(WS_ARGS);
       case 2: return launch_ws_cfg<4, 12, 4, 2, 4>(WS_ARGS);
@@ -329,9 +335,13 @@ int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_
       case 7: return launch_ws_cfg<4, 12, 4, 4, 4>(WS_ARGS);
       default: return launch_ws_cfg<4, 6, 10, 4, 4>(WS_ARGS);
     }
+#endif
   }
-  // dev knobs (tools/ws_exp.py): ws_split = producers * 100 + consumers, ws_stages = cp.async ring depth, ws_nbuf = tile buffers
-  switch ((dev_option("ws_split", 808) * 10 + dev_option("ws_stages", 2)) * 10 + dev_option("ws_nbuf", 4)) {
+#ifndef DOA_DEV_KNOBS
+  return launch_ws_cfg<8, 8, 8, 2, 4>(WS_ARGS);
+#else
+  // -DDOA_DEV_KNOBS (tools/ws_exp.py): ws_split = producers * 100 + consumers, ws_stages = cp.async ring depth, ws_nbuf = tile buffers
+  switch ((dev_option(OPT_WS_SPLIT, 808) * 10 + dev_option(OPT_WS_STAGES, 2)) * 10 + dev_option(OPT_WS_NBUF, 4)) {
     case 41232: return launch_ws_cfg<8, 4, 12, 3, 2>(WS_ARGS);      // the first fused configuration (1.91 ms)
     case 41252: return launch_ws_cfg<8, 4, 12, 5, 2>(WS_ARGS);
     case 41642: return launch_ws_cfg<8, 4, 16, 4, 2>(WS_ARGS);      // setmaxnreg re-allocated
@@ -344,6 +354,7 @@ int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_
     case 80826: return launch_ws_cfg<8, 8, 8, 2, 6>(WS_ARGS);
     default: return launch_ws_cfg<8, 8, 8, 2, 4>(WS_ARGS);
   }
+#endif
 #undef WS_ARGS
 }
 

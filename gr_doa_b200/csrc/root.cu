@@ -240,7 +240,7 @@ int launch_rootmusic_scratch(const float2* u, int M, int T, float norm_spacing, 
   const int blocks = (nframes + threads - 1) / threads;
   const int n = 2 * M - 2;
   int only_flagged = 0;
-  if (n >= 1 && n <= AB_MAX_N && dev_option("root_aberth", 1)) {
+  if (n >= 1 && n <= AB_MAX_N && dev_option(OPT_ROOT_ABERTH, 1)) {
     const size_t smem = (size_t)2 * n * AB_THREADS * sizeof(double2);
     cudaFuncSetAttribute(rootmusic_aberth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     rootmusic_aberth_kernel<<<(nframes + AB_THREADS - 1) / AB_THREADS, AB_THREADS, smem, st>>>(u, M, T, norm_spacing, nframes, out);

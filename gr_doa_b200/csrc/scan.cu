@@ -282,7 +282,7 @@ int launch_peaks_mt(const float2* u, const float2* G, const ScanTables& tb, int 
   }
   if constexpr (MT == 0) {
     const size_t wsmem = (size_t)((P + 3) & ~3) * sizeof(float) + (size_t)M * sizeof(float2);
-    if (wsmem <= 200 * 1024 && nframes <= 8 * sm_count() && dev_option("scan_wide", 1)) {
+    if (wsmem <= 200 * 1024 && nframes <= 8 * sm_count() && dev_option(OPT_SCAN_WIDE, 1)) {
       const int per = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / wsmem));
       const int grid = min(nframes, sm_count() * per);
       if (K <= 4) {
@@ -318,7 +318,7 @@ template <int MT>
 int launch_spectrum_mt(const float2* u, const ScanTables& tb, int nframes, float* out, cudaStream_t st) {
   if constexpr (MT > 0) {
     const size_t per_warp = (size_t)tb.P * sizeof(float);
-    if (per_warp <= 48 * 1024 && dev_option("spectrum_smem", 1)) {
+    if (per_warp <= 48 * 1024 && dev_option(OPT_SPECTRUM_SMEM, 1)) {
       const int warps = (int)std::max<size_t>(1, std::min<size_t>(4, (64 * 1024) / per_warp));
       const size_t smem = per_warp * warps;
       auto kern = scan_spectrum_smem_kernel<MT>;

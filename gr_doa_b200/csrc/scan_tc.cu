@@ -498,7 +498,7 @@ int launch_tc_mt(const float2* u, const float2* G, const ScanTables& tb, int nfr
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ntiles = (nframes + ST_FRAMES - 1) / ST_FRAMES;
   const int grid = std::min(ntiles, sms);
-  const int ks = scan_tc_ksteps(M), dbg = dev_option("scan_tc_dbg", 0);
+  const int ks = scan_tc_ksteps(M), dbg = dev_option(OPT_SCAN_TC_DBG, 0);
   if (K == 1) {
     auto kern = scan_tc_kernel<MT, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -516,7 +516,7 @@ int launch_scan_peaks_tc(const float2* u, const float2* G, const ScanTables& tb,
                          float* out_loc, int* out_bin, cudaStream_t st) {
   if (nframes <= 0) return 0;
   if (tb.tctab == nullptr || !scan_tc_covers(tb.M, tb.P, K)) return 0;
-  if ((reinterpret_cast<uintptr_t>(G) & 15u) != 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(G) & 15u) != 0 || (tb.M & 1)) return 0;   // the refinement stages G with 16-byte loads
   switch (tb.M) {
     case 4: return launch_tc_mt<4>(u, G, tb, nframes, K, out_val, out_loc, out_bin, st);
     case 8: return launch_tc_mt<8>(u, G, tb, nframes, K, out_val, out_loc, out_bin, st);

@@ -93,6 +93,14 @@ int main(int argc, char** argv) {
     return 3;
   }
 
+  /* scheduler hints of the fused chain blocks: a real scheduler would only offer them multiples of
+   * output_multiple(); this harness keeps offering arbitrary n to every block (the blocks accept any n) and checks the hints */
+  if (mc->output_multiple() < 2 || mc->min_output_buffer() < 4L * mc->output_multiple() || rc->output_multiple() != mc->output_multiple() ||
+      ac->output_multiple() != 1) {
+    std::fprintf(stderr, "scheduler hints: music_chain multiple %d buffer %ld, rootmusic_chain multiple %d\n", mc->output_multiple(),
+                 mc->min_output_buffer(), rc->output_multiple());
+    return 5;
+  }
   const int hop = N - overlap;
   /* GNU Radio pre-fills history()-1 zeros in front of the stream; gr-doa's QA vectors are laid out so that the first
    * snapshot starts at sample 0, i.e. the scheduler view is: read pointer at sample 0, `overlap` samples of look-ahead

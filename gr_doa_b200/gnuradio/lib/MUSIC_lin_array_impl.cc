@@ -22,7 +22,7 @@ MUSIC_lin_array_impl::MUSIC_lin_array_impl(float norm_spacing, int num_targets, 
                      gr::io_signature::make(1, 1, sizeof(float) * pspectrum_len)),
       d_norm_spacing(norm_spacing), d_num_targets(num_targets), d_num_ant_ele(num_ant_ele), d_pspectrum_len(pspectrum_len),
       d_cuda(NULL), nout_items_total(0) {
-  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", 8192);
+  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", DOA_CUDA_DEFAULT_MAX_FRAMES);
   doa_require_created(doa_cuda_music_create(&d_cuda, norm_spacing, num_targets, num_ant_ele, pspectrum_len,
                                             doa_env_int("DOA_CUDA_DEVICE", 0), d_max_frames),
                       "doa.MUSIC_lin_array");

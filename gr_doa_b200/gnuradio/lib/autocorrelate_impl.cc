@@ -25,7 +25,7 @@ autocorrelate_impl::autocorrelate_impl(int inputs, int snapshot_size, int overla
       d_cuda(NULL), d_ptrs(inputs) {
   d_nonoverlap_size = d_snapshot_size - d_overlap_size;
   set_history(d_overlap_size + 1);
-  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", 8192);
+  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", DOA_CUDA_DEFAULT_MAX_FRAMES);
   doa_require_created(doa_cuda_autocorrelate_create(&d_cuda, inputs, snapshot_size, overlap_size, avg_method,
                                                     doa_env_int("DOA_CUDA_DEVICE", 0), d_max_frames),
                       "doa.autocorrelate");

@@ -20,7 +20,7 @@ calibrate_lin_array_impl::calibrate_lin_array_impl(float norm_spacing, int num_a
     : gr::sync_block("calibrate_lin_array", gr::io_signature::make(1, 1, num_ant_ele * num_ant_ele * sizeof(gr_complex)),
                      gr::io_signature::make(1, 1, num_ant_ele * sizeof(gr_complex))),
       d_norm_spacing(norm_spacing), d_num_ant_ele(num_ant_ele), d_pilot_angle(pilot_angle), d_cuda(NULL) {
-  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", 8192);
+  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", DOA_CUDA_DEFAULT_MAX_FRAMES);
   doa_require_created(doa_cuda_calibrate_create(&d_cuda, norm_spacing, num_ant_ele, pilot_angle, doa_env_int("DOA_CUDA_DEVICE", 0),
                                                 d_max_frames),
                       "doa.calibrate_lin_array");

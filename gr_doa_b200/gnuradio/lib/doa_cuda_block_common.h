@@ -1,6 +1,10 @@
 /* Shared by the four *_impl.cc: handle ownership and the environment knobs the frozen constructor signatures cannot carry.
  *   DOA_CUDA_DEVICE      CUDA device index (default 0)
- *   DOA_CUDA_MAX_FRAMES  largest noutput_items processed per libdoa_cuda call (default 8192; larger calls are chunked)
+ *   DOA_CUDA_MAX_FRAMES  largest noutput_items processed per libdoa_cuda call (default 256; larger calls are chunked).  Device
+ *                        buffers are sized for it at construction: at 4 x 2048 samples per frame 256 frames are 16 MB per
+ *                        block, and a scheduler call carries a few dozen frames at most (64 KB items in its default buffers)
+ *   DOA_CUDA_MIN_FRAMES  scheduler hint for the fused chain blocks (default 8): set_output_multiple() keeps the scheduler from
+ *                        calling work() for fewer frames, set_min_output_buffer() sizes the output buffers for 4x as many
  *   DOA_CUDA_DEVICES     comma-separated device list for doa.music_chain: the frames of every work() call are spread over
  *                        these GPUs (doa_cuda_multi_*); unset = the single DOA_CUDA_DEVICE */
 #ifndef INCLUDED_DOA_CUDA_BLOCK_COMMON_H
@@ -10,6 +14,8 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#define DOA_CUDA_DEFAULT_MAX_FRAMES 256
+#define DOA_CUDA_DEFAULT_MIN_FRAMES 8
 namespace gr {
 namespace doa {
 inline int doa_env_int(const char* name, int dflt) {

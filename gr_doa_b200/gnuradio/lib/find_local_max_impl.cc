@@ -20,7 +20,7 @@ find_local_max_impl::find_local_max_impl(int num_max_vals, int vector_len, float
     : gr::sync_block("find_local_max", gr::io_signature::make(1, 1, sizeof(float) * vector_len),
                      gr::io_signature::make2(2, 2, num_max_vals * sizeof(float), num_max_vals * sizeof(float))),
       d_num_max_vals(num_max_vals), d_vector_len(vector_len), d_x_min(x_min), d_x_max(x_max), d_cuda(NULL) {
-  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", 8192);
+  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", DOA_CUDA_DEFAULT_MAX_FRAMES);
   doa_require_created(doa_cuda_find_local_max_create(&d_cuda, num_max_vals, vector_len, x_min, x_max,
                                                      doa_env_int("DOA_CUDA_DEVICE", 0), d_max_frames),
                       "doa.find_local_max");

@@ -38,7 +38,15 @@ music_chain_impl::music_chain_impl(int inputs, int snapshot_size, int overlap_si
       d_item_bytes(sc16_scale > 0.0f ? 2 * sizeof(short) : sizeof(gr_complex)), d_cuda(NULL), d_multi(false), d_ptrs(inputs) {
   d_nonoverlap_size = d_snapshot_size - d_overlap_size;
   set_history(d_overlap_size + 1);
-  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", 8192);
+  // Scheduler batching: the reference's blocks take whatever noutput_items the scheduler offers (often 1); a GPU call
+  // wants a batch.  Never call work() for fewer than DOA_CUDA_MIN_FRAMES frames, and ask for output buffers of four such
+  // batches so that the upstream blocks can run ahead while a batch is on the device.
+  {
+    const int min_frames = std::max(1, doa_env_int("DOA_CUDA_MIN_FRAMES", DOA_CUDA_DEFAULT_MIN_FRAMES));
+    set_output_multiple(min_frames);
+    set_min_output_buffer(4L * min_frames);
+  }
+  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", DOA_CUDA_DEFAULT_MAX_FRAMES);
   const std::vector<int> devs = doa_env_devices();
   d_multi = devs.size() > 1;
   if (d_multi) {   /* one block instance, every listed GPU: frames of a work() call are cut into one block per device */

@@ -19,7 +19,7 @@ rootMUSIC_linear_array_impl::rootMUSIC_linear_array_impl(float norm_spacing, int
     : gr::sync_block("rootMUSIC_linear_array", gr::io_signature::make(1, 1, sizeof(gr_complex) * num_ant_ele * num_ant_ele),
                      gr::io_signature::make(1, num_targets, num_targets * sizeof(float))),
       d_norm_spacing(norm_spacing), d_num_targets(num_targets), d_num_ant_ele(num_ant_ele), d_cuda(NULL) {
-  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", 8192);
+  d_max_frames = doa_env_int("DOA_CUDA_MAX_FRAMES", DOA_CUDA_DEFAULT_MAX_FRAMES);
   doa_require_created(doa_cuda_rootmusic_create(&d_cuda, norm_spacing, num_targets, num_ant_ele,
                                                 doa_env_int("DOA_CUDA_DEVICE", 0), d_max_frames),
                       "doa.rootMUSIC_linear_array");

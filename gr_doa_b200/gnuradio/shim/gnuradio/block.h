@@ -19,14 +19,18 @@ class block {
   }
   virtual int general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
                            gr_vector_void_star& output_items) = 0;
+  void set_output_multiple(int m) { d_output_multiple = m; }
+  int output_multiple() const { return d_output_multiple; }
+  void set_min_output_buffer(long n) { d_min_output_buffer = n; }
+  long min_output_buffer() const { return d_min_output_buffer; }
   void consume_each(int n) { d_consumed = n; }
   int last_consumed() const { return d_consumed; }   // shim only: what the scheduler would advance the read pointers by
  protected:
-  block() : d_history(1), d_consumed(0) {}
+  block() : d_history(1), d_consumed(0), d_output_multiple(1), d_min_output_buffer(-1) {}
   block(const std::string& name, io_signature::sptr in, io_signature::sptr out)
-      : d_name(name), d_in(in), d_out(out), d_history(1), d_consumed(0) {}
+      : d_name(name), d_in(in), d_out(out), d_history(1), d_consumed(0), d_output_multiple(1), d_min_output_buffer(-1) {}
  private:
-  std::string d_name; io_signature::sptr d_in, d_out; unsigned d_history; int d_consumed;
+  std::string d_name; io_signature::sptr d_in, d_out; unsigned d_history; int d_consumed; int d_output_multiple; long d_min_output_buffer;
 };
 }  // namespace gr
 namespace gnuradio {

@@ -72,3 +72,26 @@ def frames_torch(B, M, N, thetas_deg, d=0.5, snr_db=10.0, jitter_deg=0.0, seed=S
         nz = torch.view_as_complex(torch.randn((nb, M, N, 2), generator=g, device=device, dtype=torch.float32))
         out[b0:b1] = x + nz * (sigma / math.sqrt(2.0))
     return out, truth
+
+
+def stream_torch(M, L, thetas_deg, d=0.5, snr_db=10.0, seed=SEED_BASE, device="cuda", chunk=1 << 22):
+    """M continuous channel streams [M][L] complex64 generated on `device` in chunks along time (the streaming form:
+    frames of snapshot_size samples every hop samples are read in place from these streams)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    T = len(thetas_deg)
+    out = torch.empty((M, L), dtype=torch.complex64, device=device)
+    loc = d * 0.5 * (M - 1 - 2 * torch.arange(M, device=device, dtype=torch.float64))
+    th = torch.tensor(list(thetas_deg), device=device, dtype=torch.float64)
+    A = torch.exp(-1j * 2 * math.pi * torch.cos(torch.deg2rad(th))[:, None] * loc[None, :]).to(torch.complex64)     # [T][M]
+    w = math.pi / (torch.arange(T, device=device, dtype=torch.float64) + 2.0)
+    ph = torch.rand((T,), generator=g, device=device, dtype=torch.float64) * 2 * math.pi
+    sigma = math.sqrt(10.0 ** (-snr_db / 10.0))
+    for t0 in range(0, L, chunk):
+        t1 = min(L, t0 + chunk)
+        t = torch.arange(t0, t1, device=device, dtype=torch.float64)
+        s = torch.exp(1j * (torch.remainder(w[:, None] * t[None, :], 2 * math.pi) + ph[:, None])).to(torch.complex64)   # [T][n]
+        nz = torch.view_as_complex(torch.randn((M, t1 - t0, 2), generator=g, device=device, dtype=torch.float32))
+        out[:, t0:t1] = A.t() @ s + nz * (sigma / math.sqrt(2.0))
+    return out

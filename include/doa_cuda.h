@@ -183,6 +183,31 @@ int doa_cuda_antenna_gains_from_file(const char* config_filename, int num_ant_el
 #define DOA_CUDA_FMT_SC16 1
 int doa_cuda_set_input_format(doa_cuda_handle* h, int format, float scale);
 
+/* ---- per-handle options ------------------------------------------------------------------------------------------------
+ * Path selection for A/B measurements and the multi-GPU SM reserve.  The defaults are the shipped path; an option is stored in
+ * the handle (a multi handle forwards it to its per-device handles) and read at launch time -- there is no process-global
+ * state.  Keys (value = int):
+ *   "sms_reserve"    0..64, default 0   SMs the persistent chain kernel leaves free, so that a collective's kernel (the NCCL peak
+ *                                       gather of a multi-GPU run) can run under the next batch's chain kernel
+ *   "fused"          default 1          0: run the chain as its stage kernels (covariance, eigendecomposition, scan + peaks)
+ *                                       instead of the persistent warp-specialised kernel (4- and 8-element arrays)
+ *   "scan_tc"        default 1          0: Horner scan on the CUDA cores instead of the tensor-core contraction (unfused chain)
+ *   "herk_tc"        default 1          0: CUDA-core tiled covariance at 64 elements instead of the tensor-core HERK
+ *   "root_aberth"    default 1          0: Root-MUSIC by Hessenberg QR only
+ *   "scan_wide", "spectrum_smem", "cov16_ring", "cov_groups", "jacobi_sweeps"   kernel variants of single stages
+ * A library built with -DDOA_DEV_KNOBS (libdoa_cuda_dev.so: tools/, bit-identity tests) also carries the experimental fused
+ * kernel configurations and accepts "ws_split", "ws_stages", "ws_nbuf", "ws4", "ws_tma", "ws_fill", "scan_tc_dbg", "fused16";
+ * the product library answers DOA_CUDA_EINVAL to those.  Every variant computes identical results unless its description says
+ * otherwise. */
+int doa_cuda_set_option(doa_cuda_handle* h, const char* key, int value);
+int doa_cuda_has_dev_knobs(void);   /* 1 in a -DDOA_DEV_KNOBS build */
+
+/* ---- threading and streams ---------------------------------------------------------------------------------------------
+ * A handle serves ONE call at a time (a GNU Radio block's work() is called serially): *_run_device reuses per-handle scratch
+ * buffers on the caller's stream, so calls on the same handle from two streams or two threads must not overlap.  Different
+ * handles are independent.  Every entry point makes the handle's device current for the duration of the call and restores the
+ * calling thread's previous device before it returns; `cuda_stream` must belong to the handle's device. */
+
 /* ---- page-locking the caller's buffers -------------------------------------------------------------------------------
  * The *_run entry points accept any host memory.  Out of pageable memory (a GNU Radio scheduler's buffers) the host->device
  * copy is staged by the driver and runs at a fraction of the PCIe rate; a flowgraph's circular buffers live as long as the

@@ -167,3 +167,38 @@ def rootchain_frames(frames, avg_method, norm_spacing, num_targets, nthreads=1):
     out = np.empty((B, num_targets), np.float32)
     lib().ref_rootchain_frames(M, N, int(avg_method), C.c_float(norm_spacing), num_targets, _p(x), B, _p(out), nthreads)
     return out
+
+
+def chain_frames_procs(frames, avg_method, norm_spacing, num_targets, P, K, nprocs, root=False):
+    """The same flowgraph over `nprocs` single-threaded worker PROCESSES (oracle/ref_worker.py), the way independent GNU Radio
+    flowgraphs would use the cores; threads of one process serialise on OpenBLAS's buffer lock.  Returns (outputs, seconds)
+    with outputs = (values, locations) -- or (angles,) for root=True -- and seconds = the slowest worker's timed pass
+    (start-up, file I/O and warm-up excluded)."""
+    import json
+    import subprocess
+    import tempfile
+    x = _c64(frames)
+    B = x.shape[0]
+    nprocs = max(1, min(int(nprocs), B))
+    root_dir = os.path.dirname(_HERE)
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=shm) as td:
+        fpath, prefix = os.path.join(td, "frames.npy"), os.path.join(td, "out")
+        np.save(fpath, x)
+        env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", PYTHONPATH=root_dir + os.pathsep + os.environ.get("PYTHONPATH", ""),
+                   CUDA_VISIBLE_DEVICES="")
+        procs = [subprocess.Popen([sys.executable, "-m", "oracle.ref_worker", fpath, prefix, str(w), str(nprocs), str(int(avg_method)),
+                                   repr(float(norm_spacing)), str(num_targets), str(P), str(K)] + (["root"] if root else []),
+                                  cwd=root_dir, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for w in range(nprocs)]
+        stats = []
+        for p in procs:
+            so, se = p.communicate()
+            if p.returncode != 0:
+                raise RuntimeError(f"ref_worker failed: {se[-400:]}")
+            stats.append(json.loads([l for l in so.splitlines() if l.startswith("{")][-1]))
+        parts = [np.load(f"{prefix}.{w}.npy") for w in range(nprocs) if stats[w]["frames"] > 0]
+    out = np.concatenate(parts, axis=0)
+    seconds = max(s["seconds"] for s in stats)
+    if root:
+        return (out,), seconds
+    return (out[:, :K].copy(), out[:, K:].copy()), seconds

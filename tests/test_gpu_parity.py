@@ -256,18 +256,14 @@ def test_large_array_covariance_tensor_core(doa, oracle, torch_cuda, N, overlap,
     """M = 64: the tcgen05 3xTF32 HERK (herk_tc.cu) and the CUDA-core tiled kernel both meet the covariance tolerance and
     agree with one another; an odd snapshot size is outside the tensor-core kernel's 16-byte pieces and takes the CUDA-core
     kernel on both settings (whose time slices meet in shared-memory atomics: reproducible to rounding, not bit for bit).  Long snapshots are the case that exposes a truncating accumulator (error grows with N)."""
-    from gr_doa_b200 import synth, _lib
-    L = _lib.lib()
+    from gr_doa_b200 import synth
     x = synth.stream_numpy(B, 64, N, overlap, [40.0, 75.0, 120.0], seed=N + B)
     exp = oracle.autocorrelate(x, N, overlap, avg, nthreads=oracle.max_threads())
     ac = doa.autocorrelate(64, N, overlap, avg, max_frames=B)
     got = {}
-    try:
-        for tc in (0, 1):
-            L.doa_cuda_dev_set(b"herk_tc", tc)
-            got[tc] = ac.work(x)
-    finally:
-        L.doa_cuda_dev_set(b"herk_tc", 1)
+    for tc in (0, 1):
+        ac.set_option("herk_tc", tc)
+        got[tc] = ac.work(x)
     for tc in (0, 1):
         assert got[tc].shape == exp.shape
         assert parity.rel_fro(got[tc], exp) <= 2e-6 <= parity.COV_REL_FRO, (tc, parity.rel_fro(got[tc], exp))
@@ -345,17 +341,13 @@ def test_large_array_scan_cta_per_frame_equals_warp_per_frame(doa, torch_cuda, B
     """Generic-M scan with few frames: the CTA-per-frame kernel (coarse spectrum evaluated by all warps into shared memory,
     then the unchanged walker) returns the same bits as the warp-per-frame kernel.  M = 64 with even N so that the covariance
     in front of it is the deterministic tensor-core kernel."""
-    from gr_doa_b200 import synth, _lib
-    L = _lib.lib()
+    from gr_doa_b200 import synth
     x, _ = synth.frames_torch(B, 64, N, [30.0 + 120.0 * i / max(1, T - 1) for i in range(T)], jitter_deg=2.0, device="cuda", chunk=16)
     ch = doa.DoaChain(64, N, 0, 0, 0.5, T, P, K, max_frames=B)
     got = {}
-    try:
-        for wide in (0, 1):
-            L.doa_cuda_dev_set(b"scan_wide", wide)
-            got[wide] = [t.clone() for t in ch.run_device(x)]
-    finally:
-        L.doa_cuda_dev_set(b"scan_wide", 1)
+    for wide in (0, 1):
+        ch.set_option("scan_wide", wide)
+        got[wide] = [t.clone() for t in ch.run_device(x)]
     assert all(torch_cuda.equal(a.view(torch_cuda.int32), b.view(torch_cuda.int32)) for a, b in zip(got[0], got[1]))
 
 
@@ -363,23 +355,20 @@ def test_large_array_scan_cta_per_frame_equals_warp_per_frame(doa, torch_cuda, B
 def test_fused_chain_equals_three_kernels_other_shapes(doa, torch_cuda, M, T, P, K, avg):
     """The fused warp-specialised kernel also covers 4-element arrays and K = 1 (index_max: global arg-max): same bits as the
     three stage kernels at sizes around the tile boundaries."""
-    from gr_doa_b200 import synth, _lib
-    L = _lib.lib()
+    from gr_doa_b200 import synth
     N = 512
     thetas = [60.0] if T == 1 else list(np.linspace(50.0, 130.0, T))
     x, _ = synth.frames_torch(5000, M, N, thetas, jitter_deg=2.0, device="cuda", chunk=1024)
     ch = doa.DoaChain(M, N, 0, avg, 0.5, T, P, K, max_frames=5000)
-    try:
-        for nb in (1, 63, 64, 65, 1000, 5000):
-            L.doa_cuda_dev_set(b"fused", 0)
-            a = [t.clone() for t in ch.run_device(x[:nb])]
-            assert ch.launches() == 3
-            L.doa_cuda_dev_set(b"fused", 1)
-            b = ch.run_device(x[:nb])
-            assert ch.launches() == 1
-            assert all(torch_cuda.equal(p, q) for p, q in zip(a, b)), nb
-    finally:
-        L.doa_cuda_dev_set(b"fused", 1)
+    ch.set_option("scan_tc", 0)      # the Horner scan: the stage kernels then run the fused kernel's own device code
+    for nb in (1, 63, 64, 65, 1000, 5000):
+        ch.set_option("fused", 0)
+        a = [t.clone() for t in ch.run_device(x[:nb])]
+        assert ch.launches() == 3
+        ch.set_option("fused", 1)
+        b = ch.run_device(x[:nb])
+        assert ch.launches() == 1
+        assert all(torch_cuda.equal(p, q) for p, q in zip(a, b)), nb
 
 
 @pytest.mark.parametrize("M,T,snr", [(8, 3, 10.0), (4, 2, 10.0), (8, 7, 20.0), (16, 5, 10.0), (2, 1, 10.0)])
@@ -387,20 +376,16 @@ def test_rootmusic_aberth_path_agrees_with_the_qr_path(doa, oracle, torch_cuda, 
     """Root-MUSIC roots from the Aberth-Ehrlich iteration (registers / shared memory) and from the Hessenberg QR (global
     scratch, also the fallback of frames the iteration gives up on) select the same angles, and both meet the tolerance
     against the float64 LAPACK twin away from the unit circle."""
-    from gr_doa_b200 import synth, _lib
-    L = _lib.lib()
+    from gr_doa_b200 import synth
     B = 3000
     thetas = [75.0] if T == 1 else list(np.linspace(30.0, 150.0, T))
     fr, _ = synth.frames_numpy(B, M, 256, thetas, snr_db=snr, seed=31 * M + T)
     R = oracle.autocorrelate_frames(fr, 0, nthreads=oracle.max_threads())
     rm = doa.rootMUSIC_linear_array(0.5, T, M, max_frames=B)
     got = {}
-    try:
-        for ab in (0, 1):
-            L.doa_cuda_dev_set(b"root_aberth", ab)
-            got[ab] = rm.work(R)
-    finally:
-        L.doa_cuda_dev_set(b"root_aberth", 1)
+    for ab in (0, 1):
+        rm.set_option("root_aberth", ab)
+        got[ab] = rm.work(R)
     a64, d64 = oracle.rootmusic_f64(R, 0.5, T, M, return_dist=True, nthreads=oracle.max_threads())
     for ab in (0, 1):
         worst, near_circle = parity.root_angles_ok(got[ab], a64, d64)
@@ -426,3 +411,39 @@ def test_page_locked_caller_buffers_change_nothing_but_speed(doa):
     assert L.doa_cuda_unpin_host_buffer(fr.ctypes.data) == 0
     assert L.doa_cuda_unpin_host_buffer(fr.ctypes.data) != 0
     assert all(np.array_equal(a, b) for a, b in zip(ch.run_host(fr), ref))
+
+
+@pytest.mark.parametrize("N,avg,nb", [(1024, 0, 1), (1024, 0, 7), (1024, 1, 8), (200, 0, 9), (1024, 0, 1184), (512, 1, 2500)])
+def test_fused16_equals_the_stage_kernels(doa, torch_cuda, N, avg, nb):
+    """16 elements: covariance + Jacobi in one persistent warp-specialised kernel (fused16.cu, an experiment kept in the dev build: slower than the stage
+    kernels) followed by the scan, against the three stage kernels: the stage kernels' own device code and operation order, hence the same bits -- at tile-boundary sizes
+    (8 frames per tile, 2 frames per CTA minimum) and with more frames than SMs."""
+    from gr_doa_b200 import synth
+    M, T, P, K = 16, 3, 1024, 3
+    x, _ = synth.frames_torch(nb, M, N, [40.0, 90.0, 140.0], jitter_deg=3.0, device="cuda", chunk=512, seed=77 + N)
+    ch = doa.DoaChain(M, N, 0, avg, 0.5, T, P, K, max_frames=nb)          # product: the stage kernels (+ tensor-core scan)
+    a = [t.clone() for t in ch.run_device(x)]
+    assert ch.launches() == 3
+    with doa.dev_library():                                             # the experiment lives in the -DDOA_DEV_KNOBS build
+        dch = doa.DoaChain(M, N, 0, avg, 0.5, T, P, K, max_frames=nb)
+    dch.set_option("fused16", 1)
+    b = dch.run_device(x)
+    assert dch.launches() == 2
+    assert all(torch_cuda.equal(p, q) for p, q in zip(a, b))
+
+
+def test_streams_call_up_to_max_frames_beyond_the_host_chunk_size(doa):
+    """doa_cuda_chain_run_streams stages the whole [M][L] span on lane 0: a handle whose max_frames frames exceed the 256 MiB
+    host-chunk size must still take nframes <= max_frames (it used to answer ECAPACITY above ~4096 frames at M = 4, N = 2048)."""
+    from gr_doa_b200 import synth
+    M, N, T, P, K, n = 4, 2048, 1, 512, 1, 6000
+    x = synth.stream_numpy(n, M, N, 0, [60.0], seed=9)
+    ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=8192)
+    val, loc, bins = ch.run_streams([x[k] for k in range(M)], n)
+    v2, l2, b2 = ch.run_host(x.reshape(M, n, N).transpose(1, 0, 2).copy())
+    assert np.array_equal(bins, b2) and np.array_equal(val, v2)
+    assert np.abs(loc - 60.0).max() < 1.0
+    with pytest.raises(ValueError):
+        ch.run_streams([x[k][:-5] for k in range(M)], n)          # short arrays are refused before the library reads them
+    with pytest.raises(ValueError):
+        ch.run_streams([x[k] for k in range(M - 1)], n)

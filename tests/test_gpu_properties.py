@@ -78,46 +78,77 @@ def test_oracle_spot_check_on_the_resident_buffer(full, oracle):
 
 def test_fused_kernel_equals_three_kernel_path(full):
     """The warp-specialised fused kernel runs the stage kernels own device code with R, G, u in shared memory: bit-identical."""
-    from gr_doa_b200 import _lib
     torch = full["torch"]
-    L = _lib.lib()
+    ch = full["ch"]
     try:
+        ch.set_option("scan_tc", 0)      # the Horner scan: the stage kernels then run the fused kernel's own device code
         for nb in (1, 31, 47, 48, 49, 97, 4097, 20000):
-            L.doa_cuda_dev_set(b"fused", 0)
-            a = [t.clone() for t in full["ch"].run_device(full["x"][:nb])]
-            assert full["ch"].launches() == 3
-            L.doa_cuda_dev_set(b"fused", 1)
-            b = full["ch"].run_device(full["x"][:nb])
-            assert full["ch"].launches() == 1
+            ch.set_option("fused", 0)
+            a = [t.clone() for t in ch.run_device(full["x"][:nb])]
+            assert ch.launches() == 3
+            ch.set_option("fused", 1)
+            b = ch.run_device(full["x"][:nb])
+            assert ch.launches() == 1
             assert all(torch.equal(p, q) for p, q in zip(a, b))
     finally:
-        L.doa_cuda_dev_set(b"fused", 1)
+        ch.set_option("fused", 1)
+        ch.set_option("scan_tc", 1)
+
+
+def test_tensor_core_scan_agrees_with_the_horner_scan(full):
+    """The three-kernel chain with the scan on the tensor cores (scan_tc.cu: 3xTF32 contraction, stateless peak detection out of
+    TMEM) against the same chain with the Horner scan: both only LOCATE the minima, the reported bins and heights come from the
+    same refinement with the reference arithmetic, so the outputs are identical (a coarse candidate could differ only where two
+    minima are closer than the coarse arithmetic's noise)."""
+    torch = full["torch"]
+    ch = full["ch"]
+    x = full["x"][:32768]
+    try:
+        ch.set_option("fused", 0)
+        ch.set_option("scan_tc", 0)
+        a = [t.clone() for t in ch.run_device(x)]
+        ch.set_option("scan_tc", 1)
+        b = ch.run_device(x)
+        assert ch.launches() == 3
+        same = (a[2] == b[2]).all(dim=1)
+        assert float(same.float().mean()) >= 0.9995
+        assert torch.equal(a[0][same], b[0][same]) and torch.equal(a[1][same], b[1][same])
+    finally:
+        ch.set_option("fused", 1)
 
 
 def test_fused_kernel_configurations_are_bit_identical(full):
     """Producer/consumer split, cp.async ring depth, tile-buffer count, register re-allocation (setmaxnreg), bulk (TMA) instead of
     per-lane ring fills and the SMs left to NCCL only change the schedule: every configuration returns the same bits, at tile-boundary sizes and at full size."""
-    from gr_doa_b200 import _lib
+    import gr_doa_b200 as doa
     torch = full["torch"]
-    L = _lib.lib()
+    # the shipped configuration (product library) is the reference; the variants only exist in the -DDOA_DEV_KNOBS build
+    with doa.dev_library():
+        dch = doa.DoaChain(8, N, 0, 0, 0.5, T, P, K, max_frames=B)
 
     def select(split, stages, nbuf, reserve=0, tma=0, fill=0):
-        L.doa_cuda_dev_set(b"ws_tma", tma)
-        L.doa_cuda_dev_set(b"ws_fill", fill)       # 2: channel-major ring fills (one address + immediates per lane)
-        L.doa_cuda_dev_set(b"ws_split", split); L.doa_cuda_dev_set(b"ws_stages", stages); L.doa_cuda_dev_set(b"ws_nbuf", nbuf)
-        L.doa_cuda_dev_set(b"chain_sms_reserve", reserve)
+        dch.set_option("ws_tma", tma)
+        dch.set_option("ws_fill", fill)       # 2: channel-major ring fills (one address + immediates per lane)
+        dch.set_option("ws_split", split); dch.set_option("ws_stages", stages); dch.set_option("ws_nbuf", nbuf)
+        dch.set_option("sms_reserve", reserve)
 
     try:
         for nb in (33, 129, 5000, B):
             x = full["x"][:nb]
-            select(808, 2, 4)
             ref = [t.clone() for t in full["ch"].run_device(x)]
             assert full["ch"].launches() == 1
-            for cfg in ((412, 3, 2), (412, 5, 2), (416, 4, 2), (610, 3, 2), (812, 3, 2), (808, 3, 2), (808, 3, 3), (808, 2, 5), (808, 2, 4, 2),
-                        (808, 2, 4, 147), (808, 2, 4, 0, 1), (808, 2, 4, 0, 0, 2)):
+            for cfg in ((808, 2, 4), (412, 3, 2), (412, 5, 2), (416, 4, 2), (610, 3, 2), (812, 3, 2), (808, 3, 2), (808, 3, 3), (808, 2, 5), (808, 2, 4, 2),
+                        (808, 2, 4, 64), (808, 2, 4, 0, 1), (808, 2, 4, 0, 0, 2)):
                 select(*cfg)
-                got = full["ch"].run_device(x)
-                assert full["ch"].launches() == 1, cfg
+                got = dch.run_device(x)
+                assert dch.launches() == 1, cfg
                 assert all(torch.equal(p, q) for p, q in zip(ref, got)), (nb, cfg)
+        # the product library refuses options that select kernels it does not contain
+        with pytest.raises(Exception):
+            full["ch"].set_option("ws_split", 412)
+        full["ch"].set_option("sms_reserve", 2)
+        got = full["ch"].run_device(full["x"][:5000])
+        full["ch"].set_option("sms_reserve", 0)
+        assert all(torch.equal(p, q) for p, q in zip(full["ch"].run_device(full["x"][:5000]), got))
     finally:
-        select(808, 2, 4, 0)
+        dch.close()

@@ -60,7 +60,7 @@ def test_sc16_covariance_equals_fc32_on_converted_samples(M, N, overlap, avg):
     q[-1, -1] = (32767, -32768)
     ac = doa.autocorrelate(M, N, overlap, avg, max_frames=16)
     if M == 64:
-        doa._lib.lib().doa_cuda_dev_set(b"herk_tc", 0)   # the tensor-core HERK is an fc32-only path with its own rounding
+        ac.set_option("herk_tc", 0)   # the tensor-core HERK is an fc32-only path with its own rounding
     try:
         ref = ac.work(to_fc32(q, S15))
         ac.set_input_format("sc16", S15)
@@ -79,7 +79,7 @@ def test_sc16_covariance_equals_fc32_on_converted_samples(M, N, overlap, avg):
         assert parity.rel_fro(got2, oracle.autocorrelate(to_fc32(q, s), N, overlap, avg)) <= parity.COV_REL_FRO
         assert np.array_equal(ac.work(to_fc32(q, S15)), ref)                                    # and fc32 is back
     finally:
-        doa._lib.lib().doa_cuda_dev_set(b"herk_tc", 1)
+        ac.close()
 
 
 @pytest.mark.gpu
@@ -179,22 +179,20 @@ def test_channel_major_ring_fills_change_nothing(M, T, P, K, N):
     import torch
     import gr_doa_b200 as doa
     from gr_doa_b200 import synth
-    L = doa._lib.lib()
     B = 900
     fr, _ = synth.frames_numpy(B, M, N, list(np.linspace(50.0, 130.0, T)), snr_db=10.0, seed=M + N)
     q = quantise(fr)
-    ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
-    try:
-        for fmt, x in (("fc32", torch.from_numpy(to_fc32(q, S15)).cuda()), ("sc16", torch.from_numpy(q).cuda())):
-            ch.set_input_format(fmt, S15)
-            L.doa_cuda_dev_set(b"ws_fill", 0)
-            ref = [t.clone() for t in ch.run_device(x)]
-            L.doa_cuda_dev_set(b"ws_fill", 2)
-            got = ch.run_device(x)
-            assert ch.launches() == 1
-            assert all(torch.equal(a, b) for a, b in zip(got, ref)), fmt
-    finally:
-        L.doa_cuda_dev_set(b"ws_fill", 0)
+    ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)          # the shipped configuration
+    with doa.dev_library():                                          # the variant lives in the -DDOA_DEV_KNOBS build
+        dch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
+    dch.set_option("ws_fill", 2)
+    for fmt, x in (("fc32", torch.from_numpy(to_fc32(q, S15)).cuda()), ("sc16", torch.from_numpy(q).cuda())):
+        ch.set_input_format(fmt, S15)
+        dch.set_input_format(fmt, S15)
+        ref = [t.clone() for t in ch.run_device(x)]
+        got = dch.run_device(x)
+        assert dch.launches() == 1
+        assert all(torch.equal(a, b) for a, b in zip(got, ref)), fmt
 
 
 # ---- committed golden fixtures (tests/golden/sc16_*.npz, written by tests/golden/make_golden.py) -----------------------

@@ -9,7 +9,7 @@ for (B, N, avg) in ((7, 66, 1), (65536, 1024, 0), (1000, 2048, 1)):
     ac = doa.autocorrelate(16, N, 0, avg, max_frames=B)
     res = {}
     for ring in (0, 1):
-        L.doa_cuda_dev_set(b"cov16_ring", ring)
+        doa.set_default_option("cov16_ring", ring)
         for _ in range(2): R = ac.work_device(x)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -49,7 +49,7 @@ def timing(B=65536, M=8, N=2048, T=3, P=4096, K=3):
     ch.set_profiling(True)
     L = _lib.lib()
     for variant in (2, 1):
-        L.doa_cuda_dev_set(b"cov_groups", variant)
+        doa.set_default_option("cov_groups", variant)
         for it in range(4):
             torch.cuda.synchronize(); t = time.time()
             out = ch.run_device(x); torch.cuda.synchronize(); dt = time.time() - t

@@ -11,14 +11,14 @@ for (B, N, avg) in ((2, 64, 0), (3, 4096, 1), (5, 1000, 0), (300, 2048, 0), (3, 
     R_o = O.autocorrelate_frames(fr, avg, nthreads=8)
     x = torch.from_numpy(fr).cuda()
     ac = doa.autocorrelate(64, N, 0, avg, max_frames=B)
-    L.doa_cuda_dev_set(b"herk_tc", 0); R0 = ac.work_device(x).cpu().numpy()
-    L.doa_cuda_dev_set(b"herk_tc", 1); R1 = ac.work_device(x).cpu().numpy()
+    doa.set_default_option("herk_tc", 0); R0 = ac.work_device(x).cpu().numpy()
+    doa.set_default_option("herk_tc", 1); R1 = ac.work_device(x).cpu().numpy()
     print(f"B={B} N={N} avg={avg}: CUDA-core relfro {relfro(R0, R_o):.2e}  tensor-core relfro {relfro(R1, R_o):.2e}  max|diff| {np.abs(R1-R_o).max():.2e}", flush=True)
 B, N = 592, 16384
 x, _ = synth.frames_torch(B, 64, N, [30.0 + 120.0 * i / 7 for i in range(8)], jitter_deg=2.0, device="cuda", chunk=32)
 ac = doa.autocorrelate(64, N, 0, 0, max_frames=B)
 for tc in (0, 1):
-    L.doa_cuda_dev_set(b"herk_tc", tc)
+    doa.set_default_option("herk_tc", tc)
     for _ in range(2): R = ac.work_device(x)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

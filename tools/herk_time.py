@@ -7,7 +7,7 @@ L = _lib.lib()
 B, N = int(os.environ.get("HB", 592)), int(os.environ.get("HN", 16384))
 x, _ = synth.frames_torch(B, 64, N, [30.0 + 120.0 * i / 7 for i in range(8)], jitter_deg=2.0, device="cuda", chunk=32)
 ac = doa.autocorrelate(64, N, 0, 0, max_frames=B)
-L.doa_cuda_dev_set(b"herk_tc", 1)
+doa.set_default_option("herk_tc", 1)
 for _ in range(2): R = ac.work_device(x)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -13,7 +13,7 @@ ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
 if len(sys.argv) > 3 and sys.argv[3] == "sc16":
     x = torch.view_as_real(x).mul(8192.0).round_().clamp_(-32768, 32767).to(torch.int16)
     ch.set_input_format("sc16", 1.0 / 32768)
-_lib.lib().doa_cuda_dev_set(b"fused", fused)
+doa.set_default_option("fused", fused)
 for it in range(4):
     out = ch.run_device(x)
 torch.cuda.synchronize()

@@ -12,7 +12,7 @@ for (B, M, N, T, th, snr) in ((65536, 8, 2048, 3, [40.0, 90.0, 140.0], 10.0), (2
     rm = doa.rootMUSIC_linear_array(0.5, T, M, max_frames=B)
     res = {}
     for ab in (0, 1):
-        L.doa_cuda_dev_set(b"root_aberth", ab)
+        doa.set_default_option("root_aberth", ab)
         for _ in range(2): out = rm.work_device(R)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -25,4 +25,4 @@ for (B, M, N, T, th, snr) in ((65536, 8, 2048, 3, [40.0, 90.0, 140.0], 10.0), (2
     d = (a - b).abs()[both]
     print(f"M={M} T={T} snr={snr} B={B}: QR {res[0][1]:.3f} ms, Aberth(+QR fallback) {res[1][1]:.3f} ms; max |angle diff| {d.max().item():.2e} deg, "
           f"frames > 1e-4 deg: {int((d.view(-1) > 1e-4).sum())}, NaN pattern equal: {bool((torch.isfinite(a) == torch.isfinite(b)).all())}", flush=True)
-L.doa_cuda_dev_set(b"root_aberth", 1)
+doa.set_default_option("root_aberth", 1)

@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from gr_doa_b200 import synth, _lib
 import gr_doa_b200 as doa
+doa.dev_library().__enter__()   # the -DDOA_DEV_KNOBS build (python -m gr_doa_b200.build --dev): experimental kernel variants
 L = _lib.lib()
 def chain(B, M, N, T, P, K, avg=0):
     x, _ = synth.frames_torch(B, M, N, list(np.linspace(40.0, 140.0, T)) if T > 1 else [70.0], jitter_deg=2.0, device="cuda", chunk=64)
@@ -22,9 +23,9 @@ chain(37, 16, 192, 3, 512, 3)              # cov16 ring + group Jacobi 16
 chain(5, 64, 1056, 4, 1024, 5)             # tcgen05 HERK + block Jacobi + wide scan
 chain(9, 12, 100, 2, 300, 2)               # generic tiled covariance
 for cfg in ((412, 3, 2), (416, 4, 2), (812, 3, 2), (808, 3, 3)):
-    L.doa_cuda_dev_set(b"ws_split", cfg[0]); L.doa_cuda_dev_set(b"ws_stages", cfg[1]); L.doa_cuda_dev_set(b"ws_nbuf", cfg[2])
+    doa.set_default_option("ws_split", cfg[0]); doa.set_default_option("ws_stages", cfg[1]); doa.set_default_option("ws_nbuf", cfg[2])
     chain(70, 8, 256, 3, 1024, 3)
-L.doa_cuda_dev_set(b"ws_split", 808); L.doa_cuda_dev_set(b"ws_stages", 2); L.doa_cuda_dev_set(b"ws_nbuf", 4)
-L.doa_cuda_dev_set(b"ws_tma", 1); chain(70, 8, 256, 3, 1024, 3); L.doa_cuda_dev_set(b"ws_tma", 0)
-L.doa_cuda_dev_set(b"root_aberth", 0); chain(20, 8, 128, 3, 256, 3); L.doa_cuda_dev_set(b"root_aberth", 1)
+doa.set_default_option("ws_split", 808); doa.set_default_option("ws_stages", 2); doa.set_default_option("ws_nbuf", 4)
+doa.set_default_option("ws_tma", 1); chain(70, 8, 256, 3, 1024, 3); doa.set_default_option("ws_tma", 0)
+doa.set_default_option("root_aberth", 0); chain(20, 8, 128, 3, 256, 3); doa.set_default_option("root_aberth", 1)
 print("sanitize_small: done")

@@ -9,6 +9,7 @@ import torch
 from oracle import oracle as O
 from gr_doa_b200 import synth, _lib
 import gr_doa_b200 as doa
+doa.dev_library().__enter__()   # the -DDOA_DEV_KNOBS build (python -m gr_doa_b200.build --dev): experimental kernel variants
 
 L = _lib.lib()
 SHAPES = {
@@ -25,13 +26,13 @@ def parity(name, c, B=2048):
     fr, _ = synth.frames_numpy(B, M, N, c["th"], jitter_deg=5.0, snr_db=10.0, seed=synth.SEED_BASE + M)
     x = torch.from_numpy(fr).cuda()
     ch = doa.DoaChain(M, N, 0, c["avg"], 0.5, T, P, K, max_frames=B)
-    L.doa_cuda_dev_set(b"fused", 0)
+    doa.set_default_option("fused", 0)
     out = {}
     for tc in (0, 1):
-        L.doa_cuda_dev_set(b"scan_tc", tc)
+        doa.set_default_option("scan_tc", tc)
         v, l, b = [t.cpu().numpy() for t in ch.run_device(x)]
         out[tc] = (v, l, b, ch.launches())
-    L.doa_cuda_dev_set(b"fused", 1)
+    doa.set_default_option("fused", 1)
     vo, lo, bo = O.chain_frames(fr, c["avg"], 0.5, T, P, K, nthreads=O.max_threads())
     res = {"shape": name, "frames": B, "launches": [out[0][3], out[1][3]]}
     for tc in (0, 1):
@@ -49,11 +50,11 @@ def timing(name, c, B=65536):
     M, N, T, P, K = c["M"], c["N"], c["T"], c["P"], c["K"]
     x, _ = synth.frames_torch(B, M, N, c["th"], jitter_deg=5.0, device="cuda", chunk=max(1, 2**28 // (M * N * 8)))
     ch = doa.DoaChain(M, N, 0, c["avg"], 0.5, T, P, K, max_frames=B)
-    L.doa_cuda_dev_set(b"fused", 0)
+    doa.set_default_option("fused", 0)
     res = {"shape": name, "frames": B}
     for tc in (0, 1, 2, 3):   # 0: Horner scan, 1: tensor-core scan, 2: its scan phase alone, 3: long flats not redone (wrong on those frames)
-        L.doa_cuda_dev_set(b"scan_tc", min(tc, 1))
-        L.doa_cuda_dev_set(b"scan_tc_dbg", {0: 0, 1: 0, 2: 1, 3: 2}[tc])
+        doa.set_default_option("scan_tc", min(tc, 1))
+        doa.set_default_option("scan_tc_dbg", {0: 0, 1: 0, 2: 1, 3: 2}[tc])
         for _ in range(3): ch.run_device(x)
         torch.cuda.synchronize()
         ch.set_profiling(True)
@@ -61,8 +62,8 @@ def timing(name, c, B=65536):
         torch.cuda.synchronize()
         res[f"tc{tc}_stages_ms"] = [round(v, 4) for v in ch.stage_ms()]
         ch.set_profiling(False)
-    L.doa_cuda_dev_set(b"fused", 1)
-    L.doa_cuda_dev_set(b"scan_tc_dbg", 0)
+    doa.set_default_option("fused", 1)
+    doa.set_default_option("scan_tc_dbg", 0)
     print(json.dumps(res), flush=True)
 
 

@@ -10,7 +10,7 @@ for (B, M, N, T, P, K) in ((256, 64, 16384, 8, 16384, 8), (300, 64, 128, 4, 1024
     ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
     res = {}
     for wide in (0, 1):
-        L.doa_cuda_dev_set(b"scan_wide", wide)
+        doa.set_default_option("scan_wide", wide)
         for _ in range(2): out = ch.run_device(x)
         ch.set_profiling(True)
         for _ in range(5): out = ch.run_device(x)
@@ -19,4 +19,4 @@ for (B, M, N, T, P, K) in ((256, 64, 16384, 8, 16384, 8), (300, 64, 128, 4, 1024
         ch.set_profiling(False)
     same = all(torch.equal(a.view(torch.int32), b.view(torch.int32)) for a, b in zip(res[0][0], res[1][0]))
     print(f"B={B} M={M} P={P} K={K}: stages (cov, eig, scan) warp-per-frame {[round(v,3) for v in res[0][1]]} ms, CTA-per-frame {[round(v,3) for v in res[1][1]]} ms, bit-identical {same}", flush=True)
-L.doa_cuda_dev_set(b"scan_wide", 1)
+doa.set_default_option("scan_wide", 1)

@@ -20,7 +20,7 @@ for name, c in CFG.items():
     ch = doa.DoaChain(M, N, 0, c.get("avg", 0), 0.5, T, P, K, max_frames=B)
     res = {}
     for fused in (0, 1):
-        L.doa_cuda_dev_set(b"fused", fused)
+        doa.set_default_option("fused", fused)
         for _ in range(3): ch.run_device(x)
         torch.cuda.synchronize()
         if fused == 0:

@@ -5,16 +5,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gr_doa_b200 import synth, _lib
 import gr_doa_b200 as doa
+doa.dev_library().__enter__()   # the -DDOA_DEV_KNOBS build (python -m gr_doa_b200.build --dev): experimental kernel variants
 L = _lib.lib()
 B, M, N, T, P, K = 65536, 8, 2048, 3, 4096, 3
 x, _ = synth.frames_torch(B, M, N, [40.0, 90.0, 140.0], jitter_deg=2.0, device="cuda", chunk=2048)
 ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
 cfgs = sys.argv[1:] or ["80824"]            # a trailing 't' = bulk (TMA) ring fills instead of per-lane cp.async (80824 only); 'c' = channel-major fills
 def select(cs):
-    L.doa_cuda_dev_set(b"ws_tma", 1 if cs.endswith("t") else 0)
-    L.doa_cuda_dev_set(b"ws_fill", 2 if cs.endswith("c") else 0)
+    doa.set_default_option("ws_tma", 1 if cs.endswith("t") else 0)
+    doa.set_default_option("ws_fill", 2 if cs.endswith("c") else 0)
     c = int(cs.rstrip("tc"))
-    L.doa_cuda_dev_set(b"ws_split", c // 100); L.doa_cuda_dev_set(b"ws_stages", (c // 10) % 10); L.doa_cuda_dev_set(b"ws_nbuf", c % 10)
+    doa.set_default_option("ws_split", c // 100); doa.set_default_option("ws_stages", (c // 10) % 10); doa.set_default_option("ws_nbuf", c % 10)
 ref, same, times, launches = None, {}, {c: [] for c in cfgs}, {}
 for c in cfgs:
     select(c)
