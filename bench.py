@@ -262,7 +262,8 @@ def main():
     # measured (B200 x8 box): the serial gather costs 0.03 ms per step at 2 GPUs, 0.24 ms at 8; pipelined with 2 SMs left to
     # NCCL: 8 GPUs 1.87-1.95 -> 1.74 ms per step, 4 GPUs no change, 2 GPUs 2-3 % slower (the reserved SMs)
     pipelined = os.environ.get("DOA_PIPELINE", "1" if world > 4 else "0") != "0"
-    peaks = sharding.PeakExchange(B, K, dev, world=world, is_dst=(rank == 0), pipelined=pipelined)
+    gather_mode = os.environ.get("DOA_GATHER", "gather")        # "gather" (send/recv to rank 0) or "allgather" (all_gather_into_tensor)
+    peaks = sharding.PeakExchange(B, K, dev, world=world, is_dst=(rank == 0), pipelined=pipelined, mode=gather_mode)
     reserve = int(os.environ.get("DOA_SMS_RESERVE", "2")) if (world > 1 and pipelined) else 0
     chain.set_sms_reserve(reserve)
     out = peaks.bufs[0].outputs()
@@ -475,7 +476,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_text(w), "frames_per_gpu": B, "parallelism": f"frames sharded x{world}, one peak gather per step" + (" (double-buffered on a side stream, under the next step's kernel; 2 SMs left to NCCL)" if (world > 1 and pipelined) else ""),
+            "config": {"workload": workload_text(w), "frames_per_gpu": B, "peak_exchange": gather_mode if world > 1 else None, "parallelism": f"frames sharded x{world}, one peak gather per step" + (" (double-buffered on a side stream, under the next step's kernel; 2 SMs left to NCCL)" if (world > 1 and pipelined) else ""),
                        "l2": "inputs (8 GiB/GPU) larger than L2 (126 MB): no flush between iterations",
                        "timer": "CUDA events on the launching stream, max over ranks",
                        "regime": f"burst: {args.steps} steps = {ms:.0f} ms; see `sustained` for >= 2 s of back-to-back steps"},
@@ -616,7 +617,7 @@ def bench_cfg5(doa, synth, sharding, torch, dist, np, dev, local, rank, world, p
     call = min(Bl, 262144)                                     # frames per chain call: bounds the per-call intermediates (R, G, u)
     ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, device=local, max_frames=call)
     longest = -(-total // world)
-    pk = sharding.PeakExchange(longest, K, dev, world=world, is_dst=(rank == 0), pipelined=False)
+    pk = sharding.PeakExchange(longest, K, dev, world=world, is_dst=(rank == 0), pipelined=False, mode=os.environ.get("DOA_GATHER", "gather"))
 
     def step():
         val, loc, bins = pk.begin()

@@ -426,10 +426,11 @@ int doa_cuda_autocorrelate_run_device(doa_cuda_handle* h, const void* in_dev, lo
 // A GNU Radio scheduler hands work() pageable buffers and a handful of frames.  Copied straight out of pageable memory every
 // channel stream (and every output array) is its own driver-staged, blocking transfer; here the call's samples are first
 // gathered into the handle's page-locked buffer in the device layout, so that ONE asynchronous copy moves them, and the
-// outputs come back through the same buffer.  Large transfers (batch jobs; anything over PIN_STAGE_BYTES) keep the direct
-// route: a single host thread cannot memcpy faster than the driver's own pageable path.  Caller memory that already is
+// outputs come back through the same buffer.  Measured (tools/latency.py, B200 box): 81 -> 60 us for a one-frame call at the
+// cfg1 shape, even at 1 MB per call, and SLOWER beyond (387 against 326 us at 4 MB: a single host thread's memcpy is no match for
+// the driver's own pageable path), hence the 1 MiB limit; larger transfers keep the direct route.  Caller memory that already is
 // page-locked (cudaHostAlloc, doa_cuda_pin_host_buffer) is never staged.
-static const size_t PIN_STAGE_BYTES = 8u << 20;
+static const size_t PIN_STAGE_BYTES = 1u << 20;
 
 static bool is_pageable(const void* p) {
   cudaPointerAttributes a;
@@ -788,6 +789,22 @@ static int chain_on_lane(doa_cuda_handle* h, Lane& l, const void* in_dev, long l
   if (dev_option(OPT_FUSED, 1)) {
     // one persistent kernel for the whole chain when the shape allows it; stage events collapse to (0, 0, total)
     if (prof) { CK(h, cudaEventRecord(ev[1], st)); CK(h, cudaEventRecord(ev[2], st)); }
+#ifdef DOA_DEV_KNOBS
+    if (dev_option(OPT_FUSED, 1) == 2) {
+      // experiment: covariance + Jacobi in the persistent kernel (G, u to global memory), the scan on the tensor cores afterwards
+      int f2 = launch_chain_fused(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, h->T, tables_of(h), h->K, val, loc, bin, st,
+                                  h->d_gains, h->fmt, l.G, l.u);
+      if (f2 > 0) {
+        if (prof) { CK(h, cudaEventRecord(ev[1], st)); CK(h, cudaEventRecord(ev[2], st)); }
+        int c2 = launch_scan_peaks_tc(l.u, l.G, tables_of(h), nframes, h->K, val, loc, bin, st);
+        if (c2 <= 0) return fail(h, DOA_CUDA_EINVAL, "split form needs the tensor-core scan");
+        if (prof) CK(h, cudaEventRecord(ev[3], st));
+        h->launches += f2 + c2;
+        CK(h, cudaGetLastError());
+        return DOA_CUDA_OK;
+      }
+    }
+#endif
     int f = launch_chain_fused(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, h->T, tables_of(h), h->K, val,
                                loc, bin, st, h->d_gains, h->fmt);
     if (f < 0) return fail(h, f, "fused chain launch rejected");

@@ -65,7 +65,8 @@ void build_scan_tc_table(float norm_spacing, int M, int P, const std::vector<flo
 // then runs the three stage kernels), <0 on error.  Bit-identical to the three-kernel path.
 int launch_chain_fused(const void* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
                        int avg_method, int T, const ScanTables& tb, int K, float* out_val, float* out_loc, int* out_bin,
-                       cudaStream_t st, const float2* gains = nullptr, InputFormat fmt = InputFormat());
+                       cudaStream_t st, const float2* gains = nullptr, InputFormat fmt = InputFormat(),
+                       float2* G_out = nullptr, float2* u_out = nullptr);   // G_out / u_out non-null: split form, no scan (dev builds)
 
 // 16-element arrays: covariance + eigendecomposition in one persistent warp-specialised kernel (fused16.cu); G and u as from
 // launch_noise_subspace.  Returns 1 if launched, 0 if the shape is not covered.  Bit-identical to the two stage kernels and

@@ -66,7 +66,7 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
                 int avg_method, float scale, float bscale, int T, int max_sweeps, const float* __restrict__ zpair,
                 const float2* __restrict__ zplain, const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int P, int K,
                 float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin,
-                const float2* __restrict__ gains) {
+                const float2* __restrict__ gains, float2* __restrict__ G_out, float2* __restrict__ u_out) {
   static_assert(M == 8 || M == 4, "instantiated for 8 and 4 lanes per matrix");
   constexpr bool TMA = FILL == 1;
   static_assert(!TMA || sizeof(S) == 8, "bulk ring fills are an fc32 variant");
@@ -219,12 +219,19 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
       bar_sync(BAR_FULL + b, NTHREADS);
       {
         const int g = ct / M, j = ct % M;
-        jacobi_group_solve<M>(Rbuf + ((size_t)b * TILE + g) * MM, j, T, max_sweeps, g < nt, Gs + g * MM, us + g * M, nullptr);
+        if (G_out != nullptr) {
+          // split form: the noise projector and its diagonal sums go to global memory, the scan runs as its own kernel (scan_tc.cu)
+          const long long f = lo + (long long)t * TILE + min(g, nt - 1);
+          jacobi_group_solve<M>(Rbuf + ((size_t)b * TILE + g) * MM, j, T, max_sweeps, g < nt, G_out + f * MM, u_out + f * M, nullptr);
+        } else {
+          jacobi_group_solve<M>(Rbuf + ((size_t)b * TILE + g) * MM, j, T, max_sweeps, g < nt, Gs + g * MM, us + g * M, nullptr);
+        }
       }
       // A consumer warp owns its 32/M matrices end to end (Jacobi -> G/u -> scan), so nothing but the tile buffer is shared:
       // no consumer-wide barrier, a warp whose matrices converge early starts scanning early.
       __syncwarp();
       if (t + WS_NBUF < ntiles) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NTHREADS); }
+      if (G_out != nullptr) continue;
       for (int i = cw * (32 / M); i < min(nt, (cw + 1) * (32 / M)); ++i) {
         const long long f = lo + (long long)t * TILE + i;
         if (K == 1)   // index_max: the global arg-max (find_local_max_impl.h:53-56), not a local-peak search
@@ -241,7 +248,8 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
 
 template <int M, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF, int FILL, typename S>
 int launch_ws_cfg2(const S* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
-                  int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st, const float2* gains, float in_scale2) {
+                  int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st, const float2* gains, float in_scale2,
+                  float2* G_out = nullptr, float2* u_out = nullptr) {
   constexpr int TILE = WS_C * 32 / M;
   const size_t smem = ((ztab_floats(tb.P) + 3) & ~(size_t)3) * sizeof(float) + ((size_t)(WS_NBUF + 1) * TILE * M * M + (size_t)TILE * M) * sizeof(float2) +
                       (size_t)WS_P * M * M * sizeof(float) + (size_t)WS_P * WS_STAGES * M * 32 * sizeof(typename RingSlot<S>::type);
@@ -259,13 +267,14 @@ int launch_ws_cfg2(const S* in, long long fs, long long cs, int N, int nframes, 
   const int grid = std::max(1, std::min(sms, (nframes + GRP - 1) / GRP));
   const float scale = (float)(1.0 / N) * in_scale2, bscale = (float)(0.5 / N);   // in_scale2: sc16 converter scale squared (cov.cu)
   kern<<<grid, (WS_P + WS_C) * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.z, tb.V, tb.xaxis, tb.P,
-                                               K, out_val, out_loc, out_bin, gains);
+                                               K, out_val, out_loc, out_bin, gains, G_out, u_out);
   return 1;
 }
 
 template <int M, int WS_P, int WS_C, int WS_STAGES, int WS_NBUF = 3>
 int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nframes, int avg, int T, const ScanTables& tb,
-                  int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st, const float2* gains) {
+                  int K, float* out_val, float* out_loc, int* out_bin, cudaStream_t st, const float2* gains,
+                  float2* G_out = nullptr, float2* u_out = nullptr) {
   const float in_scale2 = 1.0f;
   // Bulk (TMA) ring fills, measured at cfg3: 1.99 ms against 1.67 ms with per-lane cp.async -- a 512-byte copy per channel and
   // chunk is too small for the bulk-copy engine (16.8 M copies per launch) and larger ones do not fit per-warp rings.  Kept
@@ -281,7 +290,7 @@ int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nfram
       return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 2>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
   }
 #endif
-  return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 0>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
+  return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 0>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2, G_out, u_out);
 }
 
 }  // namespace
@@ -291,7 +300,7 @@ int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nfram
 // SM's shared memory (P <= ~6000).  M = 4 (cfg1 / cfg2 shapes): 3.15 / 3.33 ms unfused -> 2.47 / 2.40 ms, ~7 TB/s of input.
 int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_stride, int M, int N, int nframes,
                        int avg_method, int T, const ScanTables& tb, int K, float* out_val, float* out_loc, int* out_bin,
-                       cudaStream_t st, const float2* gains, InputFormat fmt) {
+                       cudaStream_t st, const float2* gains, InputFormat fmt, float2* G_out, float2* u_out) {
   if (nframes <= 0 || (M != 8 && M != 4)) return 0;
   if (K < 1 || K > 4) return 0;                       // K > 4: the wide candidate lists
   const bool vec2 = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
@@ -319,7 +328,7 @@ int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_
   // barrier 41 % of the time while each producer warp, alone on its scheduler, issues at 0.25 IPC.  At 8+8 the tile barriers
   // still hold 12 % of the warp samples, but that is slack, not lost throughput: a variant with pairwise hand-off (producer w
   // feeds consumer w through a private ring of 4-frame slots and mbarriers, no CTA-wide barrier) measured the same 1.67 ms.
-#define WS_ARGS in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains
+#define WS_ARGS in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, G_out, u_out
   if (M == 4) {   // covariance-dominated (80 % of the step): the consumers only have to hide 0.1 + 0.7 ms under 2.6 ms of streaming
 #ifndef DOA_DEV_KNOBS
     return launch_ws_cfg<4, 8, 8, 6, 4>(WS_ARGS);
@@ -341,6 +350,14 @@ int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_
   return launch_ws_cfg<8, 8, 8, 2, 4>(WS_ARGS);
 #else
   // -DDOA_DEV_KNOBS (tools/ws_exp.py): ws_split = producers * 100 + consumers, ws_stages = cp.async ring depth, ws_nbuf = tile buffers
+  if (G_out != nullptr) {   // split form (covariance + Jacobi here, scan as its own kernel): the consumers have less to do
+    switch (dev_option(OPT_WS_SPLIT, 808)) {
+      case 1204: return launch_ws_cfg<8, 12, 4, 2, 4>(WS_ARGS);
+      case 1006: return launch_ws_cfg<8, 10, 6, 2, 4>(WS_ARGS);
+      case 1204 + 1: return launch_ws_cfg<8, 12, 4, 3, 4>(WS_ARGS);
+      default: return launch_ws_cfg<8, 8, 8, 2, 4>(WS_ARGS);
+    }
+  }
   switch ((dev_option(OPT_WS_SPLIT, 808) * 10 + dev_option(OPT_WS_STAGES, 2)) * 10 + dev_option(OPT_WS_NBUF, 4)) {
     case 41232: return launch_ws_cfg<8, 4, 12, 3, 2>(WS_ARGS);      // the first fused configuration (1.91 ms)
     case 41252: return launch_ws_cfg<8, 4, 12, 5, 2>(WS_ARGS);

@@ -305,7 +305,7 @@ __device__ __forceinline__ void scan_frame_argmax(const float2* __restrict__ uf,
     const float ov = __shfl_xor_sync(FULLM, bv, o); const int oi = __shfl_xor_sync(FULLM, bi, o);
     if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
   }
-  argmax_refine_emit(bi, Gf, Vtab, xaxis, M, P, lane, o_val, o_loc, o_bin);
+  argmax_refine_emit<MT, false>(bi, Gf, Vtab, xaxis, M, P, lane, o_val, o_loc, o_bin);
 }
 
 // Second half of the peak search, shared by the Horner scan below and the tensor-core scan (scan_tc.cu): from the merged
@@ -499,7 +499,8 @@ __device__ __forceinline__ void scan_frame_peaks(const float2* __restrict__ uf, 
     for (; k < s1 - s0; ++k) { const float q = q_at(s0 + k); w.step(prev, q, s0 + k, q_at); prev = q; }
   }
   Merged m = stitch_and_merge<KL, false>(w, K, lane, q_at);
-  peaks_refine_emit(m, q_at(0), q_at(P - 1), q_at, Gf, Vtab, xaxis, M, P, K, lane, o_val, o_loc, o_bin);
+  // compile-time M: steering rows in registers, unrolled row sums; ZS (fused kernel): the projector is in shared memory too
+  peaks_refine_emit<MT, ZS>(m, q_at(0), q_at(P - 1), q_at, Gf, Vtab, xaxis, M, P, K, lane, o_val, o_loc, o_bin);
 }
 
 }  // namespace

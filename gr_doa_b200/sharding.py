@@ -68,14 +68,18 @@ class PeakBuffers:
     the per-step exchange is a single collective on a preallocated buffer with no packing kernels around it:
     `val`, `loc`, `bins` are views the chain writes into; on the destination rank `gathered` is [world][3][n][K]."""
 
-    def __init__(self, n: int, K: int, device, world: int = 1, is_dst: bool = False):
-        self.n, self.K, self.world = n, K, world
+    def __init__(self, n: int, K: int, device, world: int = 1, is_dst: bool = False, mode: str = "gather"):
+        """mode "gather": dist.gather to dst (NCCL: grouped send/recv, only dst receives); "allgather":
+        dist.all_gather_into_tensor (one ring / NVLS collective, every rank receives world * 36 n bytes and all but dst drop them)."""
+        self.n, self.K, self.world, self.mode = n, K, world, mode
         self.buf = torch.empty((3, n, K), dtype=torch.int32, device=device)
         self.val = self.buf[0].view(torch.float32)
         self.loc = self.buf[1].view(torch.float32)
         self.bins = self.buf[2]
-        self.gathered = torch.empty((world, 3, n, K), dtype=torch.int32, device=device) if (is_dst and world > 1) else None
-        self._views = [self.gathered[r] for r in range(world)] if self.gathered is not None else None
+        need = world > 1 and (is_dst or mode == "allgather")
+        self.gathered = torch.empty((world, 3, n, K), dtype=torch.int32, device=device) if need else None
+        self._views = [self.gathered[r] for r in range(world)] if (self.gathered is not None and is_dst) else None
+        self.is_dst = is_dst
 
     def outputs(self):
         return self.val, self.loc, self.bins
@@ -84,6 +88,9 @@ class PeakBuffers:
         """Equal-size shards only (bench / streaming slabs); returns the [world][3][n][K] buffer on dst, None elsewhere."""
         if self.world == 1:
             return self.buf[None]
+        if self.mode == "allgather":
+            dist.all_gather_into_tensor(self.gathered.view(-1), self.buf.view(-1), group=group)
+            return self.gathered if self.is_dst else None
         dist.gather(self.buf, self._views, dst=dst, group=group)
         return self.gathered
 
@@ -103,8 +110,8 @@ class PeakExchange:
     synchronously."""
 
     def __init__(self, n: int, K: int, device, world: int = 1, is_dst: bool = False, depth: int = 2, dst: int = 0, group=None,
-                 pipelined: bool = True):
-        self.bufs = [PeakBuffers(n, K, device, world=world, is_dst=is_dst) for _ in range(depth)]
+                 pipelined: bool = True, mode: str = "gather"):
+        self.bufs = [PeakBuffers(n, K, device, world=world, is_dst=is_dst, mode=mode) for _ in range(depth)]
         self.world, self.dst, self.group, self.i = world, dst, group, 0
         self.cuda = torch.device(device).type == "cuda" and pipelined   # otherwise: the gather runs in stream order
         if self.cuda and world > 1:
@@ -149,7 +156,7 @@ class PeakExchange:
         pb = self.last
         if self.world == 1:
             return pb.outputs()
-        return PeakBuffers.split(pb.gathered) if pb.gathered is not None else None
+        return PeakBuffers.split(pb.gathered) if (pb.gathered is not None and pb.is_dst) else None
 
 
 def run_sharded(chain_fn, frames_local, nframes_total: int, dst: int = 0, group=None):

@@ -57,5 +57,8 @@ def test_rootchain_equals_the_two_blocks(oracle, M, T, N, overlap, avg):
     rc.set_input_format("sc16", S15)
     assert np.array_equal(rc.run_host(q), ref2)
     from gr_doa_b200._lib import DoaCudaError
+    longer = synth.stream_numpy(n + 1, M, N, overlap, thetas, seed=M + T)
     with pytest.raises(DoaCudaError):
-        rc.run_streams(list(quantise(x)), n + 1)                          # beyond max_frames
+        rc.run_streams(list(quantise(longer)), n + 1)                     # beyond max_frames
+    with pytest.raises(ValueError):
+        rc.run_streams(list(quantise(x)), n + 1)                          # arrays too short for n + 1 frames: refused before the library reads them

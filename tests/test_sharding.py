@@ -38,11 +38,11 @@ def test_pack_roundtrip_is_bit_exact():
     assert torch.equal(v, val) and torch.equal(l, loc) and torch.equal(b, bins)
 
 
-def _worker_packed(rank, world, port, q):
+def _worker_packed(rank, world, port, q, mode="gather"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     n, K = 6, 3
-    pb = sharding.PeakBuffers(n, K, "cpu", world=world, is_dst=(rank == 0))
+    pb = sharding.PeakBuffers(n, K, "cpu", world=world, is_dst=(rank == 0), mode=mode)
     g = torch.Generator().manual_seed(100 + rank)
     pb.val.copy_(torch.randn((n, K), generator=g)); pb.loc.copy_(torch.randn((n, K), generator=g))
     pb.bins.copy_(torch.randint(0, 4096, (n, K), generator=g, dtype=torch.int32))
@@ -62,11 +62,13 @@ def _worker_packed(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_packed_peak_buffers_gather():
+@pytest.mark.parametrize("mode", ["gather", "allgather"])
+def test_packed_peak_buffers_gather(mode):
+    """Both forms of the one collective: gather to rank 0, or all_gather_into_tensor with the other ranks dropping the result."""
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker_packed, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker_packed, args=(r, 2, port, q, mode)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
