@@ -159,8 +159,8 @@ def run_reference(args, w):
     mod, kind = cpu_arm()
     cores = mod.max_threads()
     per_step = (64 if kind == "reference" else 128) * cores     # ~2 ms (reference build) / ~0.5 ms (port) per frame and core
-    fr, _ = synth.frames_numpy(per_step, w["M"], w["N"], w["thetas"], d=w["d"], snr_db=w["snr_db"], jitter_deg=w["jitter"],
-                               seed=synth.SEED_BASE + 3)
+    fr, _ = synth.frames_philox_numpy(0, per_step, w["M"], w["N"], w["thetas"], d=w["d"], snr_db=w["snr_db"], jitter_deg=w["jitter"],
+                                      seed=synth.SEED_BASE + 3)      # the first frames of the very batch the GPU arm times
     for _ in range(min(args.warmup, 1)):
         cpu_chain(mod, kind, fr, 0, w["d"], w["T"], w["P"], w["K"], cores)
     dt = 0.0
@@ -254,17 +254,22 @@ def main():
         return [float(v) for v in t.tolist()]
 
     B, M, N, T, P, K = w["frames"], w["M"], w["N"], w["T"], w["P"], w["K"]
-    x, _ = synth.frames_torch(B, M, N, w["thetas"], d=w["d"], snr_db=w["snr_db"], jitter_deg=w["jitter"],
-                              seed=synth.SEED_BASE + 3 + 1000 * rank, device=dev)
+    # counter-based batch: frame f is a pure function of (seed, f); rank r holds frames [r B, (r + 1) B), and any of
+    # them can be regenerated on the host (the CPU arm below does, for a slice, and compares)
+    x, _ = synth.frames_philox_torch(rank * B, B, M, N, w["thetas"], d=w["d"], snr_db=w["snr_db"], jitter_deg=w["jitter"],
+                                     seed=synth.SEED_BASE + 3, device=dev)
     chain = doa.DoaChain(M, N, 0, 0, w["d"], T, P, K, device=local, max_frames=B)
     # the one collective of the path: packed peaks of every shard to rank 0, double-buffered on a side stream so that the
     # gather of step i runs under the chain kernel of step i+1 (every gather completes inside the timed region: drain())
-    # measured (B200 x8 box): the serial gather costs 0.03 ms per step at 2 GPUs, 0.24 ms at 8; pipelined with 2 SMs left to
-    # NCCL: 8 GPUs 1.87-1.95 -> 1.74 ms per step, 4 GPUs no change, 2 GPUs 2-3 % slower (the reserved SMs)
+    # measured (B200 x8 boxes): the serial gather costs 0.03 ms per step at 2 GPUs, 0.24 ms at 8; pipelined with SMs left to NCCL:
+    # round 1: 8 GPUs 1.87-1.95 -> 1.74 ms per step (2 SMs), 4 GPUs no change, 2 GPUs 2-3 % slower (the reserved SMs);
+    # round 2 (profiles/r02_bench_n8*.json, another box): serial gather 2.30 ms, pipelined 2.00 (2 SMs) / 1.83 (1 SM);
+    # all_gather_into_tensor instead of gather: 2.07 serial, 2.39 / 2.05 pipelined (2 / 4 SMs) -- every rank then receives
+    # 8 x 2.4 MB it drops, and its ring kernel needs more SMs: not better, gather stays
     pipelined = os.environ.get("DOA_PIPELINE", "1" if world > 4 else "0") != "0"
     gather_mode = os.environ.get("DOA_GATHER", "gather")        # "gather" (send/recv to rank 0) or "allgather" (all_gather_into_tensor)
     peaks = sharding.PeakExchange(B, K, dev, world=world, is_dst=(rank == 0), pipelined=pipelined, mode=gather_mode)
-    reserve = int(os.environ.get("DOA_SMS_RESERVE", "2")) if (world > 1 and pipelined) else 0
+    reserve = int(os.environ.get("DOA_SMS_RESERVE", "1")) if (world > 1 and pipelined) else 0
     chain.set_sms_reserve(reserve)
     out = peaks.bufs[0].outputs()
     total = B * world
@@ -429,6 +434,12 @@ def main():
         dt_port = time.perf_counter() - t0
         bins_gpu = out[2][:ns].cpu().numpy()
         parity = {"against_port": classify_against_cpu(np, O, sub, bins_gpu, b_o, w, cores)}
+        r0 = min(B - 64, 12345)             # any slice of the device batch can be re-derived on the host
+        host, _ = synth.frames_philox_numpy(rank * B + r0, 64, M, N, w["thetas"], d=w["d"], snr_db=w["snr_db"], jitter_deg=w["jitter"],
+                                            seed=synth.SEED_BASE + 3)
+        devs = x[r0:r0 + 64].cpu().numpy()
+        parity["host_regeneration"] = {"frames": [r0, r0 + 64], "samples_bit_identical_frac": float((host.view(np.uint32) == devs.view(np.uint32)).mean()),
+                                       "max_abs_diff": float(np.abs(host - devs).max())}
         cpu = {"value": ns / dt_port, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {ns} frames of the timed batch, oracle port, OpenMP over frames ({cores} threads), BLAS single-threaded",
                "peak_bins_identical_frac": 1.0 - parity["against_port"]["frames_with_different_bins"] / ns}
@@ -476,7 +487,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_text(w), "frames_per_gpu": B, "peak_exchange": gather_mode if world > 1 else None, "parallelism": f"frames sharded x{world}, one peak gather per step" + (" (double-buffered on a side stream, under the next step's kernel; 2 SMs left to NCCL)" if (world > 1 and pipelined) else ""),
+            "config": {"workload": workload_text(w), "frames_per_gpu": B, "peak_exchange": gather_mode if world > 1 else None, "parallelism": f"frames sharded x{world}, one peak gather per step" + (" (double-buffered on a side stream, under the next step's kernel; " + str(reserve) + " SM left to NCCL)" if (world > 1 and pipelined) else ""),
                        "l2": "inputs (8 GiB/GPU) larger than L2 (126 MB): no flush between iterations",
                        "timer": "CUDA events on the launching stream, max over ranks",
                        "regime": f"burst: {args.steps} steps = {ms:.0f} ms; see `sustained` for >= 2 s of back-to-back steps"},
