@@ -53,22 +53,32 @@ def main():
         print("stall reasons (warps per issue-active cycle): " + ", ".join(f"{k}={v:.2f}" for v, k in st[:10]))
         print()
     src = page(rep, "source")
-    hi = [i for i, r in enumerate(src[:12]) if "Address" in r]
-    if not hi:
-        return
-    hh = src[hi[0]]
-    data = src[hi[0] + 1:]
+    heads = [i for i, r in enumerate(src) if "Address" in r and "Source" in r]
+    for n, h0 in enumerate(heads):
+        hh = src[h0]
+        data = [r for r in src[h0 + 1:(heads[n + 1] if n + 1 < len(heads) else len(src))] if len(r) == len(hh)]
+        kn = src[h0 - 1][1][:100] if h0 > 0 and len(src[h0 - 1]) > 1 else ""
+        region_table(hh, data, kn)
+
+
+def region_table(hh, data, kernel_name):
     isrc, isamp, iex = hh.index("Source"), hh.index("Warp Stall Sampling (All Samples)"), hh.index("Instructions Executed")
+
+    def num(v):
+        try:
+            return int(v or 0)
+        except ValueError:
+            return 0
     stc = [i for i, n in enumerate(hh) if n.startswith("stall_") and "Not Issued" not in n]
-    tot = sum(int(r[isamp] or 0) for r in data)
-    totex = sum(int(r[iex] or 0) for r in data)
+    tot = sum(num(r[isamp]) for r in data) or 1
+    totex = sum(num(r[iex]) for r in data) or 1
     step = 240
-    print(f"warp-stall sampling by SASS region (blocks of {step} instructions in address order; {tot} samples, {totex} warp-instructions):")
+    print(f"warp-stall sampling by SASS region, {kernel_name} (blocks of {step} instructions in address order; {tot} samples, {totex} warp-instructions):")
     print("  first-instr  samples  executed  dominant opcodes | dominant stall reasons")
     for a in range(0, len(data), step):
         blk = data[a:a + step]
-        s = sum(int(r[isamp] or 0) for r in blk)
-        e = sum(int(r[iex] or 0) for r in blk)
+        s = sum(num(r[isamp]) for r in blk)
+        e = sum(num(r[iex]) for r in blk)
         if s < tot * 0.005 and e < totex * 0.005:
             continue
         ops, d = {}, {}
@@ -79,13 +89,14 @@ def main():
             op = (t[1] if t[0].startswith("@") and len(t) > 1 else t[0]).split(".")[0]
             ops[op] = ops.get(op, 0) + 1
             for i in stc:
-                v = int(r[i] or 0)
+                v = num(r[i])
                 if v:
                     d[hh[i][6:]] = d.get(hh[i][6:], 0) + v
         topo = ", ".join(f"{k}:{v}" for k, v in sorted(ops.items(), key=lambda x: -x[1])[:4])
         ds = sum(d.values()) or 1
         tops = ", ".join(f"{k}:{100 * v // ds}%" for k, v in sorted(d.items(), key=lambda x: -x[1])[:5])
         print(f"  {a:7d}  {100 * s / tot:5.1f}%  {100 * e / totex:5.1f}%  {topo} | {tops}")
+    print()
 
 
 if __name__ == "__main__":
