@@ -97,7 +97,7 @@ cov16_kernel(const S* __restrict__ in, long long frame_stride, long long chan_st
 #pragma unroll
       for (int p = 0; p < 28; ++p) { d0.get(p, a[2 * p], a[2 * p + 1]); d1.get(p, a[64 + 2 * p], a[64 + 2 * p + 1]); }
 #pragma unroll
-      for (int r = 0; r < 8; ++r) { a[56 + r] = d0.dg[r]; a[120 + r] = d1.dg[r]; }
+      for (int r = 0; r < 8; ++r) { a[56 + r] = d0.diag(r); a[120 + r] = d1.diag(r); }
     } else {
       f32x2 od[64];                                 // (re, im) of R[8 + i][j] at od[i * 8 + j]
 #pragma unroll

@@ -117,7 +117,7 @@ __device__ __forceinline__ float2 folded_entry(const float* red, int r, int c, f
 }
 
 
-// Per-lane accumulators of the Hermitian lower half (M diagonal reals + M(M-1)/2 complex = M*M floats).  An off-diagonal
+// Per-lane accumulators of the Hermitian lower half (M diagonal pairs + M(M-1)/2 complex).  An off-diagonal
 // entry is one packed pair (re, im) updated by two fma.rn.f32x2 per sample:
 //     (re, im) += (x_r.re, x_r.im) * x_c.re          (re, im) += (x_r.im, -x_r.re) * x_c.im
 // which is, per component and in this order, the scalar form  re = fma(xr.re, xc.re, re); re = fma(xr.im, xc.im, re);
@@ -126,11 +126,16 @@ __device__ __forceinline__ float2 folded_entry(const float* red, int r, int c, f
 template <int M>
 struct CovAcc {
   static constexpr int NP = M * (M - 1) / 2;
-  float dg[M];
+  // M > 8: a diagonal entry as the packed pair (sum re^2, sum im^2), ONE fma.rn.f32x2 per sample instead of two dependent FFMA,
+  // the halves added when the lanes' partial sums are folded (the 16-element covariance: 1.67 -> 1.55 ms per 65,536 frames).
+  // M <= 8 keeps the scalar chain: measured 0.3 % (8 elements) and 0.7 % (4) slower packed, A/B on one box (tools/ab_libs.py).
+  static constexpr bool PKD = M > 8;
+  float dg[PKD ? 1 : M];
+  f32x2 dg2[PKD ? M : 1];
   f32x2 od[NP > 0 ? NP : 1];
   __device__ __forceinline__ void clear() {
 #pragma unroll
-    for (int r = 0; r < M; ++r) dg[r] = 0.0f;
+    for (int r = 0; r < M; ++r) { if constexpr (PKD) dg2[r] = 0ull; else dg[r] = 0.0f; }
 #pragma unroll
     for (int p = 0; p < NP; ++p) od[p] = 0ull;
   }
@@ -139,9 +144,9 @@ struct CovAcc {
 #pragma unroll
     for (int r = 0; r < M; ++r) {
       const float2 xr = x[r];
-      dg[r] = fmaf(xr.x, xr.x, dg[r]);
-      dg[r] = fmaf(xr.y, xr.y, dg[r]);
       const f32x2 xp = pk2(xr.x, xr.y), xs = pk2(xr.y, -xr.x);
+      if constexpr (PKD) dg2[r] = fma2(xp, xp, dg2[r]);
+      else { dg[r] = fmaf(xr.x, xr.x, dg[r]); dg[r] = fmaf(xr.y, xr.y, dg[r]); }
 #pragma unroll
       for (int c = 0; c < r; ++c) {
         const float2 xc = x[c];
@@ -152,6 +157,10 @@ struct CovAcc {
     }
   }
   __device__ __forceinline__ void get(int p, float& re, float& im) const { upk2(od[p], re, im); }
+  __device__ __forceinline__ float diag(int r) const {
+    if constexpr (PKD) { float a, b; upk2(dg2[r], a, b); return a + b; }
+    else return dg[r];
+  }
   // fold the 32 lanes' partial matrices; `red` (M*M floats, shared, this warp's) receives the raw sums
   __device__ __forceinline__ void fold(unsigned lane, float* red) {
     constexpr int CNT = M * M;
@@ -159,7 +168,7 @@ struct CovAcc {
 #pragma unroll
     for (int p = 0; p < NP; ++p) upk2(od[p], a[2 * p], a[2 * p + 1]);
 #pragma unroll
-    for (int r = 0; r < M; ++r) a[2 * NP + r] = dg[r];
+    for (int r = 0; r < M; ++r) a[2 * NP + r] = diag(r);
     warp_reduce_scatter<CNT, 16>(a, lane);
     const int b = rs_base<CNT>(lane);
     constexpr int F = CNT >= 32 ? CNT / 32 : 1;
@@ -277,13 +286,13 @@ __device__ __forceinline__ void cov16_ring_role(const S* __restrict__ in, long l
   for (int q = 0; q < C16_STAGES - 2; ++q) { if (issued < total) issue(); cp_async_commit(); }
 
   f32x2 od[64];                                       // ROLE 0: two CovAcc<8>-style diagonal blocks; ROLE 1: R[8 + i][j] at od[i * 8 + j]
-  float dg[ROLE == 0 ? 16 : 1];
+  f32x2 dg2[ROLE == 0 ? 16 : 1];                      // (sum re^2, sum im^2) per diagonal entry, see CovAcc
   auto clear = [&]() {
 #pragma unroll
     for (int i = 0; i < 64; ++i) od[i] = 0ull;
     if constexpr (ROLE == 0) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) dg[i] = 0.0f;
+      for (int i = 0; i < 16; ++i) dg2[i] = 0ull;
     }
   };
   clear();
@@ -312,9 +321,8 @@ __device__ __forceinline__ void cov16_ring_role(const S* __restrict__ in, long l
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             const float2 xr = x[s][8 * b + r];
-            dg[8 * b + r] = fmaf(xr.x, xr.x, dg[8 * b + r]);
-            dg[8 * b + r] = fmaf(xr.y, xr.y, dg[8 * b + r]);
             const f32x2 xp = pk2(xr.x, xr.y), xs = pk2(xr.y, -xr.x);
+            dg2[8 * b + r] = fma2(xp, xp, dg2[8 * b + r]);
 #pragma unroll
             for (int cc = 0; cc < r; ++cc) {
               const float2 xc = x[s][8 * b + cc];
@@ -346,7 +354,7 @@ __device__ __forceinline__ void cov16_ring_role(const S* __restrict__ in, long l
 #pragma unroll
           for (int p = 0; p < 28; ++p) upk2(od[32 * b + p], a[64 * b + 2 * p], a[64 * b + 2 * p + 1]);
 #pragma unroll
-          for (int r = 0; r < 8; ++r) a[64 * b + 56 + r] = dg[8 * b + r];
+          for (int r = 0; r < 8; ++r) { float d0, d1; upk2(dg2[8 * b + r], d0, d1); a[64 * b + 56 + r] = d0 + d1; }
         }
       } else {
 #pragma unroll

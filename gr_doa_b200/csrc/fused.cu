@@ -17,7 +17,10 @@
 #include "eig_device.cuh"
 #include "scan_device.cuh"
 
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
+
 #include <algorithm>
+#include <cstring>
 
 namespace doa {
 namespace {
@@ -45,6 +48,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
                :: "r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
+// FILL 3: ONE tensor-map copy per stage -- cp.async.bulk.tensor.3d of the box [1 frame][M channels][64 samples] (M x 512 bytes),
+// coordinates (sample, channel, frame); samples beyond the frame are zero-filled by the copy engine.  SASS: UTMALDG.3D.
+__device__ __forceinline__ void tma_box_g2s(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               :: "r"(smem_addr(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar)) : "memory");
+}
+
 // S = float2: fc32 samples, a ring slot is one float4 (two samples) per lane and channel; S = unsigned: sc16 samples, a ring
 // slot is one uint2 (the same two samples in 8 bytes).  Either way lane l of chunk c holds samples 64 c + 2 l and + 1, so the
 // two formats accumulate in the same order.
@@ -55,6 +65,7 @@ template <> struct RingSlot<unsigned> { typedef uint2 type; };
 //   0  lane l copies samples 2l, 2l+1 of the chunk for each of the M channels: M cp.async per lane, each with its own 64-bit
 //      source address (k * chan_stride is a run-time stride);
 //   1  bulk (TMA) copies issued by one lane (fc32 only);
+//   3  one tensor-map TMA copy per stage (fc32, dense [B][M][N] batches only);
 //   2  lane l copies for channel l / (32/M) only: its M cp.async are 64 bytes apart (sc16: 32) in that channel, i.e. ONE 64-bit
 //      address and immediates -- about 30 fewer address instructions per chunk in an issue-bound loop.  A warp-wide copy
 //      then touches M segments of 64 bytes instead of 512 contiguous bytes (the same 16 sectors).  Measured at cfg3
@@ -66,9 +77,10 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
                 int avg_method, float scale, float bscale, int T, int max_sweeps, const float* __restrict__ zpair,
                 const float2* __restrict__ zplain, const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int P, int K,
                 float* __restrict__ out_val, float* __restrict__ out_loc, int* __restrict__ out_bin,
-                const float2* __restrict__ gains, float2* __restrict__ G_out, float2* __restrict__ u_out) {
+                const float2* __restrict__ gains, float2* __restrict__ G_out, float2* __restrict__ u_out,
+                const __grid_constant__ CUtensorMap tmap) {
   static_assert(M == 8 || M == 4, "instantiated for 8 and 4 lanes per matrix");
-  constexpr bool TMA = FILL == 1;
+  constexpr bool TMA = FILL == 1 || FILL == 3;
   static_assert(!TMA || sizeof(S) == 8, "bulk ring fills are an fc32 variant");
   typedef typename RingSlot<S>::type Slot;
   constexpr bool SC16 = sizeof(S) == 4;
@@ -85,6 +97,10 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
   float2* us = Gs + TILE * MM;                                       // [TILE][M]
   float* red = reinterpret_cast<float*>(us + TILE * M);              // [WS_P][MM]
   Slot* ring = reinterpret_cast<Slot*>(red + WS_P * MM);             // [WS_P][WS_STAGES][M][32]
+  if constexpr (FILL == 3) {   // a tensor-map copy wants a 128-byte aligned destination (offset, not an integer round trip: keeps LDS)
+    char* rb = reinterpret_cast<char*>(ring);
+    ring = reinterpret_cast<Slot*>(rb + ((128u - (smem_addr(rb) & 127u)) & 127u));
+  }
   __shared__ unsigned long long ring_bar[TMA ? WS_P * WS_STAGES : 1];
   if constexpr (TMA) {
     if (threadIdx.x < WS_P * WS_STAGES) mbar_init(&ring_bar[threadIdx.x], 1);
@@ -117,10 +133,17 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
     // issue cursor (frame base pointer, chunk in frame, ring stage) advances incrementally: no divisions in the loop
     constexpr int LPC = 32 / M;                                      // FILL 2: lanes per channel
     const S* ibase = in + (lo + w) * frame_stride;
+    long long iframe = lo + w;                                       // FILL 3: the frame coordinate of the tensor map
     if constexpr (FILL == 2) ibase += (long long)(lane / LPC) * chan_stride + (lane % LPC) * 2;
     int ic = 0, istage = 0, issued = 0;
     auto issue = [&]() {
-      if constexpr (TMA) {
+      if constexpr (FILL == 3) {
+        if (lane == 0) {
+          unsigned long long* bar = &ring_bar[w * WS_STAGES + istage];
+          mbar_expect_tx(bar, M * 512u);
+          tma_box_g2s(myring + (size_t)istage * M * 32, &tmap, ic * 64, 0, (int)iframe, bar);
+        }
+      } else if constexpr (TMA) {
         if (lane == 0) {
           unsigned long long* bar = &ring_bar[w * WS_STAGES + istage];
           mbar_expect_tx(bar, M * 512u);
@@ -155,7 +178,7 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
           else cp_async16(dst + k * 32, ibase + (long long)k * chan_stride + (nbytes ? t : 0), nbytes);
         }
       }
-      if (++ic == NCH) { ic = 0; ibase += (long long)WS_P * frame_stride; }
+      if (++ic == NCH) { ic = 0; ibase += (long long)WS_P * frame_stride; iframe += WS_P; }
       if (++istage == WS_STAGES) istage = 0;
       ++issued;
     };
@@ -252,7 +275,7 @@ int launch_ws_cfg2(const S* in, long long fs, long long cs, int N, int nframes, 
                   float2* G_out = nullptr, float2* u_out = nullptr) {
   constexpr int TILE = WS_C * 32 / M;
   const size_t smem = ((ztab_floats(tb.P) + 3) & ~(size_t)3) * sizeof(float) + ((size_t)(WS_NBUF + 1) * TILE * M * M + (size_t)TILE * M) * sizeof(float2) +
-                      (size_t)WS_P * M * M * sizeof(float) + (size_t)WS_P * WS_STAGES * M * 32 * sizeof(typename RingSlot<S>::type);
+                      (size_t)WS_P * M * M * sizeof(float) + (size_t)WS_P * WS_STAGES * M * 32 * sizeof(typename RingSlot<S>::type) + (FILL == 3 ? 128 : 0);
   if (smem > 225 * 1024) return 0;
   auto kern = chain_ws_kernel<M, 4, WS_P, WS_C, WS_STAGES, WS_NBUF, FILL, S>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -266,8 +289,28 @@ int launch_ws_cfg2(const S* in, long long fs, long long cs, int N, int nframes, 
   constexpr int GRP = 32 / M;
   const int grid = std::max(1, std::min(sms, (nframes + GRP - 1) / GRP));
   const float scale = (float)(1.0 / N) * in_scale2, bscale = (float)(0.5 / N);   // in_scale2: sc16 converter scale squared (cov.cu)
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  if constexpr (FILL == 3) {
+    // [B][M][N] complex64 as a rank-3 tensor of 8-byte elements (sample, channel, frame); box = 64 samples x M channels x 1 frame
+    typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_t encode = nullptr;
+    if (encode == nullptr) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || fn == nullptr) return 0;
+      encode = (encode_t)fn;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)nframes};
+    const cuuint64_t strides[2] = {(cuuint64_t)cs * 8u, (cuuint64_t)fs * 8u};
+    const cuuint32_t box[3] = {64u, (cuuint32_t)M, 1u}, estr[3] = {1u, 1u, 1u};
+    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<S*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 0;
+  }
   kern<<<grid, (WS_P + WS_C) * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.z, tb.V, tb.xaxis, tb.P,
-                                               K, out_val, out_loc, out_bin, gains, G_out, u_out);
+                                               K, out_val, out_loc, out_bin, gains, G_out, u_out, tmap);
   return 1;
 }
 
@@ -279,9 +322,31 @@ int launch_ws_cfg(const float2* in, long long fs, long long cs, int N, int nfram
   // Bulk (TMA) ring fills, measured at cfg3: 1.99 ms against 1.67 ms with per-lane cp.async -- a 512-byte copy per channel and
   // chunk is too small for the bulk-copy engine (16.8 M copies per launch) and larger ones do not fit per-warp rings.  Kept
   // selectable (dev knob ws_tma) for the default configuration only.
+  // Tensor-map TMA ring fills (FILL 3, SASS UTMALDG.3D): one cp.async.bulk.tensor.3d box [1 frame][M channels][64 samples] per stage
+  // and producer warp, issued by one lane -- no per-lane addresses and no LSU instructions in the streaming loop, tail samples
+  // zero-filled by the copy engine.  Needs the dense [B][M][N] layout (a rank-3 tensor map); measured at cfg3 against per-lane
+  // cp.async, interleaved (tools/ws_exp.py 80824 80824m, profiles/r02_ws_tma_map*.log): 1.648-1.657 against 1.672-1.677 ms,
+  // same bits.  (The round-1 bulk variant -- M separate 512-byte UBLKCP copies per stage -- measured 2.09 ms: eight times the
+  // copies.)  Shipped for the 8-element configuration on batches of at least 1024 frames (a tensor map is encoded per call); at 4
+  // elements (2 KB boxes, six stages) it measured SLOWER (2.76 against 2.46 ms per 262,144 frames) and is not used; streaming
+  // layouts (overlapping frames) and sc16 samples keep cp.async.  Option "tma" = 0 switches it off.
+  if constexpr (M == 8 && WS_P == 8 && WS_C == 8 && WS_STAGES == 2 && WS_NBUF == 4) {
+    if (dev_option(OPT_TMA, 1) && dev_option(OPT_WS_TMA, 0) == 0 && dev_option(OPT_WS_FILL, 0) == 0 && nframes >= 1024 && cs == N &&
+        fs == (long long)M * N && (N % 2) == 0) {
+      const int r3 = launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 3>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2, G_out, u_out);
+      if (r3) return r3;
+    }
+  }
 #ifdef DOA_DEV_KNOBS
+  // the same fills for a handful of other configurations, for the sweep (tools/ws_exp.py, suffix 'm')
+  if constexpr (WS_P + WS_C <= 16 && (WS_STAGES == 2 || WS_STAGES == 3) && WS_NBUF >= 2 && WS_NBUF <= 4) {
+    if (dev_option(OPT_WS_TMA, 0) == 2 && cs == N && fs == (long long)M * N && (cs % 2) == 0) {
+      const int r3 = launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 3>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2, G_out, u_out);
+      if (r3) return r3;
+    }
+  }
   if constexpr (WS_P == 8 && WS_C == 8 && WS_STAGES == 2 && WS_NBUF == 4) {
-    if (N % 64 == 0 && dev_option(OPT_WS_TMA, 0))
+    if (N % 64 == 0 && dev_option(OPT_WS_TMA, 0) == 1)
       return launch_ws_cfg2<M, WS_P, WS_C, WS_STAGES, WS_NBUF, 1>(in, fs, cs, N, nframes, avg, T, tb, K, out_val, out_loc, out_bin, st, gains, in_scale2);
   }
   // channel-major fills (FILL 2): instantiated for the shipped configurations only
@@ -369,6 +434,10 @@ int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_
     case 80823: return launch_ws_cfg<8, 8, 8, 2, 3>(WS_ARGS);
     case 80825: return launch_ws_cfg<8, 8, 8, 2, 5>(WS_ARGS);
     case 80826: return launch_ws_cfg<8, 8, 8, 2, 6>(WS_ARGS);
+    case 70924: return launch_ws_cfg<8, 7, 9, 2, 4>(WS_ARGS);
+    case 61024: return launch_ws_cfg<8, 6, 10, 2, 4>(WS_ARGS);
+    case 61034: return launch_ws_cfg<8, 6, 10, 3, 4>(WS_ARGS);
+    case 90724: return launch_ws_cfg<8, 9, 7, 2, 4>(WS_ARGS);
     default: return launch_ws_cfg<8, 8, 8, 2, 4>(WS_ARGS);
   }
 #endif

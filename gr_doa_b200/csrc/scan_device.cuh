@@ -198,12 +198,18 @@ __device__ __forceinline__ float db_value(float q, float qmin_global) {
   return __fmul_rn(10.0f, log10f(__fdiv_rn(y, ymax)));
 }
 
-// Sort K values held by lanes 0..K-1 descending (ties: lower lane first) and return this lane's destination slot.
+// Sort K values held by lanes 0..K-1 descending (ties: lower lane first) and return this lane's destination slot.  A total
+// order also with NaNs among the values (they go last, by lane), so that the K destinations are always a permutation of
+// 0..K-1 and every output slot is written: a peak value is NaN when the null spectrum rounds to a non-positive number at
+// that bin (num_targets = num_ant_ele - 1 puts exact zeros of Q on the grid's doorstep), exactly as the reference's
+// 10*log10((1/Q)/max) is (MUSIC_lin_array_impl.cc:140-142).
 __device__ __forceinline__ int rank_desc(float v, int K, int lane) {
   int rank = 0;
+  const bool vn = v != v;
   for (int r = 0; r < K; ++r) {
     const float o = __shfl_sync(FULL, v, r);
-    rank += (o > v || (o == v && r < lane)) ? 1 : 0;
+    const bool before = (o != o) ? (vn && r < lane) : (vn || o > v || (o == v && r < lane));
+    rank += before ? 1 : 0;
   }
   return rank;
 }
@@ -375,10 +381,11 @@ __device__ __forceinline__ void peaks_refine_emit(const Merged& m, float q0, flo
   if (m.nvalid == 0) { fin_q = gmin_q; fin_bin = gmin_bin; }   // no local peak at all: every entry is the arg-max (:149-150)
   fin_bin = min(fin_bin, P - 1);
   {   // the 0 dB level is the smallest refined value anywhere (two nulls of near-equal depth can swap order on refinement)
-    float mq = (lane < K) ? fin_q : INFINITY;
+    // ... among the POSITIVE ones: the level is max(1/Q), and 1/Q of a value that rounded to below zero is negative
+    float mq = (lane < K && fin_q > 0.f) ? fin_q : INFINITY;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) mq = fminf(mq, __shfl_xor_sync(FULL, mq, o));
-    gmin_q = fminf(gmin_q, mq);
+    gmin_q = fminf(gmin_q > 0.f ? gmin_q : INFINITY, mq);
   }
   float val = (lane < K) ? db_value(fin_q, gmin_q) : -INFINITY;
   // entries 0..nref-1 are real peaks: order them by height like sort_index(..., "descend"); fill-ins stay behind

@@ -191,6 +191,7 @@ int doa_cuda_set_input_format(doa_cuda_handle* h, int format, float scale);
  *                                       gather of a multi-GPU run) can run under the next batch's chain kernel
  *   "fused"          default 1          0: run the chain as its stage kernels (covariance, eigendecomposition, scan + peaks)
  *                                       instead of the persistent warp-specialised kernel (4- and 8-element arrays)
+ *   "tma"            default 1          0: per-lane cp.async ring fills in the fused kernel instead of tensor-map TMA boxes
  *   "scan_tc"        default 1          0: Horner scan on the CUDA cores instead of the tensor-core contraction (unfused chain)
  *   "herk_tc"        default 1          0: CUDA-core tiled covariance at 64 elements instead of the tensor-core HERK
  *   "root_aberth"    default 1          0: Root-MUSIC by Hessenberg QR only

@@ -447,3 +447,52 @@ def test_streams_call_up_to_max_frames_beyond_the_host_chunk_size(doa):
         ch.run_streams([x[k][:-5] for k in range(M)], n)          # short arrays are refused before the library reads them
     with pytest.raises(ValueError):
         ch.run_streams([x[k] for k in range(M - 1)], n)
+
+
+@pytest.mark.parametrize("M,T,N,P,K", [(8, 3, 2048, 4096, 3), (8, 3, 200, 1024, 3), (8, 1, 130, 512, 1), (8, 7, 1000, 1024, 4)])
+def test_tensor_map_ring_fills_equal_cp_async(doa, torch_cuda, M, T, N, P, K):
+    """Dense batches of >= 1024 frames fill the fused kernel's rings with tensor-map TMA boxes (cp.async.bulk.tensor.3d, one
+    [1][M][64]-sample box per stage, tail samples zero-filled by the copy engine) instead of per-lane cp.async: only the way
+    the samples reach shared memory changes, so the outputs are the same bits -- also for snapshot sizes that are not a
+    multiple of the 64-sample box."""
+    from gr_doa_b200 import synth
+    thetas = [60.0] if T == 1 else list(np.linspace(50.0, 130.0, T))
+    nb = 3000
+    x, _ = synth.frames_torch(nb, M, N, thetas, jitter_deg=2.0, device="cuda", chunk=1024, seed=5 + N)
+    ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=nb)
+    a = [t.clone() for t in ch.run_device(x)]
+    assert ch.launches() == 1
+    ch.set_option("tma", 0)
+    b = ch.run_device(x)
+    assert ch.launches() == 1
+    same = lambda p, q: torch_cuda.equal(p.view(torch_cuda.int32), q.view(torch_cuda.int32))      # bits (an empty slot is NaN)
+    assert all(same(p, q) for p, q in zip(a, b))
+    c = [t.clone() for t in ch.run_device(x[:1000])]                     # below the threshold: cp.async either way
+    ch.set_option("tma", 1)
+    assert all(same(p, q) for p, q in zip(c, ch.run_device(x[:1000])))
+    assert all(same(p[:1000], q) for p, q in zip(a, c))
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+def test_every_output_slot_written_when_null_spectrum_rounds_nonpositive(doa, torch_cuda, fused):
+    """num_targets = num_ant_ele - 1 leaves a one-dimensional noise subspace: Q has exact zeros next to grid bins, and in a few
+    frames per thousand its float32 value at a peak rounds to <= 0.  The reference's arithmetic then gives NaN for that
+    entry (10*log10 of a negative ratio, MUSIC_lin_array_impl.cc:140-142); ours does the same, takes the 0 dB level from
+    the positive values, orders NaN entries last -- and still writes every slot of every frame (a NaN among the sort keys
+    once made several entries claim slot 0 and left the others unwritten)."""
+    from gr_doa_b200 import synth
+    t = torch_cuda
+    M, T, N, P, K, nb = 8, 7, 1000, 1024, 4, 3000
+    x, _ = synth.frames_torch(nb, M, N, list(np.linspace(50.0, 130.0, T)), jitter_deg=2.0, device="cuda", chunk=1024, seed=5 + N)
+    ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=nb)
+    ch.set_option("fused", fused)
+    out = (t.full((nb, K), -7777.0, device="cuda"), t.full((nb, K), -7777.0, device="cuda"), t.full((nb, K), -7777, dtype=t.int32, device="cuda"))
+    ch.run_device(x, out=out)
+    val, loc, bins = [o.cpu().numpy() for o in out]
+    assert not (val == -7777.0).any() and not (loc == -7777.0).any() and not (bins == -7777).any()
+    assert ((bins >= 0) & (bins < P)).all()
+    nan = np.isnan(val)
+    assert nan.any(axis=1).mean() < 0.02                                         # a few frames per thousand
+    assert not (nan[:, :-1] & ~nan[:, 1:]).any()                                 # NaN entries come last
+    fin = ~nan.any(axis=1)
+    assert (val[fin, 0] == 0.0).all() and (np.diff(val[fin], axis=1) <= 0).all()  # 0 dB first, descending

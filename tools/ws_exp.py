@@ -10,11 +10,12 @@ L = _lib.lib()
 B, M, N, T, P, K = 65536, 8, 2048, 3, 4096, 3
 x, _ = synth.frames_torch(B, M, N, [40.0, 90.0, 140.0], jitter_deg=2.0, device="cuda", chunk=2048)
 ch = doa.DoaChain(M, N, 0, 0, 0.5, T, P, K, max_frames=B)
-cfgs = sys.argv[1:] or ["80824"]            # a trailing 't' = bulk (TMA) ring fills instead of per-lane cp.async (80824 only); 'c' = channel-major fills
+cfgs = sys.argv[1:] or ["80824"]            # a trailing 't' = bulk (UBLKCP) ring fills instead of per-lane cp.async (80824 only); 'm' = tensor-map TMA (UTMALDG) fills; 'c' = channel-major fills
 def select(cs):
-    doa.set_default_option("ws_tma", 1 if cs.endswith("t") else 0)
+    doa.set_default_option("tma", 0)   # the sweep selects the fill explicitly
+    doa.set_default_option("ws_tma", 1 if cs.endswith("t") else 2 if cs.endswith("m") else 0)     # 'm': one tensor-map TMA box per stage
     doa.set_default_option("ws_fill", 2 if cs.endswith("c") else 0)
-    c = int(cs.rstrip("tc"))
+    c = int(cs.rstrip("tcm"))
     doa.set_default_option("ws_split", c // 100); doa.set_default_option("ws_stages", (c // 10) % 10); doa.set_default_option("ws_nbuf", c % 10)
 ref, same, times, launches = None, {}, {c: [] for c in cfgs}, {}
 for c in cfgs:
