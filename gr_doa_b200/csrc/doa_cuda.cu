@@ -287,7 +287,7 @@ int doa_cuda_set_option(doa_cuda_handle* h, const char* key, int value) {
   static const struct { const char* name; Opt opt; } kNames[] = {
       {"fused", OPT_FUSED}, {"scan_tc", OPT_SCAN_TC}, {"sms_reserve", OPT_SMS_RESERVE}, {"cov_groups", OPT_COV_GROUPS},
       {"cov16_ring", OPT_COV16_RING}, {"herk_tc", OPT_HERK_TC}, {"scan_wide", OPT_SCAN_WIDE}, {"spectrum_smem", OPT_SPECTRUM_SMEM},
-      {"root_aberth", OPT_ROOT_ABERTH}, {"jacobi_sweeps", OPT_JACOBI_SWEEPS}, {"tma", OPT_TMA}, {"ws_split", OPT_WS_SPLIT}, {"ws_stages", OPT_WS_STAGES},
+      {"root_aberth", OPT_ROOT_ABERTH}, {"jacobi_sweeps", OPT_JACOBI_SWEEPS}, {"tma", OPT_TMA}, {"eig_onesided", OPT_EIG_ONESIDED}, {"ws_split", OPT_WS_SPLIT}, {"ws_stages", OPT_WS_STAGES},
       {"ws_nbuf", OPT_WS_NBUF}, {"ws4", OPT_WS4}, {"ws_tma", OPT_WS_TMA}, {"ws_fill", OPT_WS_FILL}, {"scan_tc_dbg", OPT_SCAN_TC_DBG}, {"fused16", OPT_FUSED16}};
   if (!h || !key) return DOA_CUDA_EINVAL;
   for (const auto& n : kNames) {

@@ -93,7 +93,7 @@ int launch_rootmusic_scratch(const float2* u, int M, int T, float norm_spacing, 
 // no global mutable state, no lock, no lookup on the launch path.
 enum Opt {
   OPT_FUSED, OPT_SCAN_TC, OPT_SMS_RESERVE, OPT_COV_GROUPS, OPT_COV16_RING, OPT_HERK_TC, OPT_SCAN_WIDE, OPT_SPECTRUM_SMEM,
-  OPT_ROOT_ABERTH, OPT_JACOBI_SWEEPS, OPT_TMA,
+  OPT_ROOT_ABERTH, OPT_JACOBI_SWEEPS, OPT_TMA, OPT_EIG_ONESIDED,
   // kernel variants that only exist in a -DDOA_DEV_KNOBS build (libdoa_cuda_dev.so, used by tools/ and the bit-identity tests)
   OPT_WS_SPLIT, OPT_WS_STAGES, OPT_WS_NBUF, OPT_WS4, OPT_WS_TMA, OPT_WS_FILL, OPT_SCAN_TC_DBG, OPT_FUSED16,
   OPT_COUNT

@@ -4,7 +4,9 @@
 // gr-doa lib/MUSIC_lin_array_impl.cc:128-133 and lib/rootMUSIC_linear_array_impl.cc:112-116 (LAPACK cheevd there).
 //
 // jacobi_group_kernel<M> (M = 2, 4, 8, 16): M lanes per matrix, 32/M matrices per warp, everything in registers.
-// Lane j holds column j of the working matrix A and of the accumulated eigenvector matrix V.  One sweep is M-1
+// 8 and 16 elements: one-sided Jacobi on the Cholesky factor (eig_os_device.cuh).  2 and 4 elements, and any matrix the
+// factorisation rejects: the two-sided iteration of eig_device.cuh --
+// lane j holds column j of the working matrix A and of the accumulated eigenvector matrix V.  One sweep is M-1
 // steps of a round-robin tournament; the M/2 disjoint rotations of a step are applied together:
 //   columns (A J, V J): lane exchanges its column with its partner's through shuffles,
 //   rows    (J^H A)   : every lane rotates the element pairs (p_k, q_k) of its own column, indices static.
@@ -16,7 +18,7 @@
 // Outputs per frame: G = sum_{n<M-T} e_n e_n^H (eigenvalues ascending, column-major), the diagonal sums
 // u_l = sum_r G[r][r+l] (the Root-MUSIC polynomial / ULA null-spectrum coefficients, cf.
 // lib/rootMUSIC_linear_array_impl.cc:74-79), and the sorted eigenvalues.
-#include "eig_device.cuh"
+#include "eig_os_device.cuh"
 
 namespace doa {
 namespace {
@@ -41,8 +43,8 @@ jacobi_group_kernel(const float2* __restrict__ R, int T, int nframes, float2* __
     for (int i = 0; i < M; ++i) S[i + j * M] = src[i + j * M];
   }
   __syncwarp();
-  jacobi_group_solve<M>(S, j, T, max_sweeps, live, G ? G + mat * M * M : nullptr, u ? u + mat * M : nullptr,
-                        w ? w + mat * M : nullptr);
+  noise_subspace_solve<M>(S, j, T, max_sweeps, live, G ? G + mat * M * M : nullptr, u ? u + mat * M : nullptr,
+                          w ? w + mat * M : nullptr);
 }
 
 // ---- generic M: one CTA per matrix ----------------------------------------------------------------------------
@@ -246,7 +248,7 @@ template <int M>
 int launch_group(const float2* R, int T, int nframes, float2* G, float2* u, float* w, cudaStream_t st) {
   constexpr int per_block = JG_WARPS * (32 / M);
   const int blocks = (nframes + per_block - 1) / per_block;
-  jacobi_group_kernel<M><<<blocks, JG_WARPS * 32, 0, st>>>(R, T, nframes, G, u, w, dev_option(OPT_JACOBI_SWEEPS, M <= 8 ? 12 : 16));
+  jacobi_group_kernel<M><<<blocks, JG_WARPS * 32, 0, st>>>(R, T, nframes, G, u, w, eig_sweeps_arg(M));
   return 1;
 }
 

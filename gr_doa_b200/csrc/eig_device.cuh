@@ -121,6 +121,77 @@ __device__ __forceinline__ void jacobi_sweep(float2 (&a)[M], float2 (&v)[M], con
 }
 
 
+// Shared tail of the eigensolvers: lane j holds the unit eigenvector v of eigenvalue lam (any column order).  Ranks the
+// eigenvalues ascending (ties by column index), then writes (any may be null) the eigenvalues, the diagonal sums u and the
+// noise projector G = sum over the M - T smallest eigenvalues of e e^H.  `S` (M*M float2 of shared memory) is overwritten
+// unless use_S is false (a matrix whose results are not wanted: live must be false then).
+template <int M>
+__device__ __forceinline__ void subspace_outputs(float2* S, const int j, const int T, const bool live, const float2 (&v)[M],
+                                                 const float lam, float2* __restrict__ Gdst, float2* __restrict__ udst,
+                                                 float* __restrict__ wdst, const bool use_S = true) {
+  constexpr unsigned FULL = 0xffffffffu;
+  int rank = 0;
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    const float li = __shfl_sync(FULL, lam, i, M);
+    rank += (li < lam || (li == lam && i < j)) ? 1 : 0;
+  }
+  const int nn = M - T;
+  const bool noise = rank < nn;
+  if (wdst != nullptr && live) wdst[rank] = lam;
+
+  if (udst != nullptr) {
+    // u_l = sum_{noise n} sum_r e_n[r] conj(e_n[r+l])
+    float ux[M], uy[M];
+#pragma unroll
+    for (int l = 0; l < M; ++l) {
+      float sx = 0.0f, sy = 0.0f;
+#pragma unroll
+      for (int r = 0; r + l < M; ++r) {
+        sx = fmaf(v[r].x, v[r + l].x, sx); sx = fmaf(v[r].y, v[r + l].y, sx);
+        sy = fmaf(v[r].y, v[r + l].x, sy); sy = fmaf(-v[r].x, v[r + l].y, sy);
+      }
+      ux[l] = noise ? sx : 0.0f; uy[l] = noise ? sy : 0.0f;
+    }
+#pragma unroll
+    for (int o = M / 2; o >= 1; o >>= 1)
+#pragma unroll
+      for (int l = 0; l < M; ++l) {
+        ux[l] += __shfl_xor_sync(FULL, ux[l], o, M);
+        uy[l] += __shfl_xor_sync(FULL, uy[l], o, M);
+      }
+    float2 mine = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < M; ++l) if (l == j) mine = make_float2(ux[l], l == 0 ? 0.0f : uy[l]);
+    if (live) udst[j] = mine;
+  }
+
+  if (Gdst != nullptr) {
+    // eigenvectors to shared memory in ascending-eigenvalue order, then G(:, j) = sum_{n<nn} E(:, n) conj(E(j, n))
+#pragma unroll
+    for (int i = 0; i < M; ++i) if (use_S) S[i + rank * M] = v[i];     // use_S false: S must survive (nothing is stored either)
+    __syncwarp();
+    float2 gc[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) gc[i] = make_float2(0.f, 0.f);
+    for (int n = 0; n < nn; ++n) {
+      const float2 ej = S[j + n * M];
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        const float2 ei = S[i + n * M];
+        gc[i].x = fmaf(ei.x, ej.x, gc[i].x); gc[i].x = fmaf(ei.y, ej.y, gc[i].x);
+        gc[i].y = fmaf(ei.y, ej.x, gc[i].y); gc[i].y = fmaf(-ei.x, ej.y, gc[i].y);
+      }
+    }
+    if (live) {
+      float2* dst = Gdst + (size_t)j * M;
+#pragma unroll
+      for (int i = 0; i < M; ++i) dst[i] = gc[i];
+    }
+  }
+}
+
+
 // One M x M Hermitian matrix by M lanes (lane j = column j).  `S` is this matrix's M*M float2 staging area in shared
 // memory; on entry it holds the input column-major (only the upper triangle is used, like cheevd 'U'), it is
 // overwritten.  Outputs (any may be null): G column-major M x M, u[M] diagonal sums, w[M] eigenvalues ascending; they
@@ -174,69 +245,11 @@ __device__ __forceinline__ void jacobi_group_solve(float2* S, const int j, const
 #pragma unroll
     for (int i = 0; i < M; ++i) { v[i].x *= sc; v[i].y *= sc; }
   }
-  // eigenvalue of this lane's column, its ascending rank (ties by column index)
+  // eigenvalue of this lane's column
   float lam = 0.0f;
 #pragma unroll
   for (int i = 0; i < M; ++i) lam = (i == j) ? a[i].x : lam;
-  int rank = 0;
-#pragma unroll
-  for (int i = 0; i < M; ++i) {
-    const float li = __shfl_sync(FULL, lam, i, M);
-    rank += (li < lam || (li == lam && i < j)) ? 1 : 0;
-  }
-  const int nn = M - T;
-  const bool noise = rank < nn;
-  if (wdst != nullptr && live) wdst[rank] = lam;
-
-  if (udst != nullptr) {
-    // u_l = sum_{noise n} sum_r e_n[r] conj(e_n[r+l])
-    float ux[M], uy[M];
-#pragma unroll
-    for (int l = 0; l < M; ++l) {
-      float sx = 0.0f, sy = 0.0f;
-#pragma unroll
-      for (int r = 0; r + l < M; ++r) {
-        sx = fmaf(v[r].x, v[r + l].x, sx); sx = fmaf(v[r].y, v[r + l].y, sx);
-        sy = fmaf(v[r].y, v[r + l].x, sy); sy = fmaf(-v[r].x, v[r + l].y, sy);
-      }
-      ux[l] = noise ? sx : 0.0f; uy[l] = noise ? sy : 0.0f;
-    }
-#pragma unroll
-    for (int o = M / 2; o >= 1; o >>= 1)
-#pragma unroll
-      for (int l = 0; l < M; ++l) {
-        ux[l] += __shfl_xor_sync(FULL, ux[l], o, M);
-        uy[l] += __shfl_xor_sync(FULL, uy[l], o, M);
-      }
-    float2 mine = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int l = 0; l < M; ++l) if (l == j) mine = make_float2(ux[l], l == 0 ? 0.0f : uy[l]);
-    if (live) udst[j] = mine;
-  }
-
-  if (Gdst != nullptr) {
-    // eigenvectors to shared memory in ascending-eigenvalue order, then G(:, j) = sum_{n<nn} E(:, n) conj(E(j, n))
-#pragma unroll
-    for (int i = 0; i < M; ++i) S[i + rank * M] = v[i];
-    __syncwarp();
-    float2 gc[M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) gc[i] = make_float2(0.f, 0.f);
-    for (int n = 0; n < nn; ++n) {
-      const float2 ej = S[j + n * M];
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-        const float2 ei = S[i + n * M];
-        gc[i].x = fmaf(ei.x, ej.x, gc[i].x); gc[i].x = fmaf(ei.y, ej.y, gc[i].x);
-        gc[i].y = fmaf(ei.y, ej.x, gc[i].y); gc[i].y = fmaf(-ei.x, ej.y, gc[i].y);
-      }
-    }
-    if (live) {
-      float2* dst = Gdst + (size_t)j * M;
-#pragma unroll
-      for (int i = 0; i < M; ++i) dst[i] = gc[i];
-    }
-  }
+  subspace_outputs<M>(S, j, T, live, v, lam, Gdst, udst, wdst);
 }
 
 }  // namespace

@@ -14,7 +14,7 @@
 // the three-kernel path (tested).  Measured on B200 at cfg3: 2.21 ms (three kernels) -> 1.64 ms; a phase-structured variant
 // (two CTAs/SM alternating stream / Jacobi / scan phases behind __syncthreads) measured 2.02 ms and was dropped.
 #include "cov_device.cuh"
-#include "eig_device.cuh"
+#include "eig_os_device.cuh"
 #include "scan_device.cuh"
 
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
@@ -245,9 +245,9 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
         if (G_out != nullptr) {
           // split form: the noise projector and its diagonal sums go to global memory, the scan runs as its own kernel (scan_tc.cu)
           const long long f = lo + (long long)t * TILE + min(g, nt - 1);
-          jacobi_group_solve<M>(Rbuf + ((size_t)b * TILE + g) * MM, j, T, max_sweeps, g < nt, G_out + f * MM, u_out + f * M, nullptr);
+          noise_subspace_solve<M>(Rbuf + ((size_t)b * TILE + g) * MM, j, T, max_sweeps, g < nt, G_out + f * MM, u_out + f * M, nullptr);
         } else {
-          jacobi_group_solve<M>(Rbuf + ((size_t)b * TILE + g) * MM, j, T, max_sweeps, g < nt, Gs + g * MM, us + g * M, nullptr);
+          noise_subspace_solve<M>(Rbuf + ((size_t)b * TILE + g) * MM, j, T, max_sweeps, g < nt, Gs + g * MM, us + g * M, nullptr);
         }
       }
       // A consumer warp owns its 32/M matrices end to end (Jacobi -> G/u -> scan), so nothing but the tile buffer is shared:
@@ -309,7 +309,7 @@ int launch_ws_cfg2(const S* in, long long fs, long long cs, int N, int nframes, 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return 0;
   }
-  kern<<<grid, (WS_P + WS_C) * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, 12, tb.zpair, tb.z, tb.V, tb.xaxis, tb.P,
+  kern<<<grid, (WS_P + WS_C) * 32, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, eig_sweeps_arg(M), tb.zpair, tb.z, tb.V, tb.xaxis, tb.P,
                                                K, out_val, out_loc, out_bin, gains, G_out, u_out, tmap);
   return 1;
 }

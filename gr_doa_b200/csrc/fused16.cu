@@ -19,7 +19,7 @@
 // picking then runs on the tensor cores (scan_tc.cu) from G and u: two launches for the whole chain.
 // Device code and per-entry operation order are the stage kernels': same bits as the three-kernel path (tested).
 #include "cov_device.cuh"
-#include "eig_device.cuh"
+#include "eig_os_device.cuh"
 
 #include <algorithm>
 
@@ -95,7 +95,7 @@ chain16_kernel(const S* __restrict__ in, long long frame_stride, long long chan_
       const int slot = cw * 2 + g;
       const bool live = slot < nt;
       const long long f = lo + (long long)t * F16_TILE + (live ? slot : 0);
-      jacobi_group_solve<16>(Rbuf + ((size_t)b * F16_TILE + slot) * MM, j, T, max_sweeps, live, G_out + f * MM, u_out + f * 16, nullptr);
+      noise_subspace_solve<16>(Rbuf + ((size_t)b * F16_TILE + slot) * MM, j, T, max_sweeps, live, G_out + f * MM, u_out + f * 16, nullptr);
       __syncwarp();
       if (t + F16_NBUF < ntiles) { __threadfence_block(); bar_arrive16(F16_BAR_EMPTY + b, F16_THREADS); }
     }
@@ -116,7 +116,7 @@ int launch16(const S* in, long long fs, long long cs, int N, int nframes, int av
   sms = std::max(1, sms - std::max(0, dev_option(OPT_SMS_RESERVE, 0)));
   const int grid = std::max(1, std::min(sms, (nframes + NPAIR - 1) / NPAIR));
   const float scale = (float)(1.0 / N) * in_scale2, bscale = (float)(0.5 / N);
-  kern<<<grid, F16_THREADS, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, dev_option(OPT_JACOBI_SWEEPS, 16), G, u, gains);
+  kern<<<grid, F16_THREADS, smem, st>>>(in, fs, cs, N, nframes, avg, scale, bscale, T, eig_sweeps_arg(16), G, u, gains);
   return 1;
 }
 
