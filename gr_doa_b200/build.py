@@ -1,4 +1,4 @@
-"""Build libdoa_cuda.so in-tree with nvcc for sm_100a (no torch, no cmake: four .cu files, one shared library).
+"""Build libdoa_cuda.so in-tree with nvcc for sm_100a (no torch, no cmake: a handful of .cu files, one shared library).
 
     python -m gr_doa_b200.build [--force]
 
@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libdoa_cuda.so")
-SOURCES = ["doa_cuda.cu", "cov.cu", "eig.cu", "scan.cu", "root.cu", "fused.cu", "herk_tc.cu", "scan_tc.cu", "fused16.cu"]
+SOURCES = ["doa_cuda.cu", "cov.cu", "eig.cu", "eig_block.cu", "scan.cu", "root.cu", "fused.cu", "herk_tc.cu", "scan_tc.cu", "fused16.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
 

@@ -33,6 +33,8 @@ int launch_covariance_tc(const float2* in, long long frame_stride, long long cha
 //   u[f][l]       = sum_r G[r][r+l], l = 0..M-1          (complex, u[0] real; may be null)
 //   w[f][M]       eigenvalues ascending                  (may be null)
 int launch_noise_subspace(const float2* R, int M, int T, int nframes, float2* G, float2* u, float* w, cudaStream_t st);
+// its CTA-per-matrix form for 17..64 elements (eig_block.cu); launch_noise_subspace dispatches to it
+int launch_noise_subspace_block(const float2* R, int M, int T, int nframes, float2* G, float2* u, float* w, cudaStream_t st);
 
 // calibrate_lin_array: from the one-source noise projector G and the pilot steering vector v [M] to the unit-norm
 // gain/phase estimate conj(v) o u_S per frame ([nframes][M]).

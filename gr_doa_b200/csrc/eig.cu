@@ -13,7 +13,7 @@
 // The tournament is unrolled at compile time so no register array is indexed dynamically.
 // Like cheevd('U') only the upper triangle of the input is read.
 //
-// jacobi_block_kernel (any M <= 64): one CTA per matrix in shared memory, same tournament, threads over (pair,row).
+// Any other M <= 64: one CTA per matrix in shared memory (eig_block.cu).
 //
 // Outputs per frame: G = sum_{n<M-T} e_n e_n^H (eigenvalues ascending, column-major), the diagonal sums
 // u_l = sum_r G[r][r+l] (the Root-MUSIC polynomial / ULA null-spectrum coefficients, cf.
@@ -24,9 +24,12 @@ namespace doa {
 namespace {
 
 constexpr int JG_WARPS = 4;
+#ifndef DOA_JG_MINBLOCKS
+#define DOA_JG_MINBLOCKS 5   // 96 registers at 16 elements: 20 warps per SM instead of 16 (1.22 -> 1.12 ms per 65,536; 6 blocks: no further gain)
+#endif
 
 template <int M>
-__global__ void __launch_bounds__(JG_WARPS * 32)
+__global__ void __launch_bounds__(JG_WARPS * 32, DOA_JG_MINBLOCKS)
 jacobi_group_kernel(const float2* __restrict__ R, int T, int nframes, float2* __restrict__ G, float2* __restrict__ u,
                     float* __restrict__ w, int max_sweeps) {
   constexpr int GPW = 32 / M;                 // matrices per warp
@@ -45,135 +48,6 @@ jacobi_group_kernel(const float2* __restrict__ R, int T, int nframes, float2* __
   __syncwarp();
   noise_subspace_solve<M>(S, j, T, max_sweeps, live, G ? G + mat * M * M : nullptr, u ? u + mat * M : nullptr,
                           w ? w + mat * M : nullptr);
-}
-
-// ---- generic M: one CTA per matrix ----------------------------------------------------------------------------
-// A and V live in shared memory with an odd leading dimension (M+1 float2) so that both the column phase (threads walk a
-// column) and the row phase (threads walk a row, stride LD) are bank-conflict free.
-constexpr int JB_THREADS = 512;
-
-__global__ void __launch_bounds__(JB_THREADS)
-jacobi_block_kernel(const float2* __restrict__ R, int M, int T, int nframes, float2* __restrict__ G,
-                    float2* __restrict__ u, float* __restrict__ w, int max_sweeps) {
-  extern __shared__ float2 sm[];
-  const int LD = M | 1;              // odd leading dimension
-  float2* A = sm;                    // element (i, j) at A[i + j*LD]
-  float2* V = A + (size_t)M * LD;
-  float* rc = reinterpret_cast<float*>(V + (size_t)M * LD);   // rotation params: c[32], sx[32], sy[32]
-  int* pp = reinterpret_cast<int*>(rc + 3 * 32);              // p[32], q[32]
-  float* lam = reinterpret_cast<float*>(pp + 2 * 32);         // [64]
-  int* rk = reinterpret_cast<int*>(lam + 64);                 // [64]
-  __shared__ float red[2];
-  const int tid = threadIdx.x;
-  const int Mp = (M + 1) & ~1, HP = Mp / 2;
-
-  for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
-    const float2* src = R + (long long)f * M * M;
-    for (int e = tid; e < M * M; e += JB_THREADS) {
-      const int i = e % M, j = e / M;
-      float2 x;
-      if (i < j) x = src[i + j * M];                      // upper triangle only, like cheevd 'U'
-      else if (i == j) x = make_float2(src[e].x, 0.f);
-      else { const float2 t = src[j + i * M]; x = make_float2(t.x, -t.y); }
-      A[i + j * LD] = x;
-      V[i + j * LD] = make_float2(i == j ? 1.f : 0.f, 0.f);
-    }
-    __syncthreads();
-    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-      if (tid == 0) { red[0] = 0.f; red[1] = 0.f; }
-      __syncthreads();
-      float off = 0.f, dg = 0.f;
-      for (int e = tid; e < M * M; e += JB_THREADS) {
-        const int i = e % M, j = e / M;
-        const float2 a = A[i + j * LD];
-        const float m2 = a.x * a.x + a.y * a.y;
-        if (i == j) dg += m2; else off += m2;
-      }
-      for (int o = 16; o >= 1; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dg += __shfl_xor_sync(0xffffffffu, dg, o); }
-      if ((tid & 31) == 0) { atomicAdd(&red[0], off); atomicAdd(&red[1], dg); }
-      __syncthreads();
-      const bool conv = red[0] <= red[1] * (1.5e-14f * M * M);
-      __syncthreads();
-      if (conv) break;
-      for (int s = 0; s < Mp - 1; ++s) {
-        if (tid < HP) {
-          int a_ = (tid == 0) ? s : (s + tid) % (Mp - 1);
-          int b_ = (tid == 0) ? (Mp - 1) : (s - tid + (Mp - 1)) % (Mp - 1);
-          int p = min(a_, b_), q = max(a_, b_);
-          Rot r; r.c = 1.f; r.sx = 0.f; r.sy = 0.f;
-          if (q < M) r = make_rotation(A[p + p * LD].x, A[q + q * LD].x, A[p + q * LD]);
-          else { p = -1; }   // pair with the padding index: skip
-          rc[tid] = r.c; rc[32 + tid] = r.sx; rc[64 + tid] = r.sy; pp[tid] = p; pp[32 + tid] = q;
-        }
-        __syncthreads();
-        for (int it = tid; it < HP * M; it += JB_THREADS) {   // columns of A and V: A <- A J, V <- V J
-          const int k = it / M, i = it % M;
-          const int p = pp[k], q = pp[32 + k];
-          if (p < 0) continue;
-          const float c = rc[k], sx = rc[32 + k], sy = rc[64 + k];
-          {
-            const float2 x = A[i + p * LD], y = A[i + q * LD];
-            A[i + p * LD] = make_float2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
-            A[i + q * LD] = make_float2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
-          }
-          {
-            const float2 x = V[i + p * LD], y = V[i + q * LD];
-            V[i + p * LD] = make_float2(c * x.x - (sx * y.x + sy * y.y), c * x.y - (sx * y.y - sy * y.x));
-            V[i + q * LD] = make_float2(sx * x.x - sy * x.y + c * y.x, sx * x.y + sy * x.x + c * y.y);
-          }
-        }
-        __syncthreads();
-        for (int it = tid; it < HP * M; it += JB_THREADS) {   // rows of A: A <- J^H A
-          const int k = it / M, i = it % M;
-          const int p = pp[k], q = pp[32 + k];
-          if (p < 0) continue;
-          const float c = rc[k], sx = rc[32 + k], sy = rc[64 + k];
-          const float2 x = A[p + i * LD], y = A[q + i * LD];
-          A[p + i * LD] = make_float2(c * x.x - (sx * y.x - sy * y.y), c * x.y - (sx * y.y + sy * y.x));
-          A[q + i * LD] = make_float2(sx * x.x + sy * x.y + c * y.x, sx * x.y - sy * x.x + c * y.y);
-        }
-        __syncthreads();
-      }
-    }
-    // unit eigenvectors (the MUFU rotations let column norms drift by O(1e-7) per rotation), eigenvalues, ranks
-    for (int j = tid; j < M; j += JB_THREADS) {
-      float n2 = 0.f;
-      for (int i = 0; i < M; ++i) { const float2 v = V[i + j * LD]; n2 = fmaf(v.x, v.x, fmaf(v.y, v.y, n2)); }
-      const float sc = 1.0f / sqrtf(n2);
-      for (int i = 0; i < M; ++i) { V[i + j * LD].x *= sc; V[i + j * LD].y *= sc; }
-      lam[j] = A[j + j * LD].x;
-    }
-    __syncthreads();
-    for (int j = tid; j < M; j += JB_THREADS) {
-      int r = 0;
-      for (int i = 0; i < M; ++i) r += (lam[i] < lam[j] || (lam[i] == lam[j] && i < j)) ? 1 : 0;
-      rk[r] = j;   // rk[rank] = column holding that eigenvalue
-      if (w) w[(long long)f * M + r] = lam[j];
-    }
-    __syncthreads();
-    const int nn = M - T;
-    // G into A's storage (A no longer needed)
-    for (int e = tid; e < M * M; e += JB_THREADS) {
-      const int i = e % M, j = e / M;
-      float gx = 0.f, gy = 0.f;
-      for (int n = 0; n < nn; ++n) {
-        const float2 ei = V[i + rk[n] * LD], ej = V[j + rk[n] * LD];
-        gx = fmaf(ei.x, ej.x, gx); gx = fmaf(ei.y, ej.y, gx);
-        gy = fmaf(ei.y, ej.x, gy); gy = fmaf(-ei.x, ej.y, gy);
-      }
-      A[i + j * LD] = make_float2(gx, gy);
-      if (G) G[(long long)f * M * M + e] = make_float2(gx, gy);
-    }
-    __syncthreads();
-    if (u) {
-      for (int l = tid; l < M; l += JB_THREADS) {
-        float sx = 0.f, sy = 0.f;
-        for (int r = 0; r + l < M; ++r) { sx += A[r + (r + l) * LD].x; sy += A[r + (r + l) * LD].y; }
-        u[(long long)f * M + l] = make_float2(sx, l == 0 ? 0.f : sy);
-      }
-    }
-    __syncthreads();
-  }
 }
 
 // calibrate_lin_array (gr-doa lib/calibrate_lin_array_impl.cc:112-126).  With ONE source the noise
@@ -264,15 +138,7 @@ int launch_noise_subspace(const float2* R, int M, int T, int nframes, float2* G,
     default: break;
   }
   if (M > 64 || M < 2) return DOA_CUDA_EINVAL;
-  const size_t smem = (size_t)2 * M * (M | 1) * sizeof(float2) + (3 * 32) * sizeof(float) + (2 * 32) * sizeof(int) +
-                      64 * sizeof(float) + 64 * sizeof(int);
-  cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int blocks = min(nframes, sms * 4);
-  jacobi_block_kernel<<<blocks, JB_THREADS, smem, st>>>(R, M, T, nframes, G, u, w, 20);
-  return 1;
+  return launch_noise_subspace_block(R, M, T, nframes, G, u, w, st);
 }
 
 int launch_calibrate_emit(const float2* R, const float2* G, const float2* v, int M, int nframes, float2* out, cudaStream_t st) {

@@ -16,8 +16,8 @@
 // no exchange of rotation parameters.  Squared column norms are recomputed at the start of a sweep and carried through it by
 // the rotation's own update (app - t|apq|, aqq + t|apq|).
 //
-// R + delta I (delta = 2^-14 trace R: below the noise floor of any covariance this path is given, far above fp32 rounding of a
-// rank-deficient one) is what gets factored; eigenvectors are unchanged, eigenvalues are reported as |column|^2 - delta.  A
+// R / 2^e + delta I (2^e the trace's power of two, delta = 2^-14 of the scaled trace: below the noise floor of any covariance this path is given, far above fp32 rounding of a
+// rank-deficient one) is what gets factored; eigenvectors are unchanged, eigenvalues are reported as 2^e (|column|^2 - delta).  A
 // matrix whose factorisation meets a non-positive pivot (not a covariance: indefinite, zero or non-finite input) is reported
 // back to the caller with its staging area restored, and the caller runs the two-sided solver on it (noise_subspace_solve).
 #pragma once
@@ -31,24 +31,31 @@ __device__ __forceinline__ f32x2 shfl2(f32x2 v, int src, int width) {
   return __shfl_sync(0xffffffffu, v, src, width);
 }
 
-// Rotation for the pair's Gram 2x2 [[app, apq], [conj(apq), aqq]] (see make_rotation), also returning t |apq| for the
-// norm update and whether the pair is still visibly non-orthogonal (|apq|^2 > tau^2 app aqq).
+// Bare MUFU ops: rsqrtf() / __frcp_rn() wrap the unit in denormal scaling and a Newton step with a slow-path branch (12 extra
+// instructions on the rotation's serial chain); the arguments here are normal numbers and 1-ulp results are all the rotation
+// needs (see make_rotation).
+__device__ __forceinline__ float mufu_rsq(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// Rotation for the pair's Gram 2x2 [[app, apq], [conj(apq), aqq]] (the one of make_rotation: t = sgn(d) 2b / (|d| + sqrt(d^2 + 4 b^2)),
+// d = aqq - app, b = |apq|; c = 1/sqrt(1 + t^2); sigma = t c apq / b), also returning t b for the norm update and whether the
+// pair is still visibly non-orthogonal (b^2 > tau^2 app aqq).  Written for a short dependent chain: three special-function ops
+// in series, no division, no clamping -- the caller's matrix is scaled to unit trace, so d^2 + 4 b^2 <= 20.
 __device__ __forceinline__ Rot make_rotation_os(float app, float aqq, float2 apq, bool frozen, float& tb, bool& dirty) {
   const float b2 = fmaf(apq.x, apq.x, apq.y * apq.y);
-  const bool act = b2 > 1e-36f && !frozen;                   // branch-free: an inactive pair gets the exact identity
+  const bool act = b2 > 1e-30f && !frozen;                   // branch-free: an inactive pair gets the exact identity
   dirty = act && b2 > 1e-10f * (app * aqq);                  // tau = 1e-5, see the stopping rule below
-  const float inv_b = rsqrtf(act ? b2 : 1.0f);
-  float zeta = 0.5f * (aqq - app) * inv_b;
-  zeta = fminf(fmaxf(zeta, -1e18f), 1e18f);
-  const float az = fabsf(zeta);
-  const float w = fmaf(zeta, zeta, 1.0f);
-  float t = __frcp_rn(az + w * rsqrtf(w));
-  t = (zeta < 0.0f) ? -t : t;
-  t = act ? t : 0.0f;
-  const float c = rsqrtf(fmaf(t, t, 1.0f));                  // t = 0 -> exactly 1
+  const float b2s = act ? b2 : 1.0f;
+  const float inv_b = mufu_rsq(b2s);
+  const float d = aqq - app;
+  const float r2 = fmaf(d, d, 4.0f * b2s);
+  const float den = fmaf(r2, mufu_rsq(r2), fabsf(d));        // |d| + sqrt(d^2 + 4 b^2) >= 2 b > 0
+  const float tbm = (2.0f * b2s) * mufu_rcp(den);            // |t| b
+  tb = act ? ((d < 0.0f) ? -tbm : tbm) : 0.0f;
+  const float t = tb * inv_b;
+  const float c = mufu_rsq(fmaf(t, t, 1.0f));                // t = 0 -> exactly 1
   const float sb = t * c * inv_b;
   Rot r; r.c = c; r.sx = sb * apq.x; r.sy = sb * apq.y;
-  tb = t * (b2 * inv_b);
   return r;
 }
 
@@ -69,7 +76,11 @@ __device__ __forceinline__ bool jacobi_os_solve(float2* S, const int j, const in
 #pragma unroll
   for (int o = M / 2; o >= 1; o >>= 1) tr += __shfl_xor_sync(FULL, tr, o, M);
   bool ok = tr > 0.0f && tr < 3.0e38f;                        // false for NaN as well
-  const float delta = ok ? tr * (1.0f / 16384.0f) : 1.0f;
+  // exact power-of-two scaling to a trace in [1, 2): every later quantity is bounded (column norms^2 <= 2 + delta), the
+  // results are those of the unscaled matrix bit for bit
+  const int ex = min(max((__float_as_int(tr) >> 23) & 0xff, 1), 253);
+  const float scl = __int_as_float((254 - ex) << 23), unscl = __int_as_float(ex << 23);
+  const float delta = ok ? (tr * scl) * (1.0f / 16384.0f) : 1.0f;
 
   // ---- Cholesky, lane j = row j of L.  Slot S[c + j*M] (c <= j) holds A(c, j) = conj(A(j, c)) until this lane replaces it
   // with L(j, c): the lower factor is written row-major over the upper triangle it was computed from, and only lane j ever
@@ -82,7 +93,7 @@ __device__ __forceinline__ bool jacobi_os_solve(float2* S, const int j, const in
     if (c <= j) {
       const float2 a = S[c + j * M];
       a0[c] = a;
-      acc = make_float2(c == j ? a.x + delta : a.x, c == j ? 0.0f : -a.y);
+      acc = make_float2(c == j ? fmaf(a.x, scl, delta) : a.x * scl, c == j ? 0.0f : -a.y * scl);
     }
 #pragma unroll
     for (int k = 0; k < c; ++k) {                             // acc -= L(j, k) conj(L(c, k)); row c is complete up to k < c
@@ -130,19 +141,14 @@ __device__ __forceinline__ bool jacobi_os_solve(float2* S, const int j, const in
     bool dirty_any = false;
 #pragma unroll 1
     for (int st = 0; st < R; ++st) {
-      // tournament of eig_device.cuh: pair 0 is (st, R), pair k is ((st + k) mod R, (st - k) mod R); the first is the a-role
-      int partner; bool is_a;
-      if (j == R) { partner = st; is_a = false; }
-      else {
-        int jr = j - st; jr += (jr < 0) ? R : 0;
-        if (jr == 0) { partner = R; is_a = true; }
-        else {
-          is_a = jr < H;
-          partner = is_a ? (st - jr) : (st + (R - jr));
-          partner += (partner < 0) ? R : 0;
-          partner -= (partner >= R) ? R : 0;
-        }
-      }
+      // round-robin tournament on the ring Z_R (index R sits out): in step st ring index r meets (2 st - r) mod R, and the
+      // index that would meet itself meets R.  The lower index of a pair plays the a-role (the "p" of the rotation formulas).
+      int partner = 2 * st - j;
+      partner += (partner < 0) ? R : 0;
+      partner -= (partner >= R) ? R : 0;
+      partner = (partner == j) ? R : partner;
+      partner = (j == R) ? st : partner;
+      const bool is_a = j < partner;
       f32x2 xr[H], xi[H];
 #pragma unroll
       for (int h = 0; h < H; ++h) { xr[h] = shfl2(wr[h], partner, M); xi[h] = shfl2(wi[h], partner, M); }
@@ -197,7 +203,7 @@ __device__ __forceinline__ bool jacobi_os_solve(float2* S, const int j, const in
     upk2(wr[h], r0, r1); upk2(wi[h], i0, i1);
     v[2 * h] = make_float2(r0 * sc, i0 * sc); v[2 * h + 1] = make_float2(r1 * sc, i1 * sc);
   }
-  subspace_outputs<M>(S, j, T, live && ok, v, n2 - delta, Gdst, udst, wdst, ok);
+  subspace_outputs<M>(S, j, T, live && ok, v, (n2 - delta) * unscl, Gdst, udst, wdst, ok);
   return ok;
 }
 

@@ -496,3 +496,76 @@ def test_every_output_slot_written_when_null_spectrum_rounds_nonpositive(doa, to
     assert not (nan[:, :-1] & ~nan[:, 1:]).any()                                 # NaN entries come last
     fin = ~nan.any(axis=1)
     assert (val[fin, 0] == 0.0).all() and (np.diff(val[fin], axis=1) <= 0).all()  # 0 dB first, descending
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The 8- / 16-element eigensolver: one-sided Jacobi on the Cholesky factor (csrc/eig_os_device.cuh), two-sided Jacobi
+# (csrc/eig_device.cuh) as the fallback for matrices the factorisation rejects and behind option "eig_onesided" = 0.
+def _projector_f64(R, M, T):
+    """float64 noise projector of column-major [B][M*M] covariances (upper triangle, like cheevd 'U')."""
+    A = R.reshape(-1, M, M).transpose(0, 2, 1).astype(np.complex128)
+    A = np.triu(A) + np.triu(A, 1).conj().transpose(0, 2, 1)
+    w, V = np.linalg.eigh(A)
+    En = V[:, :, : M - T]
+    return En @ En.conj().transpose(0, 2, 1), w
+
+
+@pytest.mark.parametrize("M,T,N,snr", [(16, 3, 1024, 10.0), (16, 3, 1024, 40.0), (8, 3, 2048, 10.0), (8, 7, 256, 0.0), (16, 15, 64, -5.0)])
+def test_onesided_eigensolver_is_as_accurate_as_lapack(doa, oracle, torch_cuda, M, T, N, snr):
+    from gr_doa_b200 import synth
+    B = 1024
+    th = [20.0 + 140.0 * i / max(T - 1, 1) for i in range(T)]
+    fr, _ = synth.frames_numpy(B, M, N, th, snr_db=snr, jitter_deg=2.0, seed=77)
+    R = oracle.autocorrelate_frames(fr, 0, nthreads=4)
+    G64, w64 = _projector_f64(R, M, T)
+    G_o, _ = oracle.noise_projector(R, T, M, nthreads=4)                       # LAPACK cheevd in float32
+    err_ref = np.abs(G_o.reshape(B, M, M).transpose(0, 2, 1) - G64).max(axis=(1, 2))
+    mus = doa.MUSIC_lin_array(0.5, T, M, 256, max_frames=B)
+    errs = {}
+    for onesided in (1, 0):
+        mus.set_option("eig_onesided", onesided)
+        G, u, w = [t.cpu().numpy() for t in mus.noise_subspace_device(torch_cuda.from_numpy(R).cuda())]
+        errs[onesided] = np.abs(G.reshape(B, M, M).transpose(0, 2, 1) - G64).max(axis=(1, 2))
+        assert np.abs(w - w64).max() <= 1e-5 * np.abs(w64).max()
+        # the diagonal sums are those of the projector that was stored
+        Gm = G.reshape(B, M, M).transpose(0, 2, 1)
+        for l in (0, 1, M - 1):
+            ul = np.stack([np.trace(Gm[b], offset=l) for b in range(0, B, 64)])
+            assert np.abs(ul - u[::64, l]).max() <= 2e-6 * M
+    # no heavier tail than LAPACK's float32 path (the stopping rule's job) and a mean within 3x of it
+    assert errs[1].max() <= max(4.0 * err_ref.max(), 2e-6), (errs[1].max(), err_ref.max())
+    assert errs[1].mean() <= 3.0 * err_ref.mean() + 1e-8, (errs[1].mean(), err_ref.mean())
+    assert errs[1].mean() <= 1.25 * errs[0].mean() + 1e-8                     # and not worse than the solver it replaces
+
+
+@pytest.mark.parametrize("M", [8, 16])
+def test_onesided_eigensolver_falls_back_on_matrices_that_are_not_covariances(doa, torch_cuda, M):
+    """Indefinite, zero and non-finite inputs fail the Cholesky factorisation and are redone by the two-sided solver with its
+    bits; a positive definite frame next to them in the same warp keeps the result it has in any other company."""
+    torch = torch_cuda
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    B, T = 64, 1
+    A = torch.randn((B, M, M), generator=g, device="cuda") + 1j * torch.randn((B, M, M), generator=g, device="cuda")
+    indef = (A + A.conj().transpose(1, 2)).to(torch.complex64)
+    spd = (A @ A.conj().transpose(1, 2) / M + 0.5 * torch.eye(M, device="cuda")).to(torch.complex64)
+    zero = torch.zeros_like(indef)
+    nanm = indef.clone(); nanm[::2, 0, 0] = float("nan")
+    mus = doa.MUSIC_lin_array(0.5, T, M, 256, max_frames=4 * B)
+
+    def run(mat, onesided):
+        mus.set_option("eig_onesided", onesided)
+        Rin = mat.transpose(1, 2).contiguous().view(mat.shape[0], M * M)
+        return [torch.nan_to_num(torch.view_as_real(t) if t.is_complex() else t, nan=7.0).clone() for t in mus.noise_subspace_device(Rin)]
+
+    for mat in (indef, zero, nanm):
+        assert all(torch.equal(a, b) for a, b in zip(run(mat, 1), run(mat, 0)))
+    alone = run(spd, 1)
+    mixed = torch.stack([spd[i // 2] if i % 2 == 0 else indef[i // 2] for i in range(2 * B)])       # every warp holds both kinds
+    got = run(mixed, 1)
+    want_bad = run(indef, 0)
+    for k in range(3):
+        assert torch.equal(got[k][0::2], alone[k]) and torch.equal(got[k][1::2], want_bad[k])
+    # and the positive definite ones are right
+    G64, _ = _projector_f64(spd.transpose(1, 2).contiguous().view(B, M * M).cpu().numpy(), M, T)
+    Gg = torch.view_as_complex(alone[0]).cpu().numpy().reshape(B, M, M).transpose(0, 2, 1)
+    assert np.abs(Gg - G64).max() <= 5e-6
