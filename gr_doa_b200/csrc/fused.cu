@@ -438,6 +438,8 @@ int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_
     case 61024: return launch_ws_cfg<8, 6, 10, 2, 4>(WS_ARGS);
     case 61034: return launch_ws_cfg<8, 6, 10, 3, 4>(WS_ARGS);
     case 90724: return launch_ws_cfg<8, 9, 7, 2, 4>(WS_ARGS);
+    case 100624: return launch_ws_cfg<8, 10, 6, 2, 4>(WS_ARGS);
+    case 90734: return launch_ws_cfg<8, 9, 7, 3, 4>(WS_ARGS);
     default: return launch_ws_cfg<8, 8, 8, 2, 4>(WS_ARGS);
   }
 #endif

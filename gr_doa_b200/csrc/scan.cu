@@ -47,6 +47,53 @@ scan_peaks_kernel(const float2* __restrict__ u, const float2* __restrict__ G, co
 // walker / merge / refinement on that table.
 constexpr int SCAN_WIDE_THREADS = 256;
 
+// The refinement (v^H G v with the reference's operation order at the +-2 bins around each of the K winners and around the
+// global minimum) is M^2 complex multiply-adds per bin: at 64 elements a lane that evaluates it alone walks 4,096 dependent
+// steps through global memory, and with one warp at work the CTA spent 90 % of its time there (1.02 ms for 512 frames).  The
+// reference's order only chains the additions WITHIN a column of G (row sum over r, then the sum of the M column results over
+// c), so the M column sums of a bin are independent: warp 0 posts its 32 (slot, bin) requests of a round to shared memory, all
+// eight warps take (request, column) pairs -- G staged once per frame in shared memory with an odd leading dimension -- and
+// the requesting lane adds the M column results in column order.  Operation for operation q_faithful: identical bits.
+__device__ __forceinline__ void wide_bar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(SCAN_WIDE_THREADS) : "memory"); }
+
+struct CoopEval {
+  int* req;            // [32] bin requested by lane l of warp 0, or -1
+  float* pxs;          // [32][M + 1] column results of request l
+  const float2* Gs;    // [M][M + 1] the frame's projector, column c at Gs + c * (M + 1)
+  const float2* Vtab;
+  int M;
+  // one round by every thread of the CTA (warp 0 between its two barriers, the others in their helper loop)
+  __device__ __forceinline__ void round_work() const {
+    const int LD = M + 1;
+    for (int id = threadIdx.x; id < 32 * M; id += SCAN_WIDE_THREADS) {
+      const int rq = id / M, c = id - rq * M;
+      const int b = req[rq];
+      if (b < 0) continue;
+      const float2* v = Vtab + (size_t)b * M;
+      const float2* Gc = Gs + (size_t)c * LD;
+      float rx = 0.0f, ry = 0.0f;
+#pragma unroll 8
+      for (int r = 0; r < M; ++r) {
+        const float2 g = Gc[r]; const float2 vr = v[r];
+        const float px = __fsub_rn(__fmul_rn(vr.x, g.x), __fmul_rn(-vr.y, g.y));
+        const float py = __fadd_rn(__fmul_rn(vr.x, g.y), __fmul_rn(-vr.y, g.x));
+        rx = __fadd_rn(rx, px); ry = __fadd_rn(ry, py);
+      }
+      const float2 vc = v[c];
+      pxs[rq * LD + c] = __fsub_rn(__fmul_rn(rx, vc.x), __fmul_rn(ry, vc.y));
+    }
+  }
+  __device__ __forceinline__ float operator()(bool valid, int b, int lane) const {
+    req[lane] = valid ? b : -1;
+    wide_bar(1);                                  // requests posted
+    round_work();
+    wide_bar(2);                                  // column results ready
+    float qx = 0.0f;
+    if (valid) { const float* p = pxs + lane * (M + 1); for (int c = 0; c < M; ++c) qx = __fadd_rn(qx, p[c]); }
+    return qx;
+  }
+};
+
 template <int KL>
 __global__ void __launch_bounds__(SCAN_WIDE_THREADS)
 scan_peaks_wide_kernel(const float2* __restrict__ u, const float2* __restrict__ G, const float2* __restrict__ z,
@@ -56,18 +103,27 @@ scan_peaks_wide_kernel(const float2* __restrict__ u, const float2* __restrict__ 
   extern __shared__ float4 smem4[];
   float* qtab = reinterpret_cast<float*>(smem4);                           // [P]
   float2* us = reinterpret_cast<float2*>(qtab + ((P + 3) & ~3));            // [M]
+  float2* Gs = us + M;                                                     // [M][M + 1]
+  float* pxs = reinterpret_cast<float*>(Gs + (size_t)M * (M + 1));         // [32][M + 1]
+  int* req = reinterpret_cast<int*>(pxs + 32 * (M + 1));                   // [32]
   const ZTab zt = ztab_view(zpair, P);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const CoopEval ev{req, pxs, Gs, Vtab, M};
+  const int rounds = K / 4 + 1;                                            // peaks_refine_emit: for (base = 0; base <= K; base += 4)
   for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
-    __syncthreads();                                                       // the previous frame's walker is done with qtab / us
+    __syncthreads();                                                       // the previous frame is done with qtab / us / Gs
     for (int l = threadIdx.x; l < M; l += SCAN_WIDE_THREADS) us[l] = u[(size_t)f * M + l];
+    for (int e = threadIdx.x; e < M * M; e += SCAN_WIDE_THREADS) { const int c = e / M, r = e - c * M; Gs[c * (M + 1) + r] = G[(size_t)f * M * M + e]; }
     __syncthreads();
     const float2 dummy[1] = {make_float2(0.f, 0.f)};
     for (int i = threadIdx.x; i < P; i += SCAN_WIDE_THREADS) qtab[i] = q_coarse<0>(dummy, us, M, z[i]);
     __syncthreads();
-    if (warp == 0)
-      scan_frame_peaks<0, KL>(u + (size_t)f * M, G + (size_t)f * M * M, zt, us, Vtab, xaxis, M, P, K, lane, out_val + (size_t)f * K,
-                              out_loc + (size_t)f * K, out_bin ? out_bin + (size_t)f * K : nullptr, qtab);
+    if (warp == 0) {
+      scan_frame_peaks_ev<0, KL>(u + (size_t)f * M, ev, zt, us, xaxis, M, P, K, lane, out_val + (size_t)f * K,
+                                 out_loc + (size_t)f * K, out_bin ? out_bin + (size_t)f * K : nullptr, qtab);
+    } else {
+      for (int rd = 0; rd < rounds; ++rd) { wide_bar(1); ev.round_work(); wide_bar(2); }
+    }
   }
 }
 
@@ -281,9 +337,10 @@ int launch_peaks_mt(const float2* u, const float2* G, const ScanTables& tb, int 
     return 1;
   }
   if constexpr (MT == 0) {
-    const size_t wsmem = (size_t)((P + 3) & ~3) * sizeof(float) + (size_t)M * sizeof(float2);
+    const size_t wsmem = (size_t)((P + 3) & ~3) * sizeof(float) + (size_t)M * sizeof(float2) + (size_t)M * (M + 1) * sizeof(float2) +
+                         (size_t)32 * (M + 1) * sizeof(float) + 32 * sizeof(int);
     if (wsmem <= 200 * 1024 && nframes <= 8 * sm_count() && dev_option(OPT_SCAN_WIDE, 1)) {
-      const int per = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / wsmem));
+      const int per = (int)std::max<size_t>(1, std::min<size_t>(4, (222 * 1024) / (wsmem + 1024)));   // 227 KB per SM, 1 KB reserved per CTA
       const int grid = min(nframes, sm_count() * per);
       if (K <= 4) {
         auto kern = scan_peaks_wide_kernel<4>;

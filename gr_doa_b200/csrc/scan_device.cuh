@@ -318,9 +318,20 @@ __device__ __forceinline__ void scan_frame_argmax(const float2* __restrict__ uf,
 // coarse candidates (lane r < K holds entry r) to the K outputs.  q0 / qe: coarse values of the two end bins (never local
 // peaks, but either may hold the global minimum); q_at(bin): coarse value of any bin, used only when the frame has no local
 // minimum at all.
-template <int MT = 0, bool GS = false, typename QAT>
-__device__ __forceinline__ void peaks_refine_emit(const Merged& m, float q0, float qe, QAT&& q_at, const float2* __restrict__ Gf,
-                                                  const float2* __restrict__ Vtab, const float* __restrict__ xaxis, int M, int P,
+// How a refinement value is obtained: every lane of the warp calls the evaluator once per round of the refinement loop
+// (K/4 + 1 rounds), convergently, with its own (valid, bin).  DirectEval: the lane evaluates v^H G v itself.  The wide kernel's
+// evaluator (scan.cu: CoopEval) posts the warp's 32 requests to shared memory and lets the whole CTA evaluate them.
+template <int MT, bool GS>
+struct DirectEval {
+  const float2* Gf; const float2* Vtab; int M;
+  __device__ __forceinline__ float operator()(bool valid, int b, int) const {
+    return valid ? q_faithful_t<MT, GS>(Gf, Vtab + (size_t)b * M, M) : INFINITY;
+  }
+};
+
+template <int MT = 0, bool GS = false, typename QAT, typename EV>
+__device__ __forceinline__ void peaks_refine_emit(const Merged& m, float q0, float qe, QAT&& q_at, const EV& ev,
+                                                  const float* __restrict__ xaxis, int M, int P,
                                                   int K, int lane, float* __restrict__ o_val, float* __restrict__ o_loc,
                                                   int* __restrict__ o_bin) {
   const int nref = min(K, m.nvalid);
@@ -362,8 +373,8 @@ __device__ __forceinline__ void peaks_refine_emit(const Merged& m, float q0, flo
     else if (entry < K) { used = true; refine = entry < nref; centre = refine ? cb : pad_bin; }
     const int b = centre + (refine ? sub - REFINE_W : 0);
     const bool valid = used && b >= 0 && b < P && (refine ? sub <= 2 * REFINE_W : sub == 0);
-    float qf = INFINITY; int qb = 0x7fffffff;
-    if (valid) { qf = q_faithful_t<MT, GS>(Gf, Vtab + (size_t)b * M, M); qb = b; }
+    const float qf0 = ev(valid, b, lane);
+    float qf = valid ? qf0 : INFINITY; int qb = valid ? b : 0x7fffffff;
 #pragma unroll
     for (int o = 4; o >= 1; o >>= 1) {
       const float ov = __shfl_xor_sync(FULL, qf, o); const int ob = __shfl_xor_sync(FULL, qb, o);
@@ -408,12 +419,12 @@ __device__ __forceinline__ void peaks_refine_emit(const Merged& m, float q0, flo
 // conversion, sorted outputs.  uf: the frame's M diagonal sums, Gf: its M x M projector (global or shared memory);
 // us: M float2 of per-warp shared scratch (runtime-M path only); o_*: this frame's K output slots.
 // ZS: the z table is known to live in shared memory (fused kernel): the hot loop then uses LDS instead of generic loads.
-template <int MT, int KL, bool ZS = false>
-__device__ __forceinline__ void scan_frame_peaks(const float2* __restrict__ uf, const float2* __restrict__ Gf, const ZTab& zt,
-                                                 float2* us, const float2* __restrict__ Vtab,
-                                                 const float* __restrict__ xaxis, int M, int P, int K, int lane,
-                                                 float* __restrict__ o_val, float* __restrict__ o_loc,
-                                                 int* __restrict__ o_bin, const float* qtab = nullptr) {
+template <int MT, int KL, bool ZS = false, typename EV>
+__device__ __forceinline__ void scan_frame_peaks_ev(const float2* __restrict__ uf, const EV& ev, const ZTab& zt,
+                                                    float2* us,
+                                                    const float* __restrict__ xaxis, int M, int P, int K, int lane,
+                                                    float* __restrict__ o_val, float* __restrict__ o_loc,
+                                                    int* __restrict__ o_bin, const float* qtab = nullptr) {
   const int S = zt.S;
   const float* za = zt.za; const float* zb = zt.zb;
   const int s0 = lane * S, s1 = min(P, s0 + S);
@@ -507,7 +518,17 @@ __device__ __forceinline__ void scan_frame_peaks(const float2* __restrict__ uf, 
   }
   Merged m = stitch_and_merge<KL, false>(w, K, lane, q_at);
   // compile-time M: steering rows in registers, unrolled row sums; ZS (fused kernel): the projector is in shared memory too
-  peaks_refine_emit<MT, ZS>(m, q_at(0), q_at(P - 1), q_at, Gf, Vtab, xaxis, M, P, K, lane, o_val, o_loc, o_bin);
+  peaks_refine_emit<MT, ZS>(m, q_at(0), q_at(P - 1), q_at, ev, xaxis, M, P, K, lane, o_val, o_loc, o_bin);
+}
+
+template <int MT, int KL, bool ZS = false>
+__device__ __forceinline__ void scan_frame_peaks(const float2* __restrict__ uf, const float2* __restrict__ Gf, const ZTab& zt,
+                                                 float2* us, const float2* __restrict__ Vtab,
+                                                 const float* __restrict__ xaxis, int M, int P, int K, int lane,
+                                                 float* __restrict__ o_val, float* __restrict__ o_loc,
+                                                 int* __restrict__ o_bin, const float* qtab = nullptr) {
+  const DirectEval<MT, ZS> ev{Gf, Vtab, M};
+  scan_frame_peaks_ev<MT, KL, ZS>(uf, ev, zt, us, xaxis, M, P, K, lane, o_val, o_loc, o_bin, qtab);
 }
 
 }  // namespace

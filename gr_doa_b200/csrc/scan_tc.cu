@@ -432,7 +432,7 @@ scan_tc_kernel(const float2* __restrict__ u, const float2* __restrict__ G, const
           return q_coarse<0>(dummy, us, M, zplain[bin]);
         };
         if (m.nvalid == 0) { __syncwarp(); for (int l = lane; l < M; l += 32) us[l] = u[f * M + l]; __syncwarp(); }
-        peaks_refine_emit<MT, true>(m, res->q0[i], res->qe[i], q_at, Gf, Vtab, xaxis, M, P, K, lane, ov, ol, ob);
+        peaks_refine_emit<MT, true>(m, res->q0[i], res->qe[i], q_at, DirectEval<MT, true>{Gf, Vtab, M}, xaxis, M, P, K, lane, ov, ol, ob);
       }
       __syncwarp();
       if (more) g_park(buf ^ 1);
