@@ -14,9 +14,14 @@
 // 64 KB of shared-memory traffic (512 clk) and ~1.2 k warp-instructions, against 192 KB and three barriers in the two-sided
 // kernel below, which also needs 10 sweeps where this one needs 8.
 //
-// jacobi_block_body: the two-sided iteration on A and V in shared memory (the round-1 kernel).  It remains as the fallback for
-// a matrix the Cholesky factorisation rejects (indefinite, zero, non-finite: not a covariance) and behind option
-// "eig_onesided" = 0.
+// A matrix the Cholesky factorisation rejects (indefinite, zero: not a covariance) is handled in the same planes without a
+// factor: H = R + ||R||_F I is positive semidefinite whatever R is and has R's eigenvectors, and for a Hermitian positive
+// semidefinite H the same column rotations give H J_1 J_2 ... = U (Lambda + delta): eigenvalue = |column| - delta.  (Slightly
+// less accurate than the factored path -- the Gram matrix is H^2 -- which is why it is only the fallback.)  No second
+// shared-memory layout is needed, so the kernel runs six CTAs per SM at 64 elements.
+//
+// jacobi_block_kernel: the two-sided iteration on A and V in shared memory (the round-1 kernel), behind option
+// "eig_onesided" = 0 as the comparison.
 #include "eig_os_device.cuh"
 
 namespace doa {
@@ -165,9 +170,23 @@ struct OsBlock {
   static constexpr int THREADS = MP * 4;          // MP/2 pairs x 8 lanes
   static constexpr int NC = MP / 32;              // 4-row chunks per lane and column
   static constexpr size_t PLANE = (size_t)MP * MP * sizeof(float);
-  // planes | G staging (float2 MP*MP) | nrm[MP] | lam[MP] | rk[MP] | flags
-  static constexpr size_t SMEM_OS = 2 * PLANE + (size_t)MP * MP * sizeof(float2) + 3 * MP * sizeof(float) + 16;
+  // planes | nrm[MP] | lam[MP] | rk[MP] | red[THREADS/32]
+  static constexpr size_t SMEM_OS = 2 * PLANE + 3 * MP * sizeof(float) + (THREADS / 32) * sizeof(float);
 };
+
+// Sum of one float per thread over the CTA in a fixed order (warp butterflies, then the warps' partials in warp order).
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();                                            // scratch free
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.0f;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) s += scratch[w];
+  return s;
+}
 
 template <int MP>
 __global__ void __launch_bounds__(OsBlock<MP>::THREADS)
@@ -177,32 +196,23 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
   constexpr int NT = C::THREADS, NC = C::NC, RR = MP - 1;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float2 sm[];
-  __shared__ float red[2];
   float* Wr = reinterpret_cast<float*>(sm);                   // column c of the real plane at Wr + c*MP
   float* Wi = Wr + MP * MP;
-  float2* Gs = reinterpret_cast<float2*>(Wi + MP * MP);       // [M*M], column-major
-  float* nrm = reinterpret_cast<float*>(Gs + MP * MP);        // squared column norms (tracked)
+  float* nrm = Wi + MP * MP;                                  // squared column norms (tracked)
   float* lam = nrm + MP;
   int* rk = reinterpret_cast<int*>(lam + MP);
+  float* red = reinterpret_cast<float*>(rk + MP);             // [NT / 32]
   const int tid = threadIdx.x;
   const int grp = tid >> 3, r8 = tid & 7;                     // pair slot, lane of the slot
 
   for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
     const float2* src = R + (long long)f * M * M;
     // ---- trace, exact power-of-two scale, shift (see eig_os_device.cuh) ----
-    float tr = 0.0f;
-    if (tid < 32) {
-      for (int i = tid; i < M; i += 32) tr += src[i + (size_t)i * M].x;
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) tr += __shfl_xor_sync(FULL, tr, o);
-      if (tid == 0) red[0] = tr;
-    }
-    __syncthreads();
-    tr = red[0];
+    float tr = block_sum<NT>(tid < M ? src[tid + (size_t)tid * M].x : 0.0f, red);
     const bool tr_ok = tr > 0.0f && tr < 3.0e38f;
-    const int ex = min(max((__float_as_int(tr) >> 23) & 0xff, 1), 253);
-    const float scl = __int_as_float((254 - ex) << 23), unscl = __int_as_float(ex << 23);
-    const float delta = tr_ok ? (tr * scl) * (1.0f / 16384.0f) : 1.0f;
+    int ex = min(max((__float_as_int(tr) >> 23) & 0xff, 1), 253);
+    float scl = __int_as_float((254 - ex) << 23), unscl = __int_as_float(ex << 23);
+    float delta = tr_ok ? (tr * scl) * (1.0f / 16384.0f) : 1.0f;
     // ---- lower triangle of (R scl + delta I) from the upper triangle of R (like cheevd 'U'); the rest zero ----
     for (int e = tid; e < MP * MP; e += NT) {
       const int i = e % MP, k = e / MP;                       // row, column
@@ -217,12 +227,12 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
     __syncthreads();
     // ---- Cholesky, right-looking, in place ----
     bool ok = tr_ok;
-    for (int j = 0; j < M; ++j) {
+    for (int j = 0; j < M && ok; ++j) {
       const float piv = Wr[j * MP + j];
-      const bool good = piv > 0.0f && piv < 3.0e38f;
-      ok = ok && good;                                        // the same in every thread
-      const float d = sqrtf(good ? piv : 1.0f), inv = 1.0f / d;
+      ok = piv > 0.0f && piv < 3.0e38f;                       // the same in every thread
+      const float d = sqrtf(ok ? piv : 1.0f), inv = 1.0f / d;
       __syncthreads();                                        // everyone has read the pivot
+      if (!ok) break;
       for (int i = j + tid; i < M; i += NT) {
         if (i == j) { Wr[j * MP + j] = d; Wi[j * MP + j] = 0.0f; }
         else { Wr[j * MP + i] *= inv; Wi[j * MP + i] *= inv; }
@@ -239,19 +249,39 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
       }
       __syncthreads();
     }
-    if (!ok) {
-      // not a covariance: the two-sided iteration on the original matrix (its shared-memory layout overlays this kernel's)
+    const bool factored = ok;
+    if (!factored) {
+      // ---- not a covariance: H = R / 2^e + delta I with delta = ||R / 2^e||_F in [1, 2), all of it, no factor ----
+      float part = 0.0f;
+      for (int e = tid; e < M * M; e += NT) {
+        const int i = e % M, k = e / M;
+        if (i <= k) { const float2 a = src[e]; const float m2 = (i == k) ? a.x * a.x : 2.0f * fmaf(a.x, a.x, a.y * a.y); part += m2; }
+      }
+      // squares of huge entries overflow to +inf, of tiny ones vanish: scale by the largest-exponent estimate first is not
+      // worth its code here -- such a matrix gets delta from the clamped exponent below and still converges
+      const float fro = sqrtf(block_sum<NT>(part, red));
+      const bool any = fro > 0.0f && fro < 3.0e38f;
+      ex = min(max((__float_as_int(fro) >> 23) & 0xff, 1), 253);
+      scl = any ? __int_as_float((254 - ex) << 23) : 1.0f; unscl = any ? __int_as_float(ex << 23) : 1.0f;
+      delta = any ? fro * scl : 1.0f;                         // the zero matrix becomes the identity: eigenvalues 1 - 1
+      for (int e = tid; e < MP * MP; e += NT) {
+        const int i = e % MP, k = e / MP;
+        float re = 0.0f, im = 0.0f;
+        if (i < M && k < M) {
+          if (i == k) re = fmaf(src[i + (size_t)i * M].x, scl, delta);
+          else if (i < k) { const float2 a = src[i + (size_t)k * M]; re = a.x * scl; im = a.y * scl; }
+          else { const float2 a = src[k + (size_t)i * M]; re = a.x * scl; im = -a.y * scl; }
+        }
+        Wr[e] = re; Wi[e] = im;
+      }
       __syncthreads();
-      jacobi_block_body(src, M, T, G ? G + (long long)f * M * M : nullptr, u ? u + (long long)f * M : nullptr,
-                        w ? w + (long long)f * M : nullptr, 20, sm, red);
-      continue;
     }
 
     // ---- sweeps ----
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
       // squared column norms: four lanes per column
-      for (int c4 = tid; c4 < MP * 4; c4 += NT) {
-        const int c = c4 >> 2, sub = c4 & 3;
+      {
+        const int c = tid >> 2, sub = tid & 3;
         float s = 0.0f;
 #pragma unroll
         for (int i = 0; i < MP / 16; ++i) {
@@ -325,9 +355,9 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
       if (!__syncthreads_or(dirty_any ? 1 : 0)) break;
     }
 
-    // ---- eigenpairs: 2^e (|column|^2 - delta) and the normalised column ----
-    for (int c4 = tid; c4 < MP * 4; c4 += NT) {
-      const int c = c4 >> 2, sub = c4 & 3;
+    // ---- eigenpairs: the normalised column and 2^e (|column|^2 - delta), or 2^e (|column| - delta) without a factor ----
+    {
+      const int c = tid >> 2, sub = tid & 3;
       float s = 0.0f;
 #pragma unroll
       for (int i = 0; i < MP / 16; ++i) {
@@ -338,7 +368,7 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
       }
       s += __shfl_xor_sync(FULL, s, 1);
       s += __shfl_xor_sync(FULL, s, 2);
-      const float sc = 1.0f / sqrtf(fmaxf(s, 1e-37f));
+      const float nr = sqrtf(fmaxf(s, 1e-37f)), sc = 1.0f / nr;
 #pragma unroll
       for (int i = 0; i < MP / 16; ++i) {
         float4* a = reinterpret_cast<float4*>(Wr + c * MP + sub * (MP / 4) + 4 * i);
@@ -347,7 +377,7 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
         x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; y.x *= sc; y.y *= sc; y.z *= sc; y.w *= sc;
         *a = x; *b = y;
       }
-      if (sub == 0 && c < M) lam[c] = (s - delta) * unscl;
+      if (sub == 0 && c < M) lam[c] = ((factored ? s : nr) - delta) * unscl;
     }
     __syncthreads();
     for (int c = tid; c < M; c += NT) {
@@ -359,25 +389,35 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
     }
     __syncthreads();
     const int nn = M - T;
-    for (int e = tid; e < M * M; e += NT) {
-      const int i = e % M, jj = e / M;
-      float gx = 0.f, gy = 0.f;
-      for (int n = 0; n < nn; ++n) {
-        const int c = rk[n];
-        const float eix = Wr[c * MP + i], eiy = Wi[c * MP + i], ejx = Wr[c * MP + jj], ejy = Wi[c * MP + jj];
-        gx = fmaf(eix, ejx, gx); gx = fmaf(eiy, ejy, gx);
-        gy = fmaf(eiy, ejx, gy); gy = fmaf(-eix, ejy, gy);
+    if (G) {
+      for (int e = tid; e < M * M; e += NT) {
+        const int i = e % M, jj = e / M;
+        float gx = 0.f, gy = 0.f;
+        for (int n = 0; n < nn; ++n) {
+          const int c = rk[n];
+          const float eix = Wr[c * MP + i], eiy = Wi[c * MP + i], ejx = Wr[c * MP + jj], ejy = Wi[c * MP + jj];
+          gx = fmaf(eix, ejx, gx); gx = fmaf(eiy, ejy, gx);
+          gy = fmaf(eiy, ejx, gy); gy = fmaf(-eix, ejy, gy);
+        }
+        G[(long long)f * M * M + e] = make_float2(gx, gy);
       }
-      Gs[e] = make_float2(gx, gy);
-      if (G) G[(long long)f * M * M + e] = make_float2(gx, gy);
     }
-    __syncthreads();
     if (u) {
-      for (int l = tid; l < M; l += NT) {
-        float sx = 0.f, sy = 0.f;
-        for (int r = 0; r + l < M; ++r) { sx += Gs[r + (r + l) * M].x; sy += Gs[r + (r + l) * M].y; }
-        u[(long long)f * M + l] = make_float2(sx, l == 0 ? 0.f : sy);
+      // u_l = sum over noise eigenvectors of sum_r e[r] conj(e[r + l]): four lanes per l, rows r = part, part + 4, ...
+      const int l = tid >> 2, part = tid & 3;
+      float sx = 0.f, sy = 0.f;
+      if (l < M) {
+        for (int n = 0; n < nn; ++n) {
+          const float* er = Wr + rk[n] * MP; const float* ei = Wi + rk[n] * MP;
+          for (int r = part; r + l < M; r += 4) {
+            sx = fmaf(er[r], er[r + l], sx); sx = fmaf(ei[r], ei[r + l], sx);
+            sy = fmaf(ei[r], er[r + l], sy); sy = fmaf(-er[r], ei[r + l], sy);
+          }
+        }
       }
+      sx += __shfl_xor_sync(FULL, sx, 1); sy += __shfl_xor_sync(FULL, sy, 1);
+      sx += __shfl_xor_sync(FULL, sx, 2); sy += __shfl_xor_sync(FULL, sy, 2);
+      if (part == 0 && l < M) u[(long long)f * M + l] = make_float2(sx, l == 0 ? 0.f : sy);
     }
     __syncthreads();
   }
@@ -386,8 +426,7 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
 template <int MP>
 int launch_os_block(const float2* R, int M, int T, int nframes, float2* G, float2* u, float* w, int sweeps, cudaStream_t st) {
   using C = OsBlock<MP>;
-  const size_t body = block_body_smem(M);
-  const size_t smem = C::SMEM_OS > body ? C::SMEM_OS : body;
+  const size_t smem = C::SMEM_OS;
   auto kern = jacobi_os_block_kernel<MP>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DOA_CUDA_ECUDA;
   int dev = 0, sms = 148, per_sm = 1;

@@ -115,8 +115,33 @@ scan_peaks_wide_kernel(const float2* __restrict__ u, const float2* __restrict__ 
     for (int l = threadIdx.x; l < M; l += SCAN_WIDE_THREADS) us[l] = u[(size_t)f * M + l];
     for (int e = threadIdx.x; e < M * M; e += SCAN_WIDE_THREADS) { const int c = e / M, r = e - c * M; Gs[c * (M + 1) + r] = G[(size_t)f * M * M + e]; }
     __syncthreads();
-    const float2 dummy[1] = {make_float2(0.f, 0.f)};
-    for (int i = threadIdx.x; i < P; i += SCAN_WIDE_THREADS) qtab[i] = q_coarse<0>(dummy, us, M, z[i]);
+    // coarse spectrum: four adjacent bins per thread as two packed pairs (fma.rn.f32x2 is two scalar FMAs: the bits of
+    // q_coarse<0>), so a coefficient costs one shared-memory load per four bins
+    for (int i0 = 4 * threadIdx.x; i0 < P; i0 += 4 * SCAN_WIDE_THREADS) {
+      if (i0 + 4 <= P) {
+        const float4 za = *reinterpret_cast<const float4*>(z + i0), zb = *reinterpret_cast<const float4*>(z + i0 + 2);   // (x0,y0,x1,y1), (x2,y2,x3,y3)
+        const f32x2 zx0 = pk2(za.x, za.z), zy0 = pk2(za.y, za.w), nzy0 = pk2(-za.y, -za.w);
+        const f32x2 zx1 = pk2(zb.x, zb.z), zy1 = pk2(zb.y, zb.w), nzy1 = pk2(-zb.y, -zb.w);
+        const float2 top = us[M - 1];
+        f32x2 ax0 = pk2(top.x, top.x), ay0 = pk2(top.y, top.y), ax1 = ax0, ay1 = ay0;
+        for (int l = M - 2; l >= 1; --l) {
+          const float2 c = us[l];
+          const f32x2 cx = pk2(c.x, c.x), cy = pk2(c.y, c.y);
+          const f32x2 nx0 = fma2(ax0, zx0, fma2(ay0, nzy0, cx)), ny0 = fma2(ax0, zy0, fma2(ay0, zx0, cy));
+          const f32x2 nx1 = fma2(ax1, zx1, fma2(ay1, nzy1, cx)), ny1 = fma2(ax1, zy1, fma2(ay1, zx1, cy));
+          ax0 = nx0; ay0 = ny0; ax1 = nx1; ay1 = ny1;
+        }
+        // re = fmaf(ax, z.x, -ay * z.y);  q = fmaf(2, re, u0)
+        const f32x2 re0 = fma2(ax0, zx0, mul2(ay0, nzy0)), re1 = fma2(ax1, zx1, mul2(ay1, nzy1));
+        const f32x2 two = pk2(2.0f, 2.0f), u0 = pk2(us[0].x, us[0].x);
+        float4 q;
+        upk2(fma2(two, re0, u0), q.x, q.y); upk2(fma2(two, re1, u0), q.z, q.w);
+        *reinterpret_cast<float4*>(qtab + i0) = q;
+      } else {
+        const float2 dummy[1] = {make_float2(0.f, 0.f)};
+        for (int i = i0; i < P; ++i) qtab[i] = q_coarse<0>(dummy, us, M, z[i]);
+      }
+    }
     __syncthreads();
     if (warp == 0) {
       scan_frame_peaks_ev<0, KL>(u + (size_t)f * M, ev, zt, us, xaxis, M, P, K, lane, out_val + (size_t)f * K,

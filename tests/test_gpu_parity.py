@@ -74,7 +74,7 @@ def test_golden_chain(doa, name):
     assert np.all(val[:, 0] == 0.0)                                       # highest peak is the 0 dB reference
     bound = parity.peak_value_bound_db(z["q64"], z["bins"], z["q32"])
     assert np.all(np.abs(val[same] - z["val"][same]) <= bound[same])
-    assert ch.launches() in (1, 3)            # 1 = fused persistent kernel, 3 = covariance, Jacobi, scan
+    assert ch.launches() in (1, 3)            # 1 = fused persistent kernel, 3 = covariance, eigensolver, scan
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -569,3 +569,36 @@ def test_onesided_eigensolver_falls_back_on_matrices_that_are_not_covariances(do
     G64, _ = _projector_f64(spd.transpose(1, 2).contiguous().view(B, M * M).cpu().numpy(), M, T)
     Gg = torch.view_as_complex(alone[0]).cpu().numpy().reshape(B, M, M).transpose(0, 2, 1)
     assert np.abs(Gg - G64).max() <= 5e-6
+
+
+@pytest.mark.parametrize("M", [24, 64])
+def test_block_eigensolver_on_general_hermitian_input(doa, torch_cuda, M):
+    """17..64 elements (csrc/eig_block.cu): a covariance goes through Cholesky + one-sided Jacobi; anything else (indefinite,
+    zero) through the same rotations on R + ||R||_F I.  Both against a float64 eigendecomposition."""
+    rng = np.random.default_rng(11)
+    B, T = 12, 2
+    mats = []
+    for b in range(B):
+        Q, _ = np.linalg.qr(rng.standard_normal((M, M)) + 1j * rng.standard_normal((M, M)))
+        lam = np.concatenate([np.linspace(-3.0, 3.0, M - T), [9.0, 12.0]])           # indefinite, clear gap below the top T
+        if b % 3 == 1:
+            lam = np.concatenate([np.linspace(0.5, 1.5, M - T), [40.0, 90.0]])       # a covariance: the factored path
+        A = (Q * lam) @ Q.conj().T
+        mats.append(0.5 * (A + A.conj().T))
+    mats[2] = np.zeros((M, M), complex)
+    A = np.stack(mats)
+    Rin = np.ascontiguousarray(A.transpose(0, 2, 1).reshape(B, M * M)).astype(np.complex64)
+    G64, w64 = _projector_f64(Rin, M, T)
+    mus = doa.MUSIC_lin_array(0.5, T, M, 256, max_frames=B)
+    for onesided in (1, 0):
+        mus.set_option("eig_onesided", onesided)
+        G, u, w = [t.cpu().numpy() for t in mus.noise_subspace_device(torch_cuda.from_numpy(Rin).cuda())]
+        Gm = G.reshape(B, M, M).transpose(0, 2, 1)
+        ok = [b for b in range(B) if b != 2]
+        assert np.abs(Gm[ok] - G64[ok]).max() <= 1e-5, onesided
+        assert np.abs(w - w64).max() <= 2e-5 * 90.0, onesided
+        for l in (0, 1, M - 1):
+            ul = np.stack([np.trace(Gm[b], offset=l) for b in range(B)])
+            assert np.abs(ul - u[:, l]).max() <= 1e-5 * M
+        # the zero matrix: eigenvalues 0, eigenvectors the unit vectors in index order
+        assert np.allclose(Gm[2], np.diag([1.0] * (M - T) + [0.0] * T), atol=1e-6)
