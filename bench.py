@@ -495,7 +495,7 @@ def main():
             "msamples_per_s_aggregate": value * N * M / 1e6,
             "roofline": {"bound": "hbm", "achieved": cov_gbs, "peak": peak, "unit": "GB/s", "frac": cov_gbs / peak,
                          "traffic": traffic,
-                         "kernel": ("chain_ws_kernel<8> (covariance + Jacobi + scan/peaks in one persistent warp-specialised kernel)" if fused
+                         "kernel": ("chain_ws_kernel<8> (covariance + eigensolver + scan/peaks in one persistent warp-specialised kernel)" if fused
                                     else "cov_small_kernel<8> (covariance, dominant)"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": kern_bytes, "launch_ms": kern_ms,
                          "stage_ms": ({"fused_chain": kern_ms} if fused else {"cov": cov_ms, "eig": eig_ms, "scan_peaks": scan_ms}),
@@ -587,7 +587,7 @@ def bench_small_configs(doa, synth, torch, np, dev, local, peak, args):
         del xs
         torch.cuda.empty_cache()
 
-    # cfg4: 64-element array (tensor-core HERK covariance, block Jacobi, wide scan)
+    # cfg4: 64-element array (tensor-core HERK covariance, one-sided block eigensolver, wide scan)
     c = CFG4
     Bc = c["frames"]
     x4, _ = synth.frames_torch(Bc, c["M"], c["N"], c["thetas"], jitter_deg=2.0, device=dev, chunk=32, seed=synth.SEED_BASE + 4)
@@ -605,7 +605,7 @@ def bench_small_configs(doa, synth, torch, np, dev, local, peak, args):
     res["cfg4"] = {"workload": f"{Bc} independent 64-element frames x 16384 snapshots, 8 sources, 16384-point scan, K 8",
                    "ms": ms, "frames_per_s": Bc / (ms * 1e-3), "stage_ms": {"cov_herk_tc": st[0], "jacobi": st[1], "scan_peaks": st[2]},
                    "launches": ch.launches(),
-                   "roofline": {"bound": "tensor (covariance) / latency (Jacobi)", "algorithmic_bytes_per_frame": ALG_BYTES_CHAIN(wb),
+                   "roofline": {"bound": "tensor pipe (covariance) / shared-memory bandwidth (eigensolver)", "algorithmic_bytes_per_frame": ALG_BYTES_CHAIN(wb),
                                 "achieved_GBps": gbs, "frac_hbm": gbs / peak, "herk_tf32_mma_TFLOPs": herk_tflops,
                                 "herk_input_GBps": 8.0 * c["M"] * c["N"] * Bc / (st[0] * 1e-3) / 1e9},
                    "cpu_baseline": cpu_rate(c, 0, 1)}
@@ -667,7 +667,7 @@ def bench_cfg5(doa, synth, sharding, torch, dist, np, dev, local, rank, world, p
            "frames_per_s": total / (ms * 1e-3), "msamples_per_s_per_stream": total * N / (ms * 1e-3) / 1e6,
            "kernel_ms_per_step_per_gpu": kms, "exposed_gather_ms": ms - kms, "launches_per_step": ch.launches() * (-(-Bl // call)),
            "stage_ms_per_call": {"frames": call, "cov": st[0], "jacobi": st[1], "scan_peaks": st[2]},
-           "roofline": {"bound": "fp32 pipe (8.5 flop/B covariance + 16x16 Jacobi), reported against HBM", "algorithmic_bytes_per_frame": bytes_pf,
+           "roofline": {"bound": "fp32 pipe (8.5 flop/B covariance + 16x16 eigensolver), reported against HBM", "algorithmic_bytes_per_frame": bytes_pf,
                         "achieved_GBps_per_gpu": bytes_pf * Bl / (ms * 1e-3) / 1e9, "frac": bytes_pf * Bl / (ms * 1e-3) / 1e9 / peak,
                         "frac_kernels_only": bytes_pf * Bl / (kms * 1e-3) / 1e9 / peak},
            "timer": "CUDA events, max over ranks; inputs resident (generated per shard on the device); gather of the peaks inside the timed region"}

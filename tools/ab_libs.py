@@ -39,6 +39,14 @@ def child(path):
     x, _ = synth.frames_torch(262144, 4, 2048, [60.0], jitter_deg=2.0, device="cuda", chunk=4096)
     ch = doa.DoaChain(4, 2048, 0, 0, 0.5, 1, 2048, 1, max_frames=262144)
     out["cfg1"] = t(lambda: ch.run_device(x), 4)
+    del x, ch
+    torch.cuda.empty_cache()
+    x, _ = synth.frames_torch(512, 64, 16384, [30.0 + 120.0 * i / 7 for i in range(8)], jitter_deg=2.0, device="cuda", chunk=32)
+    ac = doa.autocorrelate(64, 16384, 0, 0, max_frames=512)
+    out["cov64"] = t(lambda: ac.work_device(x), 4)
+    ch = doa.DoaChain(64, 16384, 0, 0, 0.5, 8, 16384, 8, max_frames=512)
+    out["cfg4"] = t(lambda: ch.run_device(x), 4)
+    out["cov64_checksum"] = float(torch.view_as_real(ac.work_device(x)).double().abs().sum().item())
     print(json.dumps(out))
 
 

@@ -10,7 +10,7 @@ CFG = {
     "cfg2-shape MUSIC (M4 T2 N2048 P1024 K2, FB)": dict(B=262144, M=4, N=2048, T=2, P=1024, K=2, th=[50.0, 110.0], avg=1),
     "cfg3 (M8 T3 N2048 P4096 K3)": dict(B=65536, M=8, N=2048, T=3, P=4096, K=3, th=[40.0, 90.0, 140.0]),
     "cfg5 shard (M16 T3 N1024 P4096 K3)": dict(B=65536, M=16, N=1024, T=3, P=4096, K=3, th=[40.0, 90.0, 140.0]),
-    "cfg4 (M64 T8 N16384 P16384 K8)": dict(B=256, M=64, N=16384, T=8, P=16384, K=8, th=[30.0 + 120.0 * i / 7 for i in range(8)]),
+    "cfg4 (M64 T8 N16384 P16384 K8)": dict(B=512, M=64, N=16384, T=8, P=16384, K=8, th=[30.0 + 120.0 * i / 7 for i in range(8)]),
 }
 only = sys.argv[1:] 
 for name, c in CFG.items():
