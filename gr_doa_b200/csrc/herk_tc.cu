@@ -21,23 +21,28 @@
 // accumulator is a ping-pong pair, and every TC_CHUNK stages (16 MMAs per column block) the finished one is folded into fp32
 // REGISTERS with properly rounded adds: rel. Frobenius error 4e-7 at every N (tests/test_gpu_parity.py).
 //
-// One persistent CTA per SM, 13 warps; a "stage" is 16 complex samples = 32 K-values = 128 bytes per row:
+// One persistent CTA per SM, 17 warps; a "stage" is 16 complex samples = 32 K-values = 128 bytes per row:
 //   warp 0           : MMA issuer.  The whole warp runs the loop (warp-uniform operands, so ptxas emits bare UTCHMMA) and one
 //                      elected lane issues: wait full[s]; 4 K-steps x 2 MMAs; tcgen05.commit -> empty[s]; every TC_CHUNK
 //                      stages and at the end of a frame commit -> chunk_full[b] and switch accumulators.
-//   warps 1..8       : converters, two independent groups of 4 warps on alternate stages.  Loader role: cp.async 64 B of one
-//                      channel into the group's raw ring (HBM bytes in flight do not depend on registers).  Converter role:
+//   warps 1..12      : converters, three independent groups of 4 warps taking the stages round-robin.  Loader role: cp.async 16-byte pieces,
+//                      eight lanes per 128-byte line, into the group's raw ring (HBM bytes in flight do not depend on registers).  Converter role:
 //                      a thread IS one row of A (TMEM lanes belong to warp % 4): read the row's 32 raw values, split hi/lo
 //                      (integer round-to-nearest on the tf32 boundary), (im, -re) for W rows, tcgen05.st into the A ring;
 //                      Z rows also store the swizzled B tiles; fences, arrive on full[s].  They run ahead across frames.
-//   warps 9..12      : adders + epilogue.  Thread = one TMEM lane (row of [Re R; Im R]), 64 fp32 register accumulators:
+//   warps 13..16     : adders + epilogue.  Thread = one TMEM lane (row of [Re R; Im R]), 64 fp32 register accumulators:
 //                      wait chunk_full[b], tcgen05.ld both column blocks, add, arrive chunk_empty[b]; at the frame end stage
 //                      the 128 x 64 result in shared memory, combine Re/Im, scale, forward-backward term, store R.
 // TMEM (512 columns): accumulators @0 and @128, A ring @256 + 64 s (32 hi | 32 lo columns per stage, 4 stages).
 //
-// Measured (B200, 592 frames of 64 x 16384): 2.2 ms = 2.2 TB/s of input = 0.34 of HBM, against 5.30 ms for the CUDA-core
-// tiled kernel.  Both sides of the pipeline now cost 700-900 clk per stage of dependent latency (converter iteration; MMA
-// issue + commit), against a 384 clk tensor-pipe floor: the next step is software-pipelining the converter's fences.
+// Measured (B200, 512 frames of 64 x 16384): 2.08 ms = 2.1 TB/s of input, tensor pipe 41 % busy (ncu), against 5.30 ms for the
+// CUDA-core tiled kernel.  What the round-2 profile (profiles/r02_ncu_herk_tc.txt) says about the rest: the converters never wait
+// for the tensor core (1.6 % of their samples at empty[s]) and the MMA warp waits for them 29 % of its time -- a converter
+// iteration is ~1900 clk of dependent latency for ~250 instructions (group barrier skew between Z rows, which also store the B
+// tiles, and W rows: 22 %; raw-ring loads: 16 %; fences and the TMEM store drain: ~10 %).  Tried and measured: converting before
+// the wait on empty[s] (no change), a fully unrolled MMA-issue loop with compile-time operands (6 % SLOWER: tighter MMA issue
+// takes shared-memory cycles from the converters), line-contiguous cp.async with an XOR-swizzled raw ring (8x fewer
+// shared-memory wavefronts per copy, 1 % faster: kept), a third converter group (3 % faster: kept).
 #include "cov_device.cuh"
 
 #include <algorithm>
@@ -51,7 +56,12 @@ constexpr int TC_OP_STAGES = 4;          // operand ring depth: A = 64 TMEM colu
 constexpr int TC_RAW_STAGES = 5;         // raw fp32 ring depth PER converter group (8 KB per stage)
 constexpr int TC_CHUNK = 4;              // stages (= 16 hi*hi MMAs) per big-accumulator chunk
 constexpr int TC_TILE_BYTES = TC_M * 128; // one B tile (Z_hi or Z_lo): 64 rows x 128 B
-constexpr int TC_CONV_WARPS = 8, TC_ADD_WARPS = 4;
+#ifndef DOA_HERK_GROUPS
+#define DOA_HERK_GROUPS 3   // measured: 2 groups 2.15 ms, 3 groups 2.08 ms per 512 frames (the converters are latency-bound: more of them in flight)
+#endif
+constexpr int TC_GROUPS = DOA_HERK_GROUPS;       // converter groups of 4 warps, taking stages round-robin
+constexpr int TC_CONV_WARPS = 4 * TC_GROUPS, TC_ADD_WARPS = 4;
+constexpr int TC_RAW_STAGE_BYTES = 8 * TC_M * 16;   // one raw stage: 8 pieces x 64 channels x 16 B
 constexpr int TC_CONV_THREADS = TC_CONV_WARPS * 32;
 constexpr int TC_THREADS = (1 + TC_CONV_WARPS + TC_ADD_WARPS) * 32;
 constexpr int TC_TMEM_COLS = 512;        // D[0] @0, D[1] @128 (64 hi*hi columns | 64 cross-term columns), A ring @256 + 64 s (hi | lo)
@@ -110,14 +120,14 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
   // 1024-byte alignment by OFFSETTING the shared array (an integer round trip would turn every access into a generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* op = smem;                                                                  // B ring [OP_STAGES][Z_hi tile | Z_lo tile]
-  float4* raw = reinterpret_cast<float4*>(smem + TC_OP_STAGES * 2 * TC_TILE_BYTES);      // [2 groups][RAW_STAGES][8 pieces][64 channels]
-  float* stg = reinterpret_cast<float*>(smem + TC_OP_STAGES * 2 * TC_TILE_BYTES + 2 * TC_RAW_STAGES * TC_CONV_THREADS * 2 * 16);   // [128][65]
+  float4* raw = reinterpret_cast<float4*>(smem + TC_OP_STAGES * 2 * TC_TILE_BYTES);      // [groups][RAW_STAGES][8 pieces][64 channels ^ piece]
+  float* stg = reinterpret_cast<float*>(smem + TC_OP_STAGES * 2 * TC_TILE_BYTES + TC_GROUPS * TC_RAW_STAGES * TC_RAW_STAGE_BYTES);   // [128][65]
   __shared__ uint64_t full_bar[TC_OP_STAGES], empty_bar[TC_OP_STAGES], chunk_full[2], chunk_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < TC_OP_STAGES; ++s) { mbar_init(&full_bar[s], TC_CONV_THREADS / 2); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < TC_OP_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&chunk_full[b], 1); mbar_init(&chunk_empty[b], TC_ADD_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -178,46 +188,50 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
     }
   } else if (warp <= TC_CONV_WARPS) {
     // ================================ converters ================================
-    // Two independent groups of 4 warps take alternate stages (group g: stages q = g, g + 2, ...), each with its own raw ring
+    // TC_GROUPS independent groups of 4 warps take the stages round-robin (group g: stages q = g, g + TC_GROUPS, ...), each with its own raw ring
     // and named barrier, so one group's latencies (barrier, ring waits, TMEM store drain) hide behind the other's work.
     const int g = (warp - 1) >> 2;
     const int gt = ((warp - 1) & 3) * 32 + lane;   // 0..127 within the group
-    // loader role: channel gt >> 1, pieces 4 (gt & 1) + {0..3} of the stage's 8 (a piece = 2 complex samples = 16 B): 2 lanes
-    // cover one 128-byte line.  Raw ring layout [stage][piece][channel]: conflict-free for both roles.
-    const int lch = gt >> 1, lh = gt & 1;
+    // Loader role (a piece = 2 complex samples = 16 B, a stage = 8 pieces per channel): EIGHT consecutive lanes copy the eight 16-byte pieces of ONE channel's 128-byte line (copy j of a thread:
+    // channel 16 j + gt / 8, piece gt % 8), so a warp-wide cp.async reads four whole lines.  With two lanes per line and four
+    // copies each (round 1), every lane's 16 bytes came back from L2 in a sector of their own and were written to shared memory as a
+    // separate wavefront: 32 wavefronts per warp-wide copy instead of 4, 511 of the ~830 shared-memory wavefronts of a stage
+    // (ncu source page: 67 M wavefronts per LDGSTS against 8.4 M ideal) -- the port, not the tensor core, set the stage time.
+    // Raw ring layout [stage][piece][channel ^ piece]: the XOR keeps both the loaders' stores (fixed channel, 8 pieces) and
+    // the converters' loads (fixed piece, 32 consecutive channels) conflict-free.
+    const int lpc = gt & 7, lch0 = gt >> 3;         // piece, channel of copy 0
     float4* graw = raw + (size_t)g * TC_RAW_STAGES * (8 * TC_M);
-    float4* lraw = graw + (lh * 4) * TC_M + lch;
+    float4* lraw = graw + lpc * TC_M;
     // converter role: this thread IS row (warp & 3) * 32 + lane of A = [Z; W] (TMEM lanes are per-warp quarters)
     const int row = (warp & 3) * 32 + lane, cch = row & (TC_M - 1);
     const bool is_w = row >= TC_M;
-    const float4* craw = graw + cch;
     const uint32_t a_lane = tmem_d + TC_A_COL + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t row_off = ((uint32_t)cch >> 3) * 1024u + ((uint32_t)cch & 7u) * 128u, row_x = (uint32_t)cch & 7u;
     int isf = g % spf;
+    constexpr int NG = TC_GROUPS;
     long long fi = (long long)blockIdx.x + (long long)(g / spf) * gridDim.x;
-    const float2* ibase = in + fi * frame_stride + (long long)lch * chan_stride;
+    const float2* ibase = in + fi * frame_stride + (long long)lch0 * chan_stride;
+    const long long cstep = 16 * chan_stride;      // copy j reads channel lch0 + 16 j
     int irs = 0; long long qi = g;
     auto issue = [&]() {
-      const int t = isf * 16 + lh * 8;             // first complex sample of this thread's 8
+      const int tj = isf * 16 + 2 * lpc;           // this thread's two complex samples of the stage
+      const int nb = (tj < N) ? 16 : 0;            // N is even (launcher): a 16-byte piece is all in or all out
       float4* dst = lraw + (size_t)irs * (8 * TC_M);
+      const float2* srcp = ibase + (nb ? tj : 0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int tj = t + 2 * j;
-        const int nb = (tj < N) ? 16 : 0;          // N is even (launcher): a 16-byte piece is all in or all out
-        cp_async16z(dst + j * TC_M, ibase + (nb ? tj : 0), nb);
-      }
-      isf += 2;
+      for (int j = 0; j < 4; ++j) cp_async16z(dst + ((lch0 + 16 * j) ^ lpc), srcp + j * cstep, nb);
+      isf += NG;
       if (isf >= spf) {
         do { isf -= spf; fi += gridDim.x; } while (isf >= spf);
-        ibase = in + fi * frame_stride + (long long)lch * chan_stride;
+        ibase = in + fi * frame_stride + (long long)lch0 * chan_stride;
       }
       if (++irs == TC_RAW_STAGES) irs = 0;
-      qi += 2;
+      qi += NG;
     };
 #pragma unroll
     for (int p = 0; p < TC_RAW_STAGES - 2; ++p) { if (qi < total) issue(); asm volatile("cp.async.commit_group;" ::: "memory"); }
     int rs = 0;
-    for (long long q = g; q < total; q += 2) {
+    for (long long q = g; q < total; q += NG) {
       // the slot refilled here was read two iterations ago at the latest, before the barrier every thread passed last time
       if (qi < total) issue();
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -228,14 +242,14 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
         mbar_wait(&empty_bar[s], (uint32_t)((q >> 2) + 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
-      const float4* src = craw + (size_t)rs * (8 * TC_M);
+      const float4* src = graw + (size_t)rs * (8 * TC_M);
       uint8_t* thi = op + (size_t)s * 2 * TC_TILE_BYTES + row_off;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {                 // 16 K-values (4 pieces) at a time
         float hi[16], lo[16];
         float4 v[4];                                // (re0, im0, re1, im1) each
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = src[(4 * h + j) * TC_M];
+        for (int j = 0; j < 4; ++j) v[j] = src[(4 * h + j) * TC_M + (cch ^ (4 * h + j))];
         if (!is_w) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -335,7 +349,7 @@ int launch_covariance_tc(const float2* in, long long frame_stride, long long cha
   const bool aligned = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
                        ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
   if (!aligned) return 0;
-  const size_t smem = (size_t)TC_OP_STAGES * 2 * TC_TILE_BYTES + (size_t)2 * TC_RAW_STAGES * TC_CONV_THREADS * 2 * sizeof(float4) +
+  const size_t smem = (size_t)TC_OP_STAGES * 2 * TC_TILE_BYTES + (size_t)TC_GROUPS * TC_RAW_STAGES * TC_RAW_STAGE_BYTES +
                       (size_t)128 * 65 * sizeof(float) + 1024;
   cudaFuncSetAttribute(herk_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
