@@ -7,7 +7,7 @@ mkdir -p $o
 timeout 600 python bench.py > $o/${tag}_bench_final.json 2> $o/${tag}_bench_final.err || echo "bench failed"
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_reference.json 2>> $o/${tag}_bench_final.err || echo "reference arm failed"
 timeout 300 python tools/time_configs.py > $o/${tag}_time_configs_final.log 2>&1
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $o/${tag}_launches_raw.csv \
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"chain_ws|jacobi|scan_|cov|herk|rootmusic|find_local|calibrate" -c 400 --csv --log-file $o/${tag}_launches_raw.csv \
     python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-sustained > $o/${tag}_ncu_launch.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:chain_ws_kernel -s 4 -c 1 -o $o/${tag}_chain_ws -f \
     python tools/prof_chain.py > $o/${tag}_ncu_chain.log 2>&1
