@@ -42,7 +42,9 @@
 // tiles, and W rows: 22 %; raw-ring loads: 16 %; fences and the TMEM store drain: ~10 %).  Tried and measured: converting before
 // the wait on empty[s] (no change), a fully unrolled MMA-issue loop with compile-time operands (6 % SLOWER: tighter MMA issue
 // takes shared-memory cycles from the converters), line-contiguous cp.async with an XOR-swizzled raw ring (8x fewer
-// shared-memory wavefronts per copy, 1 % faster: kept), a third converter group (3 % faster: kept).
+// shared-memory wavefronts per copy, 1 % faster: kept), a third converter group (3 % faster: kept), the B tiles written half by the
+// Z rows and half by the W rows (10 % SLOWER: every thread then pays the generic->async proxy fence, which turns out to be the
+// expensive part of a Z-row thread's iteration, not its sixteen stores).
 #include "cov_device.cuh"
 
 #include <algorithm>
