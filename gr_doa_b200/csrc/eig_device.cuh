@@ -1,6 +1,7 @@
 // eig_device.cuh -- device code of the batched Jacobi eigensolver shared by eig.cu and fused.cu.
 #pragma once
 #include "doa_internal.h"
+#include "f32x2.cuh"
 
 namespace doa {
 namespace {
@@ -171,22 +172,24 @@ __device__ __forceinline__ void subspace_outputs(float2* S, const int j, const i
 #pragma unroll
     for (int i = 0; i < M; ++i) if (use_S) S[i + rank * M] = v[i];     // use_S false: S must survive (nothing is stored either)
     __syncwarp();
-    float2 gc[M];
+    // packed: (gx, gy) += (ei.x, ei.y) * ej.x, then += (ei.y, ei.x) * (ej.y, -ej.y) -- the scalar form's operations in its order
+    f32x2 gc[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) gc[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < M; ++i) gc[i] = pk2(0.f, 0.f);
     for (int n = 0; n < nn; ++n) {
       const float2 ej = S[j + n * M];
+      const f32x2 ejx = pk2(ej.x, ej.x), ejy = pk2(ej.y, -ej.y);
 #pragma unroll
       for (int i = 0; i < M; ++i) {
         const float2 ei = S[i + n * M];
-        gc[i].x = fmaf(ei.x, ej.x, gc[i].x); gc[i].x = fmaf(ei.y, ej.y, gc[i].x);
-        gc[i].y = fmaf(ei.y, ej.x, gc[i].y); gc[i].y = fmaf(-ei.x, ej.y, gc[i].y);
+        gc[i] = fma2(pk2(ei.x, ei.y), ejx, gc[i]);
+        gc[i] = fma2(pk2(ei.y, ei.x), ejy, gc[i]);
       }
     }
     if (live) {
       float2* dst = Gdst + (size_t)j * M;
 #pragma unroll
-      for (int i = 0; i < M; ++i) dst[i] = gc[i];
+      for (int i = 0; i < M; ++i) { float2 g; upk2(gc[i], g.x, g.y); dst[i] = g; }
     }
   }
 }

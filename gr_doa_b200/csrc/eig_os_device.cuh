@@ -104,8 +104,13 @@ __device__ __forceinline__ bool jacobi_os_solve(float2* S, const int j, const in
     const float piv = __shfl_sync(FULL, acc.x, c, M);
     const bool good = piv > 0.0f && piv < 3.0e38f;
     ok = ok && good;
-    const float d = sqrtf(good ? piv : 1.0f);
-    const float inv = 1.0f / d;
+    // 1 / sqrt(pivot) from the special-function unit plus one Newton step (relative error ~1e-7) instead of an IEEE square root
+    // and division on this serial chain: column c of L is then L(:, c) (1 + e) with |e| ~ 1e-7, a backward error of 2e |A(:, c)|
+    // in R -- the size of the rounding of R itself
+    const float pv = good ? piv : 1.0f;
+    float inv = mufu_rsq(pv);
+    inv = inv * fmaf(-0.5f * pv, inv * inv, 1.5f);
+    const float d = pv * inv;
     lrow[c] = (c == j) ? make_float2(d, 0.0f) : make_float2(acc.x * inv, acc.y * inv);
     if (c <= j) S[c + j * M] = lrow[c];
     __syncwarp();
