@@ -946,10 +946,21 @@ int doa_cuda_rootchain_run_device(doa_cuda_handle* h, const void* in_dev, long l
   ENTER(h);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   Lane& l = h->lane[0];
-  int a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains, h->fmt);
-  if (a < 0) return fail(h, a, "covariance launch rejected");
-  int b = launch_noise_subspace(l.R, h->M, h->T, nframes, nullptr, l.u, nullptr, st);
-  if (b < 0) return fail(h, b, "eigendecomposition launch rejected");
+  // 4 and 8 elements: covariance + eigensolver in the persistent warp-specialised kernel of the MUSIC chain (fused.cu, split
+  // form: the diagonal sums go to global memory, no scan) -- the covariance never leaves the SM and the streaming runs at the
+  // fused kernel's rate (cfg2: 2.47 + 0.09 ms as two kernels -> 2.1 ms); same device code, same bits.
+  int a = 0, b = 0;
+  if (dev_option(OPT_FUSED, 1)) {
+    a = launch_chain_fused(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, h->T, ScanTables(), 1, nullptr, nullptr, nullptr,
+                           st, h->d_gains, h->fmt, nullptr, l.u);
+    if (a < 0) return fail(h, a, "fused covariance + eigendecomposition launch rejected");
+  }
+  if (a == 0) {
+    a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains, h->fmt);
+    if (a < 0) return fail(h, a, "covariance launch rejected");
+    b = launch_noise_subspace(l.R, h->M, h->T, nframes, nullptr, l.u, nullptr, st);
+    if (b < 0) return fail(h, b, "eigendecomposition launch rejected");
+  }
   int c = launch_rootmusic_scratch(l.u, h->M, h->T, h->d, nframes, l.scratch, h->max_frames, (float*)out_aoa_dev, st);
   if (c < 0) return fail(h, c, "root finder launch rejected");
   h->launches = a + b + c;

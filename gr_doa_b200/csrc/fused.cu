@@ -91,7 +91,7 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
   constexpr int NTHREADS = (WS_P + WS_C) * 32;
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
-  const ZTab zt = ztab_fill(smem, zpair, P);
+  const ZTab zt = (zpair != nullptr) ? ztab_fill(smem, zpair, P) : ZTab();   // no scan table: the split form without a scan (Root-MUSIC chain)
   float2* Rbuf = reinterpret_cast<float2*>(smem + ((ztab_floats(P) + 3) & ~(size_t)3));   // [WS_NBUF][TILE][MM]
   float2* Gs = Rbuf + WS_NBUF * TILE * MM;                                 // [TILE][MM]
   float2* us = Gs + TILE * MM;                                       // [TILE][M]
@@ -242,10 +242,12 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
       bar_sync(BAR_FULL + b, NTHREADS);
       {
         const int g = ct / M, j = ct % M;
-        if (G_out != nullptr) {
-          // split form: the noise projector and its diagonal sums go to global memory, the scan runs as its own kernel (scan_tc.cu)
+        if (G_out != nullptr || u_out != nullptr) {
+          // split form: the noise projector and / or its diagonal sums go to global memory; the scan (scan_tc.cu, dev builds) or
+          // the Root-MUSIC root finder (root.cu: doa_cuda_rootchain_*) runs as its own kernel
           const long long f = lo + (long long)t * TILE + min(g, nt - 1);
-          noise_subspace_solve<M>(Rbuf + ((size_t)b * TILE + g) * MM, j, T, max_sweeps, g < nt, G_out + f * MM, u_out + f * M, nullptr);
+          noise_subspace_solve<M>(Rbuf + ((size_t)b * TILE + g) * MM, j, T, max_sweeps, g < nt, G_out ? G_out + f * MM : nullptr,
+                                  u_out ? u_out + f * M : nullptr, nullptr);
         } else {
           noise_subspace_solve<M>(Rbuf + ((size_t)b * TILE + g) * MM, j, T, max_sweeps, g < nt, Gs + g * MM, us + g * M, nullptr);
         }
@@ -254,7 +256,7 @@ chain_ws_kernel(const S* __restrict__ in, long long frame_stride, long long chan
       // no consumer-wide barrier, a warp whose matrices converge early starts scanning early.
       __syncwarp();
       if (t + WS_NBUF < ntiles) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NTHREADS); }
-      if (G_out != nullptr) continue;
+      if (G_out != nullptr || u_out != nullptr) continue;
       for (int i = cw * (32 / M); i < min(nt, (cw + 1) * (32 / M)); ++i) {
         const long long f = lo + (long long)t * TILE + i;
         if (K == 1)   // index_max: the global arg-max (find_local_max_impl.h:53-56), not a local-peak search
@@ -368,6 +370,8 @@ int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_
                        cudaStream_t st, const float2* gains, InputFormat fmt, float2* G_out, float2* u_out) {
   if (nframes <= 0 || (M != 8 && M != 4)) return 0;
   if (K < 1 || K > 4) return 0;                       // K > 4: the wide candidate lists
+  const bool split = G_out != nullptr || u_out != nullptr;
+  if (!split && tb.zpair == nullptr) return 0;        // a scan needs its table
   const bool vec2 = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
                     ((reinterpret_cast<uintptr_t>(in_v) & (fmt.sc16 ? 7u : 15u)) == 0);
   if (!vec2) return 0;
@@ -378,12 +382,12 @@ int launch_chain_fused(const void* in_v, long long frame_stride, long long chan_
     const float s2 = fmt.scale * fmt.scale;
 #ifdef DOA_DEV_KNOBS
     if (dev_option(OPT_WS_FILL, 0) == 2) {
-      if (M == 4) return launch_ws_cfg2<4, 8, 8, 6, 4, 2>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
-      return launch_ws_cfg2<8, 8, 8, 3, 4, 2>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
+      if (M == 4) return launch_ws_cfg2<4, 8, 8, 6, 4, 2>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2, G_out, u_out);
+      return launch_ws_cfg2<8, 8, 8, 3, 4, 2>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2, G_out, u_out);
     }
 #endif
-    if (M == 4) return launch_ws_cfg2<4, 8, 8, 6, 4, 0>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
-    return launch_ws_cfg2<8, 8, 8, 3, 4, 0>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2);
+    if (M == 4) return launch_ws_cfg2<4, 8, 8, 6, 4, 0>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2, G_out, u_out);
+    return launch_ws_cfg2<8, 8, 8, 3, 4, 0>(in, frame_stride, chan_stride, N, nframes, avg_method, T, tb, K, out_val, out_loc, out_bin, st, gains, s2, G_out, u_out);
   }
   const float2* in = static_cast<const float2*>(in_v);
   // Producer/consumer split, ring depth and tile buffers, measured at cfg3 with the packed (FFMA2) covariance: 8+8 warps,
