@@ -196,7 +196,8 @@ int doa_cuda_set_input_format(doa_cuda_handle* h, int format, float scale);
  *   "herk_tc"        default 1          0: CUDA-core tiled covariance at 64 elements instead of the tensor-core HERK
  *   "root_aberth"    default 1          0: Root-MUSIC by Hessenberg QR only
  *   "eig_onesided"   default 1          0: two-sided Jacobi eigensolver at 8..64 elements instead of the one-sided Jacobi on the
- *                                       Cholesky factor (results agree to ~1e-6 in the noise projector; NOT bit-identical)
+ *                                       Cholesky factor (results agree to ~1e-6 in the noise projector; NOT bit-identical);
+ *                                       2: at 17..64 elements pair columns instead of two-column blocks (comparison)
  *   "scan_wide", "spectrum_smem", "cov16_ring", "cov_groups", "jacobi_sweeps"   kernel variants of single stages
  * A library built with -DDOA_DEV_KNOBS (libdoa_cuda_dev.so: tools/, bit-identity tests) also carries the experimental fused
  * kernel configurations and accepts "ws_split", "ws_stages", "ws_nbuf", "ws4", "ws_tma", "ws_fill", "scan_tc_dbg", "fused16";
