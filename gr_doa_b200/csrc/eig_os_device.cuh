@@ -5,7 +5,7 @@
 // mutually orthogonal, L J_1 J_2 ... = U Sigma, gives R = U Sigma^2 U^H: the eigenvectors are the normalised columns
 // themselves and the eigenvalues their squared norms (Veselic & Hari).  Against the two-sided iteration of eig_device.cuh:
 //   * no eigenvector accumulator and no row rotations -- a step is one column fetch (2M shuffles), one complex dot product
-//     and one column update, all in packed f32x2 FMAs: ~170 warp-instructions per step instead of ~465 at M = 16;
+//     and one column update, all in packed f32x2 FMAs: 169 warp-instructions per step instead of 466 at M = 16;
 //   * 6-7 sweeps, like the two-sided iteration;
 //   * the Gram matrix being diagonalised is L^H L, whose condition is that of R, not of R^2, and Jacobi on a factor is
 //     relatively accurate: the projector is as close to the float64 one as LAPACK's (measured, tests).
@@ -16,10 +16,12 @@
 // no exchange of rotation parameters.  Squared column norms are recomputed at the start of a sweep and carried through it by
 // the rotation's own update (app - t|apq|, aqq + t|apq|).
 //
-// R / 2^e + delta I (2^e the trace's power of two, delta = 2^-14 of the scaled trace: below the noise floor of any covariance this path is given, far above fp32 rounding of a
-// rank-deficient one) is what gets factored; eigenvectors are unchanged, eigenvalues are reported as 2^e (|column|^2 - delta).  A
-// matrix whose factorisation meets a non-positive pivot (not a covariance: indefinite, zero or non-finite input) is reported
-// back to the caller with its staging area restored, and the caller runs the two-sided solver on it (noise_subspace_solve).
+// R / 2^e + delta I is what gets factored (2^e the trace's power of two, delta = 2^-14 of the scaled trace: far above the fp32
+// rounding of a rank-deficient covariance, so that one still factors; noise eigenvalues below delta merely cluster at delta,
+// which does not move the noise SUBSPACE -- tested at 40 dB SNR).  Eigenvectors are unchanged, eigenvalues are reported as
+// 2^e (|column|^2 - delta).  A matrix whose factorisation meets a non-positive pivot (not a covariance: indefinite, zero or
+// non-finite input) is reported back to the caller with its staging area restored, and the caller runs the two-sided solver on
+// it (noise_subspace_solve).
 #pragma once
 #include "eig_device.cuh"
 #include "f32x2.cuh"
