@@ -340,7 +340,7 @@ int launch_tiled(const S* in, long long frame_stride, long long chan_stride, int
 }  // namespace
 
 int launch_covariance(const void* in_v, long long frame_stride, long long chan_stride, int M, int N, int nframes,
-                      int avg_method, float2* out, cudaStream_t st, const float2* gains, InputFormat fmt) {
+                      int avg_method, float2* out, cudaStream_t st, const float2* gains, InputFormat fmt, void* tc_ws) {
   if (nframes <= 0) return 0;
   if (M > 64) return DOA_CUDA_EINVAL;
   const float bscale = (float)(0.5 / N);    // (0.5/d_snapshot_size), lib/autocorrelate_impl.cc:108
@@ -367,7 +367,7 @@ int launch_covariance(const void* in_v, long long frame_stride, long long chan_s
     default: break;
   }
   if (M == 64 && dev_option(OPT_HERK_TC, 1)) {   // tensor-core complex HERK (3xTF32) when alignment allows
-    const int r = launch_covariance_tc(in, frame_stride, chan_stride, M, N, nframes, avg_method, out, st, gains);
+    const int r = launch_covariance_tc(in, frame_stride, chan_stride, M, N, nframes, avg_method, out, st, gains, tc_ws);
     if (r != 0) return r;
   }
   return launch_tiled(in, frame_stride, chan_stride, M, N, nframes, out, scale, bscale, avg_method, st, gains);

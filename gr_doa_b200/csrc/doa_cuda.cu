@@ -82,6 +82,7 @@ struct Lane {   // one stream's worth of buffers (the chain's host path double-b
   double2* scratch = nullptr;
   int frames = 0;
   char* pin = nullptr; size_t pin_bytes = 0;   // page-locked host staging for small host-pointer calls (allocated on first use)
+  void* tc_ws = nullptr;                       // 64 elements: workspace of the tensor-core HERK's split tail (allocated on first use)
 };
 
 // Host threads of a multi-device handle: device 0 is driven by the calling thread, every further device by one persistent
@@ -199,7 +200,7 @@ static int fail(doa_cuda_handle* h, int code, const std::string& msg) { if (h) h
 
 static void free_lane(Lane& l) {
   cudaFree(l.in); cudaFree(l.R); cudaFree(l.G); cudaFree(l.u); cudaFree(l.spec); cudaFree(l.val); cudaFree(l.loc);
-  cudaFree(l.bin); cudaFree(l.aoa); cudaFree(l.vecs); cudaFree(l.scratch);
+  cudaFree(l.bin); cudaFree(l.aoa); cudaFree(l.vecs); cudaFree(l.scratch); cudaFree(l.tc_ws);
   if (l.pin) cudaFreeHost(l.pin);
   if (l.stream) cudaStreamDestroy(l.stream);
   l = Lane();
@@ -234,6 +235,14 @@ static int begin_create(doa_cuda_handle** out, doa_cuda_handle*& h, int kind, in
 
 template <typename Tp>
 static bool dalloc(Tp** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(Tp)) == cudaSuccess; }
+
+// 64 elements: the tensor-core HERK's split-tail workspace (counters zeroed once; the kernel leaves them zero), one per lane
+// because the chain's two lanes run on two streams.
+static bool alloc_tc_ws(const doa_cuda_handle* h, Lane& l) {
+  if (h->M != 64) return true;
+  const size_t n = covariance_tc_workspace_bytes();
+  return cudaMalloc(&l.tc_ws, n) == cudaSuccess && cudaMemset(l.tc_ws, 0, n) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+}
 
 static int finish_create(doa_cuda_handle** out, doa_cuda_handle* h, bool ok) {
   if (!ok) {
@@ -287,7 +296,7 @@ int doa_cuda_set_option(doa_cuda_handle* h, const char* key, int value) {
   static const struct { const char* name; Opt opt; } kNames[] = {
       {"fused", OPT_FUSED}, {"scan_tc", OPT_SCAN_TC}, {"sms_reserve", OPT_SMS_RESERVE}, {"cov_groups", OPT_COV_GROUPS},
       {"cov16_ring", OPT_COV16_RING}, {"herk_tc", OPT_HERK_TC}, {"scan_wide", OPT_SCAN_WIDE}, {"spectrum_smem", OPT_SPECTRUM_SMEM},
-      {"root_aberth", OPT_ROOT_ABERTH}, {"jacobi_sweeps", OPT_JACOBI_SWEEPS}, {"tma", OPT_TMA}, {"eig_onesided", OPT_EIG_ONESIDED}, {"ws_split", OPT_WS_SPLIT}, {"ws_stages", OPT_WS_STAGES},
+      {"root_aberth", OPT_ROOT_ABERTH}, {"jacobi_sweeps", OPT_JACOBI_SWEEPS}, {"tma", OPT_TMA}, {"eig_onesided", OPT_EIG_ONESIDED}, {"herk_split", OPT_HERK_SPLIT}, {"ws_split", OPT_WS_SPLIT}, {"ws_stages", OPT_WS_STAGES},
       {"ws_nbuf", OPT_WS_NBUF}, {"ws4", OPT_WS4}, {"ws_tma", OPT_WS_TMA}, {"ws_fill", OPT_WS_FILL}, {"scan_tc_dbg", OPT_SCAN_TC_DBG}, {"fused16", OPT_FUSED16}};
   if (!h || !key) return DOA_CUDA_EINVAL;
   for (const auto& n : kNames) {
@@ -400,7 +409,7 @@ int doa_cuda_autocorrelate_create(doa_cuda_handle** out, int inputs, int snapsho
   const size_t Lpad = (((size_t)(max_frames - 1) * h->hop + h->N) + 1) & ~(size_t)1;
   l.in_elems = Lpad * h->M;
   bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess && dalloc(&l.in, l.in_elems) &&
-            dalloc(&l.R, (size_t)max_frames * h->M * h->M);
+            dalloc(&l.R, (size_t)max_frames * h->M * h->M) && alloc_tc_ws(h, l);
   return finish_create(out, h, ok);
 }
 
@@ -415,7 +424,7 @@ int doa_cuda_autocorrelate_run_device(doa_cuda_handle* h, const void* in_dev, lo
   if (nframes < 0) return fail(h, DOA_CUDA_EINVAL, "nframes < 0");
   ENTER(h);
   int n = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, (float2*)out_dev,
-                            (cudaStream_t)cuda_stream, h->d_gains, h->fmt);
+                            (cudaStream_t)cuda_stream, h->d_gains, h->fmt, h->lane[0].tc_ws);
   if (n < 0) return fail(h, n, "covariance launch rejected");
   h->launches = n;
   CK(h, cudaGetLastError());
@@ -776,7 +785,7 @@ int doa_cuda_chain_create(doa_cuda_handle** out, int inputs, int snapshot_size, 
     l.in_elems = std::max((size_t)chunk * h->M * h->N + 2 * (size_t)h->M, i == 0 ? Lpad_max * h->M : (size_t)0);
     ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess && dalloc(&l.in, l.in_elems) &&
          dalloc(&l.R, nf * mm) && dalloc(&l.G, nf * mm) && dalloc(&l.u, nf * h->M) && dalloc(&l.val, nf * h->K) &&
-         dalloc(&l.loc, nf * h->K) && dalloc(&l.bin, nf * h->K);
+         dalloc(&l.loc, nf * h->K) && dalloc(&l.bin, nf * h->K) && alloc_tc_ws(h, l);
   }
   return finish_create(out, h, ok);
 }
@@ -827,7 +836,7 @@ static int chain_on_lane(doa_cuda_handle* h, Lane& l, const void* in_dev, long l
   if (a > 0) {
     if (prof) { CK(h, cudaEventRecord(ev[1], st)); CK(h, cudaEventRecord(ev[2], st)); }
   } else {
-    a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains, h->fmt);
+    a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains, h->fmt, l.tc_ws);
     if (a < 0) return fail(h, a, "covariance launch rejected");
     if (prof) CK(h, cudaEventRecord(ev[1], st));
     b = launch_noise_subspace(l.R, h->M, h->T, nframes, l.G, l.u, nullptr, st);
@@ -934,7 +943,7 @@ int doa_cuda_rootchain_create(doa_cuda_handle** out, int inputs, int snapshot_si
   l.in_elems = std::max(Lpad * h->M, (size_t)max_frames * h->M * h->N);     // streams or independent frames
   bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess && dalloc(&l.in, l.in_elems) &&
             dalloc(&l.R, max_frames * mm) && dalloc(&l.u, (size_t)max_frames * h->M) &&
-            dalloc(&l.aoa, (size_t)max_frames * h->T) && dalloc(&l.scratch, n * n * (size_t)max_frames);
+            dalloc(&l.aoa, (size_t)max_frames * h->T) && dalloc(&l.scratch, n * n * (size_t)max_frames) && alloc_tc_ws(h, l);
   return finish_create(out, h, ok);
 }
 
@@ -956,7 +965,7 @@ int doa_cuda_rootchain_run_device(doa_cuda_handle* h, const void* in_dev, long l
     if (a < 0) return fail(h, a, "fused covariance + eigendecomposition launch rejected");
   }
   if (a == 0) {
-    a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains, h->fmt);
+    a = launch_covariance(in_dev, frame_stride, chan_stride, h->M, h->N, nframes, h->avg, l.R, st, h->d_gains, h->fmt, l.tc_ws);
     if (a < 0) return fail(h, a, "covariance launch rejected");
     b = launch_noise_subspace(l.R, h->M, h->T, nframes, nullptr, l.u, nullptr, st);
     if (b < 0) return fail(h, b, "eigendecomposition launch rejected");

@@ -22,11 +22,14 @@ struct InputFormat {
 // gains (may be null): M per-channel complex gains applied in front of the covariance, R' = D R D^H.
 int launch_covariance(const void* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
                       int avg_method, float2* out, cudaStream_t st, const float2* gains = nullptr,
-                      InputFormat fmt = InputFormat());
+                      InputFormat fmt = InputFormat(), void* tc_ws = nullptr);
 
-// Tensor-core path of stage 1 for M = 64 (herk_tc.cu): 1 if launched, 0 if the shape is not covered.
+// Tensor-core path of stage 1 for M = 64 (herk_tc.cu): 1 if launched, 0 if the shape is not covered.  ws (may be null):
+// covariance_tc_workspace_bytes() of zero-initialised device memory, one per stream, for sharing the frames of an incomplete
+// last round between SMs (split-K with a fixed-order fold; same bits with or without it).
 int launch_covariance_tc(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
-                         int avg_method, float2* out, cudaStream_t st, const float2* gains = nullptr);
+                         int avg_method, float2* out, cudaStream_t st, const float2* gains = nullptr, void* ws = nullptr);
+size_t covariance_tc_workspace_bytes();
 
 // Stage 2a.  Hermitian EVD (batched Jacobi) of R (upper triangle read, like cheevd 'U') and the noise subspace:
 //   G[f][r + c*M] = sum_{n < M-T} e_n[r] conj(e_n[c])   (may be null)
@@ -95,7 +98,7 @@ int launch_rootmusic_scratch(const float2* u, int M, int T, float norm_spacing, 
 // no global mutable state, no lock, no lookup on the launch path.
 enum Opt {
   OPT_FUSED, OPT_SCAN_TC, OPT_SMS_RESERVE, OPT_COV_GROUPS, OPT_COV16_RING, OPT_HERK_TC, OPT_SCAN_WIDE, OPT_SPECTRUM_SMEM,
-  OPT_ROOT_ABERTH, OPT_JACOBI_SWEEPS, OPT_TMA, OPT_EIG_ONESIDED,
+  OPT_ROOT_ABERTH, OPT_JACOBI_SWEEPS, OPT_TMA, OPT_EIG_ONESIDED, OPT_HERK_SPLIT,
   // kernel variants that only exist in a -DDOA_DEV_KNOBS build (libdoa_cuda_dev.so, used by tools/ and the bit-identity tests)
   OPT_WS_SPLIT, OPT_WS_STAGES, OPT_WS_NBUF, OPT_WS4, OPT_WS_TMA, OPT_WS_FILL, OPT_SCAN_TC_DBG, OPT_FUSED16,
   OPT_COUNT

@@ -117,7 +117,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __global__ void __launch_bounds__(TC_THREADS, 1)
 herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long long chan_stride, int N, int nframes,
-                 float2* __restrict__ out, float scale, float bscale, int avg_method, const float2* __restrict__ gains) {
+                 float2* __restrict__ out, float scale, float bscale, int avg_method, const float2* __restrict__ gains,
+                 int nfull, int seg_len, int tail_S, int tail_sps, float* __restrict__ ws_part, unsigned* __restrict__ ws_cnt) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment by OFFSETTING the shared array (an integer round trip would turn every access into a generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -126,6 +127,7 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
   float* stg = reinterpret_cast<float*>(smem + TC_OP_STAGES * 2 * TC_TILE_BYTES + TC_GROUPS * TC_RAW_STAGES * TC_RAW_STAGE_BYTES);   // [128][65]
   __shared__ uint64_t full_bar[TC_OP_STAGES], empty_bar[TC_OP_STAGES], chunk_full[2], chunk_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int tail_last_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -143,8 +145,19 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
   const uint32_t tmem_d = tmem_base_s;
 
   const int spf = (N + 15) / 16;                                             // stages per frame (16 complex samples each)
-  const int my_frames = (nframes > (int)blockIdx.x) ? (nframes - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const long long total = (long long)my_frames * spf;
+  // Work units of this CTA: whole frames blockIdx.x + r * gridDim.x < nfull, then at most one TAIL unit -- a range of whole
+  // segments of one of the nframes - nfull frames that do not fill a round of the grid (split-K, see launch_covariance_tc).
+  const int my_frames = (nfull > (int)blockIdx.x) ? (nfull - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int nseg = (spf + seg_len - 1) / seg_len;
+  const bool has_tail = (int)blockIdx.x < (nframes - nfull) * tail_S;
+  int tail_idx = 0, tail_seg0 = 0, tail_start = 0, tail_count = 0;
+  if (has_tail) {
+    tail_idx = (int)blockIdx.x / tail_S;
+    tail_seg0 = ((int)blockIdx.x % tail_S) * tail_sps;
+    tail_start = tail_seg0 * seg_len;
+    tail_count = min(spf, min(nseg, tail_seg0 + tail_sps) * seg_len) - tail_start;
+  }
+  const long long total = (long long)my_frames * spf + tail_count;
 
   if (warp == 0) {
     // ================================ MMA issuer ================================
@@ -156,6 +169,7 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
       const uint64_t desc0 = umma_desc(smem_u32(op));
       const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
       int s = 0; uint32_t ph = 0; int sf = 0;
+      int fr = 0, cur = (my_frames > 0) ? spf : tail_count;   // unit index, stages of the current unit
       int cb = 0, in_chunk = 0; uint32_t ce_ph = 0u;   // parity bits, one per buffer (bit b)
       long long chunks = 0;
       for (long long q = 0; q < total; ++q) {
@@ -169,8 +183,8 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
         const uint32_t ahi = tmem_d + TC_A_COL + (uint32_t)s * 64u, alo = ahi + 32u;
         const uint32_t dacc = tmem_d + (uint32_t)cb * 128u;
         ++sf; ++in_chunk;
-        const bool frame_end = (sf == spf);
-        const bool chunk_end = (in_chunk == TC_CHUNK) || frame_end;
+        const bool frame_end = (sf == cur);
+        const bool chunk_end = (in_chunk == TC_CHUNK) || frame_end;   // segments are whole chunks: no chunk straddles one
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -184,7 +198,7 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
         }
         __syncwarp();
         if (chunk_end) { cb ^= 1; in_chunk = 0; }
-        if (frame_end) sf = 0;
+        if (frame_end) { sf = 0; ++fr; cur = (fr < my_frames) ? spf : tail_count; }
         if (++s == TC_OP_STAGES) { s = 0; ph ^= 1u; }
       }
     }
@@ -209,24 +223,33 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
     const bool is_w = row >= TC_M;
     const uint32_t a_lane = tmem_d + TC_A_COL + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t row_off = ((uint32_t)cch >> 3) * 1024u + ((uint32_t)cch & 7u) * 128u, row_x = (uint32_t)cch & 7u;
-    int isf = g % spf;
     constexpr int NG = TC_GROUPS;
-    long long fi = (long long)blockIdx.x + (long long)(g / spf) * gridDim.x;
-    const float2* ibase = in + fi * frame_stride + (long long)lch0 * chan_stride;
+    const int nunits = my_frames + (has_tail ? 1 : 0);
+    // loader position: unit iu, stage isf of its icnt stages (isf + ioff = stage of the frame)
+    int iu = 0, isf = g, icnt = 0, ioff = 0;
+    const float2* ibase = in;
+    auto set_unit = [&]() {
+      const bool tl = iu >= my_frames;
+      icnt = tl ? tail_count : spf;
+      ioff = tl ? tail_start : 0;
+      const long long fi = tl ? (long long)nfull + tail_idx : (long long)blockIdx.x + (long long)iu * gridDim.x;
+      ibase = in + fi * frame_stride + (long long)lch0 * chan_stride;
+    };
+    auto normalize = [&]() {
+      while (isf >= icnt) { isf -= icnt; if (++iu >= nunits) break; set_unit(); }
+    };
+    if (nunits > 0) { set_unit(); normalize(); }
     const long long cstep = 16 * chan_stride;      // copy j reads channel lch0 + 16 j
     int irs = 0; long long qi = g;
     auto issue = [&]() {
-      const int tj = isf * 16 + 2 * lpc;           // this thread's two complex samples of the stage
+      const int tj = (ioff + isf) * 16 + 2 * lpc;  // this thread's two complex samples of the stage
       const int nb = (tj < N) ? 16 : 0;            // N is even (launcher): a 16-byte piece is all in or all out
       float4* dst = lraw + (size_t)irs * (8 * TC_M);
       const float2* srcp = ibase + (nb ? tj : 0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) cp_async16z(dst + ((lch0 + 16 * j) ^ lpc), srcp + j * cstep, nb);
       isf += NG;
-      if (isf >= spf) {
-        do { isf -= spf; fi += gridDim.x; } while (isf >= spf);
-        ibase = in + fi * frame_stride + (long long)lch0 * chan_stride;
-      }
+      normalize();
       if (++irs == TC_RAW_STAGES) irs = 0;
       qi += NG;
     };
@@ -296,30 +319,82 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
     const uint32_t lane_addr = tmem_d + ((uint32_t)(q4 * 32) << 16);
     uint32_t cf_ph = 0u;                                           // parity bits, one per buffer
     int cb = 0;
-    long long fcur = blockIdx.x;
-    for (int fr = 0; fr < my_frames; ++fr) {
-      float acc[TC_M];
+    const int nunits = my_frames + (has_tail ? 1 : 0);
+    for (int un = 0; un < nunits; ++un) {
+      const bool tl = un >= my_frames;
+      const int cnt = tl ? tail_count : spf;
+      const long long fcur = tl ? (long long)nfull + tail_idx : (long long)blockIdx.x + (long long)un * gridDim.x;
+      const int segs = (cnt + seg_len - 1) / seg_len;
+      // A frame is the sum of its SEGMENTS (seg_len stages each, a function of N alone) taken in order, each segment the
+      // in-order sum of its chunks: the association is the same whether one CTA walks the frame or several share it.
+      for (int sg = 0; sg < segs; ++sg) {
+        float acc[TC_M];
 #pragma unroll
-      for (int c = 0; c < TC_M; ++c) acc[c] = 0.0f;
-      const int nchunks = (spf + TC_CHUNK - 1) / TC_CHUNK;
-      for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(&chunk_full[cb], (cf_ph >> cb) & 1u); cf_ph ^= 1u << cb;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c = 0; c < TC_M; ++c) acc[c] = 0.0f;
+        const int nchunks = (min(seg_len, cnt - sg * seg_len) + TC_CHUNK - 1) / TC_CHUNK;
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&chunk_full[cb], (cf_ph >> cb) & 1u); cf_ph ^= 1u << cb;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {               // columns 16h.. of the hi*hi block and of the cross-term block
-          uint32_t v0[16], v1[16];
-          tmem_ld16(lane_addr + (uint32_t)cb * 128u + (uint32_t)h * 16u, v0);
-          tmem_ld16(lane_addr + (uint32_t)cb * 128u + 64u + (uint32_t)h * 16u, v1);
-          tmem_ld_wait();
+          for (int h = 0; h < 4; ++h) {               // columns 16h.. of the hi*hi block and of the cross-term block
+            uint32_t v0[16], v1[16];
+            tmem_ld16(lane_addr + (uint32_t)cb * 128u + (uint32_t)h * 16u, v0);
+            tmem_ld16(lane_addr + (uint32_t)cb * 128u + 64u + (uint32_t)h * 16u, v1);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[16 * h + j] += __uint_as_float(v0[j]) + __uint_as_float(v1[j]);
+            for (int j = 0; j < 16; ++j) acc[16 * h + j] += __uint_as_float(v0[j]) + __uint_as_float(v1[j]);
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&chunk_empty[cb]);
+          cb ^= 1;
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(&chunk_empty[cb]);
-        cb ^= 1;
-      }
+        if (!tl) {                                    // running total of the frame in the staging area (own row: no barrier)
+          if (sg == 0) {
 #pragma unroll
-      for (int c = 0; c < TC_M; ++c) stg[row * 65 + c] = acc[c];
+            for (int c = 0; c < TC_M; ++c) stg[row * 65 + c] = acc[c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < TC_M; ++c) stg[row * 65 + c] += acc[c];
+          }
+        } else {                                      // shared frame: the segment goes to the workspace
+          float4* p = reinterpret_cast<float4*>(ws_part + (((size_t)tail_idx * nseg + tail_seg0 + sg) * TC_ROWS + row) * TC_M);
+#pragma unroll
+          for (int c = 0; c < TC_M / 4; ++c) __stcg(p + c, make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]));
+        }
+      }
+      if (tl) {
+        // The CTA that delivers the frame's last range folds all segments, in segment order, and emits the frame.
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (at == 0) {
+          const unsigned ticket = atomicAdd(&ws_cnt[tail_idx], 1u);
+          const int last = (ticket == (unsigned)(tail_S - 1));
+          if (last) ws_cnt[tail_idx] = 0u;           // ready for the next launch (nobody else touches it in this one)
+          tail_last_s = last;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (!tail_last_s) continue;
+        __threadfence();
+        const float4* p = reinterpret_cast<const float4*>(ws_part + (((size_t)tail_idx * nseg) * TC_ROWS + row) * TC_M);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {                 // 16 columns at a time (registers)
+          float4 a[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) a[c] = __ldcg(p + 4 * q + c);
+          for (int sg = 1; sg < nseg; ++sg) {
+            float4 v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = __ldcg(p + (size_t)sg * (TC_ROWS * TC_M / 4) + 4 * q + c);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { a[c].x += v[c].x; a[c].y += v[c].y; a[c].z += v[c].z; a[c].w += v[c].w; }
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float* d = stg + row * 65 + 16 * q + 4 * c;
+            d[0] = a[c].x; d[1] = a[c].y; d[2] = a[c].z; d[3] = a[c].w;
+          }
+        }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       float2* o = out + fcur * (long long)(TC_M * TC_M);
       for (int e = at; e < TC_M * TC_M; e += 128) {
@@ -334,7 +409,6 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
         o[e] = v;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");               // staging area free again
-      fcur += gridDim.x;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -344,9 +418,26 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
 
 }  // namespace
 
+// Workspace of the split tail (below): 256 frame counters, then per shareable frame TC_MAX_SEGS partial sums of 128 x 64 floats.
+constexpr int TC_MAX_SEGS = 8;           // segments per frame (the canonical association of a frame's sum; also the widest split)
+constexpr int TC_WS_FRAMES = 128;        // frames a launch may share between CTAs (at most half the grid)
+constexpr size_t TC_WS_CNT_BYTES = 1024;
+size_t covariance_tc_workspace_bytes() {
+  return TC_WS_CNT_BYTES + (size_t)TC_WS_FRAMES * TC_MAX_SEGS * TC_ROWS * TC_M * sizeof(float);
+}
+
 // Returns 1 if launched, 0 if the shape is not covered (caller uses the CUDA-core kernels).
+//
+// Split tail (ws != null: covariance_tc_workspace_bytes() of zero-initialised device memory owned by the caller's handle and
+// used by one stream at a time).  A persistent CTA takes whole frames, so nframes = r * SMs + t leaves the last round to t
+// SMs (512 frames on 148 SMs: a fourth round on 68 of them, 13 % of the kernel).  When t <= SMs / 2 those t frames are
+// shared instead: S CTAs take consecutive ranges of whole segments of one frame, park the per-segment partial sums in the
+// workspace, and the CTA whose ticket is the last folds ALL segments of the frame in segment order and emits it.  Whole
+// frames are accumulated with the same association (segments in order), so a frame's bits do not depend on whether it was
+// shared, on the batch size or on its position in the batch.  A call of a few frames (GNU Radio hands a block a handful per
+// work()) runs on up to 8 SMs per frame instead of one.
 int launch_covariance_tc(const float2* in, long long frame_stride, long long chan_stride, int M, int N, int nframes,
-                         int avg_method, float2* out, cudaStream_t st, const float2* gains) {
+                         int avg_method, float2* out, cudaStream_t st, const float2* gains, void* ws) {
   if (M != TC_M || nframes <= 0) return 0;
   const bool aligned = (N % 2 == 0) && (frame_stride % 2 == 0) && (chan_stride % 2 == 0) &&
                        ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
@@ -357,9 +448,21 @@ int launch_covariance_tc(const float2* in, long long frame_stride, long long cha
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = std::min(nframes, sms);
+  const int spf = (N + 15) / 16;
+  // segment length: a multiple of the chunk, at most TC_MAX_SEGS segments per frame -- a function of N alone
+  const int seg_len = std::max(TC_CHUNK, ((spf + TC_MAX_SEGS - 1) / TC_MAX_SEGS + TC_CHUNK - 1) / TC_CHUNK * TC_CHUNK);
+  const int nseg = (spf + seg_len - 1) / seg_len;
+  int grid = std::min(nframes, sms), nfull = nframes, S = 0, sps = 0;
+  const int t = nframes % sms;
+  if (ws != nullptr && dev_option(OPT_HERK_SPLIT, 1) && t > 0 && t <= TC_WS_FRAMES && nseg >= 2 && sms / t >= 2) {
+    sps = (nseg + std::min(sms / t, nseg) - 1) / std::min(sms / t, nseg);   // segments per CTA
+    S = (nseg + sps - 1) / sps;                                               // CTAs per shared frame (every one non-empty)
+    if (S >= 2) { grid = (nframes > sms) ? sms : t * S; nfull = nframes - t; } else { S = 0; sps = 0; }
+  }
   herk_tc64_kernel<<<grid, TC_THREADS, smem, st>>>(in, frame_stride, chan_stride, N, nframes, out, (float)(1.0 / N),
-                                                   (float)(0.5 / N), avg_method, gains);
+                                                   (float)(0.5 / N), avg_method, gains, nfull, seg_len, S, sps,
+                                                   ws ? reinterpret_cast<float*>(static_cast<char*>(ws) + TC_WS_CNT_BYTES) : nullptr,
+                                                   static_cast<unsigned*>(ws));
   return 1;
 }
 

@@ -274,6 +274,27 @@ def test_large_array_covariance_tensor_core(doa, oracle, torch_cuda, N, overlap,
     assert np.abs(Rm - np.conj(np.transpose(Rm, (0, 2, 1)))).max() <= 4e-6 * np.abs(Rm).max()
 
 
+@pytest.mark.parametrize("N,B", [(1000, 3), (2048, 75), (4096, 150), (16384, 5), (16384, 1), (528, 200)])
+def test_large_array_split_tail_keeps_the_bits(doa, torch_cuda, N, B):
+    """M = 64: frames that do not fill a round of the persistent grid are shared between CTAs (split-K over whole segments,
+    fixed-order fold: herk_tc.cu).  A frame's sum has the same association either way, so the covariance is bit-identical with
+    the split off, does not depend on the batch a frame came in, and repeats exactly (the fold order is not the arrival order)."""
+    from gr_doa_b200 import synth
+    x = synth.stream_numpy(B, 64, N, 0, [40.0, 75.0, 120.0], seed=7 * N + B)
+    ac = doa.autocorrelate(64, N, 0, 1, max_frames=B)
+    got = {}
+    for split in (0, 1, 1):
+        ac.set_option("herk_split", split)
+        r = ac.work(x)
+        if split in got:
+            assert np.array_equal(got[split], r)
+        got[split] = r
+    assert np.array_equal(got[0], got[1])
+    nb = max(1, B // 2)
+    sub = doa.autocorrelate(64, N, 0, 1, max_frames=nb).work(x[:, : nb * N])
+    assert np.array_equal(sub, got[1][:nb])
+
+
 # ---- find_local_max: bit-exact on anything ---------------------------------------------------------------------------------
 def unambiguous(vecs, K):
     """Rows whose K highest local peaks are well defined.  The reference orders equal peak heights with an unstable
