@@ -31,12 +31,15 @@
 //                      (integer round-to-nearest on the tf32 boundary), (im, -re) for W rows, tcgen05.st into the A ring;
 //                      Z rows also store the swizzled B tiles; fences, arrive on full[s].  They run ahead across frames.
 //   warps 13..16     : adders + epilogue.  Thread = one TMEM lane (row of [Re R; Im R]), 64 fp32 register accumulators:
-//                      wait chunk_full[b], tcgen05.ld both column blocks, add, arrive chunk_empty[b]; at the frame end stage
-//                      the 128 x 64 result in shared memory, combine Re/Im, scale, forward-backward term, store R.
+//                      wait chunk_full[b], tcgen05.ld both column blocks, add, arrive chunk_empty[b]; at the end of a SEGMENT
+//                      (at most eight per frame, a stage count that depends on N alone) add the registers to the frame's
+//                      running total in the staging area; at the frame end combine Re/Im, scale, forward-backward term, store R.
+// Frames that do not fill a round of the grid are shared between CTAs by segment ranges, the partial sums folded in segment
+// order by the last CTA to finish (launch_covariance_tc below): the association of a frame's sum never depends on the batch.
 // TMEM (512 columns): accumulators @0 and @128, A ring @256 + 64 s (32 hi | 32 lo columns per stage, 4 stages).
 //
-// Measured (B200, 512 frames of 64 x 16384): 2.08 ms = 2.1 TB/s of input, tensor pipe 41 % busy (ncu), against 5.30 ms for the
-// CUDA-core tiled kernel.  What the round-2 profile (profiles/r02_ncu_herk_tc.txt) says about the rest: the converters never wait
+// Measured (B200, 512 frames of 64 x 16384): 1.93 ms = 2.2 TB/s of input (2.10 ms before the split tail; tensor pipe 41 % busy
+// under ncu then), against 5.30 ms for the CUDA-core tiled kernel.  What the round-2 profile (profiles/r02_ncu_herk_tc.txt) says about the rest: the converters never wait
 // for the tensor core (1.6 % of their samples at empty[s]) and the MMA warp waits for them 29 % of its time -- a converter
 // iteration is ~1900 clk of dependent latency for ~250 instructions (group barrier skew between Z rows, which also store the B
 // tiles, and W rows: 22 %; raw-ring loads: 16 %; fences and the TMEM store drain: ~10 %).  Tried and measured: converting before
@@ -57,6 +60,7 @@ constexpr int TC_ROWS = 128;             // rows of [Z; W]
 constexpr int TC_OP_STAGES = 4;          // operand ring depth: A = 64 TMEM columns (hi | lo), B = 16 KB smem (hi | lo tiles of 64 x 128 B)
 constexpr int TC_RAW_STAGES = 5;         // raw fp32 ring depth PER converter group (8 KB per stage)
 constexpr int TC_CHUNK = 4;              // stages (= 16 hi*hi MMAs) per big-accumulator chunk
+constexpr int TC_MAX_SEGS = 8;           // segments per frame (the canonical association of a frame's sum; also the widest split)
 constexpr int TC_TILE_BYTES = TC_M * 128; // one B tile (Z_hi or Z_lo): 64 rows x 128 B
 #ifndef DOA_HERK_GROUPS
 #define DOA_HERK_GROUPS 3   // measured: 2 groups 2.15 ms, 3 groups 2.08 ms per 512 frames (the converters are latency-bound: more of them in flight)
@@ -376,23 +380,18 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
         if (!tail_last_s) continue;
         __threadfence();
         const float4* p = reinterpret_cast<const float4*>(ws_part + (((size_t)tail_idx * nseg) * TC_ROWS + row) * TC_M);
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {                 // 16 columns at a time (registers)
-          float4 a[4];
+#pragma unroll 2
+        for (int q = 0; q < TC_M / 4; ++q) {          // four columns at a time, every segment's load in flight together
+          float4 v[TC_MAX_SEGS];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) a[c] = __ldcg(p + 4 * q + c);
-          for (int sg = 1; sg < nseg; ++sg) {
-            float4 v[4];
+          for (int sg = 0; sg < TC_MAX_SEGS; ++sg)
+            v[sg] = (sg < nseg) ? __ldcg(p + (size_t)sg * (TC_ROWS * TC_M / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 a = v[0];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) v[c] = __ldcg(p + (size_t)sg * (TC_ROWS * TC_M / 4) + 4 * q + c);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { a[c].x += v[c].x; a[c].y += v[c].y; a[c].z += v[c].z; a[c].w += v[c].w; }
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float* d = stg + row * 65 + 16 * q + 4 * c;
-            d[0] = a[c].x; d[1] = a[c].y; d[2] = a[c].z; d[3] = a[c].w;
-          }
+          for (int sg = 1; sg < TC_MAX_SEGS; ++sg)
+            if (sg < nseg) { a.x += v[sg].x; a.y += v[sg].y; a.z += v[sg].z; a.w += v[sg].w; }
+          float* d = stg + row * 65 + 4 * q;
+          d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -419,7 +418,6 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
 }  // namespace
 
 // Workspace of the split tail (below): 256 frame counters, then per shareable frame TC_MAX_SEGS partial sums of 128 x 64 floats.
-constexpr int TC_MAX_SEGS = 8;           // segments per frame (the canonical association of a frame's sum; also the widest split)
 constexpr int TC_WS_FRAMES = 128;        // frames a launch may share between CTAs (at most half the grid)
 constexpr size_t TC_WS_CNT_BYTES = 1024;
 size_t covariance_tc_workspace_bytes() {

@@ -194,6 +194,8 @@ int doa_cuda_set_input_format(doa_cuda_handle* h, int format, float scale);
  *   "tma"            default 1          0: per-lane cp.async ring fills in the fused kernel instead of tensor-map TMA boxes
  *   "scan_tc"        default 1          0: Horner scan on the CUDA cores instead of the tensor-core contraction (unfused chain)
  *   "herk_tc"        default 1          0: CUDA-core tiled covariance at 64 elements instead of the tensor-core HERK
+ *   "herk_split"     default 1          0: the tensor-core HERK gives every frame to one SM even when the batch does not fill a
+ *                                       round of the SMs (1: such frames are shared between SMs, same bits)
  *   "root_aberth"    default 1          0: Root-MUSIC by Hessenberg QR only
  *   "eig_onesided"   default 1          0: two-sided Jacobi eigensolver at 8..64 elements instead of the one-sided Jacobi on the
  *                                       Cholesky factor (results agree to ~1e-6 in the noise projector; NOT bit-identical);
