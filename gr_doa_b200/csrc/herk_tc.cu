@@ -62,6 +62,9 @@ constexpr int TC_RAW_STAGES = 5;         // raw fp32 ring depth PER converter gr
 constexpr int TC_CHUNK = 4;              // stages (= 16 hi*hi MMAs) per big-accumulator chunk
 constexpr int TC_MAX_SEGS = 8;           // segments per frame (the canonical association of a frame's sum; also the widest split)
 constexpr int TC_TILE_BYTES = TC_M * 128; // one B tile (Z_hi or Z_lo): 64 rows x 128 B
+#ifndef DOA_HERK_EXP
+#define DOA_HERK_EXP 0      // timing experiments only (tools/herk_bound_exp.sh): bit 0 no A_lo Z_hi^T MMA, bit 1 no A_lo store, bit 2 no B tile stores
+#endif
 #ifndef DOA_HERK_GROUPS
 #define DOA_HERK_GROUPS 3   // measured: 2 groups 2.15 ms, 3 groups 2.08 ms per 512 frames (the converters are latency-bound: more of them in flight)
 #endif
@@ -195,7 +198,9 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
             // the Z_hi and Z_lo tiles are contiguous: one 128-row B operand
             const uint64_t db = ((uint64_t)desc_hi << 32) | (b32 + (uint32_t)k * 2u);
             umma_tf32_ts(dacc, ahi + k * 8, db, idesc128, k == 0 ? (uint32_t)(in_chunk != 1) : 1u);   // A_hi [Z_hi; Z_lo]^T
+#if !(DOA_HERK_EXP & 1)
             umma_tf32_ts(dacc + 64u, alo + k * 8, db, idesc64, 1u);                                   // A_lo Z_hi^T
+#endif
           }
           umma_commit(&empty_bar[s]);                               // stage s reusable once these MMAs retire
           if (chunk_end) umma_commit(&chunk_full[cb]);
@@ -298,7 +303,7 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
             }
           }
         }
-        if (!is_w) {             // Z rows are also the B operand: swizzled K-major tiles in shared memory
+        if (!is_w && !(DOA_HERK_EXP & 4)) {             // Z rows are also the B operand: swizzled K-major tiles in shared memory
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t o = (((uint32_t)(4 * h + j)) ^ row_x) << 4;
@@ -307,7 +312,9 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
           }
         }
         tmem_st16(a_lane + (uint32_t)s * 64u + (uint32_t)h * 16u, hi);
+#if !(DOA_HERK_EXP & 2)
         tmem_st16(a_lane + (uint32_t)s * 64u + 32u + (uint32_t)h * 16u, lo);
+#endif
       }
       if (!is_w) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
