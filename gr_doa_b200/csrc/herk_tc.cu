@@ -38,6 +38,11 @@
 // order by the last CTA to finish (launch_covariance_tc below): the association of a frame's sum never depends on the batch.
 // TMEM (512 columns): accumulators @0 and @128, A ring @256 + 64 s (32 hi | 32 lo columns per stage, 4 stages).
 //
+// What bounds it (end of round 2): the shared-memory port.  The MMA warp's issue sequence is back-pressured by the tensor pipe (a second
+// issuer warp changes nothing), the pipe needs ~800 clk per stage against 384 nominal and ncu shows it active 44 % of the time: it
+// waits for its B operand behind the converters' traffic (65 KB per stage through a 128 B/clk port = 510 clk before arbitration).
+// A timing-only build without the A_lo Z_hi^T MMAs (8 KB fewer operand reads per stage) is 8 % faster; that product is the
+// (negated) transpose of A_hi Z_lo^T, so it could be dropped for real at the price of a per-segment exchange of the cross term.
 // Measured (B200, 512 frames of 64 x 16384): 1.93 ms = 2.2 TB/s of input (2.10 ms before the split tail; tensor pipe 41 % busy
 // under ncu then), against 5.30 ms for the CUDA-core tiled kernel.  What the round-2 profile (profiles/r02_ncu_herk_tc.txt) says about the rest: the converters never wait
 // for the tensor core (1.6 % of their samples at empty[s]) and the MMA warp waits for them 29 % of its time -- a converter
@@ -72,10 +77,24 @@ constexpr int TC_GROUPS = DOA_HERK_GROUPS;       // converter groups of 4 warps,
 constexpr int TC_CONV_WARPS = 4 * TC_GROUPS, TC_ADD_WARPS = 4;
 constexpr int TC_RAW_STAGE_BYTES = 8 * TC_M * 16;   // one raw stage: 8 pieces x 64 channels x 16 B
 constexpr int TC_CONV_THREADS = TC_CONV_WARPS * 32;
-constexpr int TC_THREADS = (1 + TC_CONV_WARPS + TC_ADD_WARPS) * 32;
+#ifndef DOA_HERK_ISSUERS
+#define DOA_HERK_ISSUERS 1  // MMA-issuing warps (1: warp 0 alone; 2: warp 0 and the last warp take the stages alternately)
+#endif
+constexpr int TC_ISSUERS = DOA_HERK_ISSUERS;
+constexpr int TC_THREADS = (TC_ISSUERS + TC_CONV_WARPS + TC_ADD_WARPS) * 32;
+constexpr int TC_ISSUER2_WARP = (TC_ISSUERS == 2) ? 1 + TC_CONV_WARPS + TC_ADD_WARPS : -1;   // the second issuer is the LAST warp: the others keep their TMEM lane quarters
 constexpr int TC_TMEM_COLS = 512;        // D[0] @0, D[1] @128 (64 hi*hi columns | 64 cross-term columns), A ring @256 + 64 s (hi | lo)
 constexpr uint32_t TC_A_COL = 256;
 
+#ifndef DOA_HERK_TRACE
+#define DOA_HERK_TRACE 0    // 1: CTA 0 records clock64 at the ring's hand-offs for its first 1024 stages (tools/herk_trace.py)
+#endif
+#if DOA_HERK_TRACE
+__device__ long long g_herk_trace[5][1024];   // [full seen | MMAs issued | before empty wait | empty seen | full arrived][stage]
+#define HERK_TRACE(ev, q, cond) do { if (blockIdx.x == 0 && (q) < 1024 && (cond)) g_herk_trace[ev][q] = clock64(); } while (0)
+#else
+#define HERK_TRACE(ev, q, cond) do { } while (0)
+#endif
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count)); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory"); }
@@ -166,11 +185,19 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
   }
   const long long total = (long long)my_frames * spf + tail_count;
 
-  if (warp == 0) {
-    // ================================ MMA issuer ================================
-    // The whole warp runs the loop (warp-uniform control flow and operands: ptxas emits bare UTCHMMA with uniform registers);
+  if (warp == 0 || warp == TC_ISSUER2_WARP) {
+    // ================================ MMA issuers ================================
+    // A whole warp runs the loop (warp-uniform control flow and operands: ptxas emits bare UTCHMMA with uniform registers);
     // one elected lane issues.  A descriptor differs from the ring's base descriptor only in its low word (start address).
+    // -DDOA_HERK_ISSUERS=2: two issuer warps take the stages alternately -- both walk the same stage sequence, each does the waits
+    // and the set-up of its own stages, and a token (named barriers 5 / 6) serialises the issue itself, so the MMAs still enter
+    // the pipe in stage order (same accumulation order, same bits; tested).  Built because the trace (tools/herk_trace.py,
+    // profiles/r02_herk_trace.log) shows the single issuer ~850 clk per stage behind operands that have been ready for 1900 clk.
+    // Measured: NO gain (2.09 against 2.085 ms per 592 frames) -- the issue sequence is back-pressured by the tensor pipe, which
+    // takes ~800 clk for a stage's eight MMAs against 384 nominal: it starves on its B operand (shared-memory port: 24 KB of
+    // operand reads + 33 KB of converter loads / stores + 8 KB of ring fills per stage).  Default: one issuer.
     {
+      const int iw = (warp == 0) ? 0 : 1;
       const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_M >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
       const uint32_t idesc128 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * TC_M >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
       const uint64_t desc0 = umma_desc(smem_u32(op));
@@ -178,34 +205,48 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
       int s = 0; uint32_t ph = 0; int sf = 0;
       int fr = 0, cur = (my_frames > 0) ? spf : tail_count;   // unit index, stages of the current unit
       int cb = 0, in_chunk = 0; uint32_t ce_ph = 0u;   // parity bits, one per buffer (bit b)
-      long long chunks = 0;
-      for (long long q = 0; q < total; ++q) {
+      int chunks = 0;                                  // saturating: only "< 2" matters
+      const int ntot = (int)total;                     // stages of this CTA (the launcher keeps it below 2^31)
+      for (int q = 0; q < ntot; ++q) {
+        // bookkeeping of stage q, identical in both warps
+        bool ce_wait = false; uint32_t ce_par = 0u;
         if (in_chunk == 0) {                                        // first stage of a chunk: D[cb] must have been folded
-          if (chunks >= 2) { mbar_wait(&chunk_empty[cb], (ce_ph >> cb) & 1u); ce_ph ^= 1u << cb; }
-          ++chunks;
+          if (chunks >= 2) { ce_wait = true; ce_par = (ce_ph >> cb) & 1u; ce_ph ^= 1u << cb; }
+          else ++chunks;
         }
-        mbar_wait(&full_bar[s], ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t b32 = desc_lo0 + (uint32_t)s * (2u * TC_TILE_BYTES >> 4);
-        const uint32_t ahi = tmem_d + TC_A_COL + (uint32_t)s * 64u, alo = ahi + 32u;
-        const uint32_t dacc = tmem_d + (uint32_t)cb * 128u;
         ++sf; ++in_chunk;
         const bool frame_end = (sf == cur);
         const bool chunk_end = (in_chunk == TC_CHUNK) || frame_end;   // segments are whole chunks: no chunk straddles one
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // the Z_hi and Z_lo tiles are contiguous: one 128-row B operand
-            const uint64_t db = ((uint64_t)desc_hi << 32) | (b32 + (uint32_t)k * 2u);
-            umma_tf32_ts(dacc, ahi + k * 8, db, idesc128, k == 0 ? (uint32_t)(in_chunk != 1) : 1u);   // A_hi [Z_hi; Z_lo]^T
-#if !(DOA_HERK_EXP & 1)
-            umma_tf32_ts(dacc + 64u, alo + k * 8, db, idesc64, 1u);                                   // A_lo Z_hi^T
-#endif
+        if (TC_ISSUERS == 1 || (q & 1) == iw) {
+          if (ce_wait) mbar_wait(&chunk_empty[cb], ce_par);
+          mbar_wait(&full_bar[s], ph);
+          HERK_TRACE(0, q, lane == 0);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t b32 = desc_lo0 + (uint32_t)s * (2u * TC_TILE_BYTES >> 4);
+          const uint32_t ahi = tmem_d + TC_A_COL + (uint32_t)s * 64u, alo = ahi + 32u;
+          const uint32_t dacc = tmem_d + (uint32_t)cb * 128u;
+          if (TC_ISSUERS == 2 && q > 0) {                           // the other warp has issued stage q - 1
+            if (iw) asm volatile("bar.sync 5, 64;" ::: "memory"); else asm volatile("bar.sync 6, 64;" ::: "memory");
           }
-          umma_commit(&empty_bar[s]);                               // stage s reusable once these MMAs retire
-          if (chunk_end) umma_commit(&chunk_full[cb]);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // the Z_hi and Z_lo tiles are contiguous: one 128-row B operand
+              const uint64_t db = ((uint64_t)desc_hi << 32) | (b32 + (uint32_t)k * 2u);
+              umma_tf32_ts(dacc, ahi + k * 8, db, idesc128, k == 0 ? (uint32_t)(in_chunk != 1) : 1u);   // A_hi [Z_hi; Z_lo]^T
+#if !(DOA_HERK_EXP & 1)
+              umma_tf32_ts(dacc + 64u, alo + k * 8, db, idesc64, 1u);                                   // A_lo Z_hi^T
+#endif
+            }
+            umma_commit(&empty_bar[s]);                             // stage s reusable once these MMAs retire
+            if (chunk_end) umma_commit(&chunk_full[cb]);            // the pipe is in order: every MMA of the chunk has retired then
+          }
+          __syncwarp();
+          if (TC_ISSUERS == 2 && q + 1 < ntot) {
+            if (iw) asm volatile("bar.arrive 6, 64;" ::: "memory"); else asm volatile("bar.arrive 5, 64;" ::: "memory");
+          }
+          HERK_TRACE(1, q, lane == 0);
         }
-        __syncwarp();
         if (chunk_end) { cb ^= 1; in_chunk = 0; }
         if (frame_end) { sf = 0; ++fr; cur = (fr < my_frames) ? spf : tail_count; }
         if (++s == TC_OP_STAGES) { s = 0; ph ^= 1u; }
@@ -272,10 +313,12 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
       asm volatile("cp.async.wait_group %0;" :: "n"(TC_RAW_STAGES - 2) : "memory");
       asm volatile("bar.sync %0, 128;" :: "r"(2 + g) : "memory");   // every loader's pieces of this raw stage have landed
       const int s = (int)(q & (TC_OP_STAGES - 1));
+      HERK_TRACE(2, q, gt == 0);
       if (q >= TC_OP_STAGES) {                                      // MMAs of the previous use of this stage have retired
         mbar_wait(&empty_bar[s], (uint32_t)((q >> 2) + 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
+      HERK_TRACE(3, q, gt == 0);
       const float4* src = graw + (size_t)rs * (8 * TC_M);
       uint8_t* thi = op + (size_t)s * 2 * TC_TILE_BYTES + row_off;
 #pragma unroll
@@ -320,6 +363,7 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&full_bar[s]);
+      HERK_TRACE(4, q, gt == 0);
       if (++rs == TC_RAW_STAGES) rs = 0;
     }
   } else {
@@ -454,6 +498,7 @@ int launch_covariance_tc(const float2* in, long long frame_stride, long long cha
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int spf = (N + 15) / 16;
+  if (((long long)nframes / sms + 2) * spf > 0x7fffffffLL) return 0;          // a CTA counts its stages in an int
   // segment length: a multiple of the chunk, at most TC_MAX_SEGS segments per frame -- a function of N alone
   const int seg_len = std::max(TC_CHUNK, ((spf + TC_MAX_SEGS - 1) / TC_MAX_SEGS + TC_CHUNK - 1) / TC_CHUNK * TC_CHUNK);
   const int nseg = (spf + seg_len - 1) / seg_len;
@@ -472,3 +517,9 @@ int launch_covariance_tc(const float2* in, long long frame_stride, long long cha
 }
 
 }  // namespace doa
+
+#if DOA_HERK_TRACE
+extern "C" int doa_herk_trace_dump(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, doa::g_herk_trace, sizeof(long long) * 5 * 1024);
+}
+#endif
