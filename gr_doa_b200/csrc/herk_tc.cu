@@ -77,6 +77,13 @@ constexpr int TC_GROUPS = DOA_HERK_GROUPS;       // converter groups of 4 warps,
 constexpr int TC_CONV_WARPS = 4 * TC_GROUPS, TC_ADD_WARPS = 4;
 constexpr int TC_RAW_STAGE_BYTES = 8 * TC_M * 16;   // one raw stage: 8 pieces x 64 channels x 16 B
 constexpr int TC_CONV_THREADS = TC_CONV_WARPS * 32;
+#ifndef DOA_HERK_PAIRED
+#define DOA_HERK_PAIRED 0   // 1: the Z row and the W row of a channel sit in ONE warp (TMEM lanes 32k + j and 32k + 16 + j: channel 16k + j), so the
+                            //    two threads' loads of the raw row are one shared-memory broadcast (8 KB less port traffic per stage) and the
+                            //    (re, im) -> (im, -re) map is done by selects ahead of one uniform hi/lo split (same bits; tested).  Measured
+                            //    SLOWER, 2.30 against 2.055 ms per 592 frames: all four warps of a group then store B tiles and pay the
+                            //    generic->async proxy fence.  0 (shipped): Z rows in lanes 0..63, W rows in 64..127
+#endif
 #ifndef DOA_HERK_ISSUERS
 #define DOA_HERK_ISSUERS 1  // MMA-issuing warps (1: warp 0 alone; 2: warp 0 and the last warp take the stages alternately)
 #endif
@@ -85,6 +92,16 @@ constexpr int TC_THREADS = (TC_ISSUERS + TC_CONV_WARPS + TC_ADD_WARPS) * 32;
 constexpr int TC_ISSUER2_WARP = (TC_ISSUERS == 2) ? 1 + TC_CONV_WARPS + TC_ADD_WARPS : -1;   // the second issuer is the LAST warp: the others keep their TMEM lane quarters
 constexpr int TC_TMEM_COLS = 512;        // D[0] @0, D[1] @128 (64 hi*hi columns | 64 cross-term columns), A ring @256 + 64 s (hi | lo)
 constexpr uint32_t TC_A_COL = 256;
+constexpr int TC_STG_IM = TC_M * 65 + 16;  // staging area: Re rows at r * 65, Im rows at TC_STG_IM + r * 65 (the 16 keeps the two halves of a warp on different banks)
+// staging row of TMEM lane `row` (= the row of [Re R; Im R] it accumulates)
+__device__ __forceinline__ int stg_row_off(int row) {
+#if DOA_HERK_PAIRED
+  const int j = row & 31, ch = (row >> 5) * 16 + (j & 15);
+  return (j >= 16) ? TC_STG_IM + ch * 65 : ch * 65;
+#else
+  return (row >= TC_M) ? TC_STG_IM + (row - TC_M) * 65 : row * 65;
+#endif
+}
 
 #ifndef DOA_HERK_TRACE
 #define DOA_HERK_TRACE 0    // 1: CTA 0 records clock64 at the ring's hand-offs for its first 1024 stages (tools/herk_trace.py)
@@ -269,8 +286,13 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
     float4* graw = raw + (size_t)g * TC_RAW_STAGES * (8 * TC_M);
     float4* lraw = graw + lpc * TC_M;
     // converter role: this thread IS row (warp & 3) * 32 + lane of A = [Z; W] (TMEM lanes are per-warp quarters)
+#if DOA_HERK_PAIRED
+    const int cch = (warp & 3) * 16 + (lane & 15);
+    const bool is_w = lane >= 16;
+#else
     const int row = (warp & 3) * 32 + lane, cch = row & (TC_M - 1);
     const bool is_w = row >= TC_M;
+#endif
     const uint32_t a_lane = tmem_d + TC_A_COL + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t row_off = ((uint32_t)cch >> 3) * 1024u + ((uint32_t)cch & 7u) * 128u, row_x = (uint32_t)cch & 7u;
     constexpr int NG = TC_GROUPS;
@@ -327,6 +349,21 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
         float4 v[4];                                // (re0, im0, re1, im1) each
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = src[(4 * h + j) * TC_M + (cch ^ (4 * h + j))];
+#if DOA_HERK_PAIRED
+        // W row: every (re, im) pair becomes (im, -re) BEFORE the split (the split is odd-symmetric: the same bits as
+        // splitting first), by selects, so that the two halves of the warp run one instruction stream
+        {
+          const uint32_t sgn = is_w ? 0x80000000u : 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a0 = is_w ? v[j].y : v[j].x, b0 = __uint_as_float(__float_as_uint(is_w ? v[j].x : v[j].y) ^ sgn);
+            const float a1 = is_w ? v[j].w : v[j].z, b1 = __uint_as_float(__float_as_uint(is_w ? v[j].z : v[j].w) ^ sgn);
+            const float x[4] = {a0, b0, a1, b1};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { hi[4 * j + e] = to_tf32(x[e]); lo[4 * j + e] = x[e] - hi[4 * j + e]; }
+          }
+        }
+#else
         if (!is_w) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -346,6 +383,7 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
             }
           }
         }
+#endif
         if (!is_w && !(DOA_HERK_EXP & 4)) {             // Z rows are also the B operand: swizzled K-major tiles in shared memory
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -372,6 +410,7 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
     const int q4 = warp & 3;                                       // TMEM lane quarter this warp may read
     const int row = q4 * 32 + lane;                                // row of [Re R; Im R]
     const uint32_t lane_addr = tmem_d + ((uint32_t)(q4 * 32) << 16);
+    const int srow = stg_row_off(row);                             // this row's place in the staging area
     uint32_t cf_ph = 0u;                                           // parity bits, one per buffer
     int cb = 0;
     const int nunits = my_frames + (has_tail ? 1 : 0);
@@ -406,10 +445,10 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
         if (!tl) {                                    // running total of the frame in the staging area (own row: no barrier)
           if (sg == 0) {
 #pragma unroll
-            for (int c = 0; c < TC_M; ++c) stg[row * 65 + c] = acc[c];
+            for (int c = 0; c < TC_M; ++c) stg[srow + c] = acc[c];
           } else {
 #pragma unroll
-            for (int c = 0; c < TC_M; ++c) stg[row * 65 + c] += acc[c];
+            for (int c = 0; c < TC_M; ++c) stg[srow + c] += acc[c];
           }
         } else {                                      // shared frame: the segment goes to the workspace
           float4* p = reinterpret_cast<float4*>(ws_part + (((size_t)tail_idx * nseg + tail_seg0 + sg) * TC_ROWS + row) * TC_M);
@@ -441,7 +480,7 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
 #pragma unroll
           for (int sg = 1; sg < TC_MAX_SEGS; ++sg)
             if (sg < nseg) { a.x += v[sg].x; a.y += v[sg].y; a.z += v[sg].z; a.w += v[sg].w; }
-          float* d = stg + row * 65 + 4 * q;
+          float* d = stg + srow + 4 * q;
           d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
         }
       }
@@ -449,10 +488,10 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
       float2* o = out + fcur * (long long)(TC_M * TC_M);
       for (int e = at; e < TC_M * TC_M; e += 128) {
         const int r = e % TC_M, c = e / TC_M;
-        float2 v = apply_gain(make_float2(stg[r * 65 + c] * scale, stg[(TC_M + r) * 65 + c] * scale), gains, r, c);
+        float2 v = apply_gain(make_float2(stg[r * 65 + c] * scale, stg[TC_STG_IM + r * 65 + c] * scale), gains, r, c);
         if (avg_method == 1) {
           const int rr = TC_M - 1 - r, cc = TC_M - 1 - c;
-          const float2 w = apply_gain(make_float2(stg[rr * 65 + cc] * scale, stg[(TC_M + rr) * 65 + cc] * scale), gains, rr, cc);
+          const float2 w = apply_gain(make_float2(stg[rr * 65 + cc] * scale, stg[TC_STG_IM + rr * 65 + cc] * scale), gains, rr, cc);
           v.x = __fadd_rn(__fmul_rn(0.5f, v.x), __fmul_rn(bscale, w.x));
           v.y = __fadd_rn(__fmul_rn(0.5f, v.y), __fmul_rn(bscale, -w.y));
         }
@@ -492,7 +531,7 @@ int launch_covariance_tc(const float2* in, long long frame_stride, long long cha
                        ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
   if (!aligned) return 0;
   const size_t smem = (size_t)TC_OP_STAGES * 2 * TC_TILE_BYTES + (size_t)TC_GROUPS * TC_RAW_STAGES * TC_RAW_STAGE_BYTES +
-                      (size_t)128 * 65 * sizeof(float) + 1024;
+                      (size_t)(128 * 65 + 16) * sizeof(float) + 1024;
   cudaFuncSetAttribute(herk_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
