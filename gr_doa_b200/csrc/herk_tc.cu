@@ -54,6 +54,7 @@
 // Z rows and half by the W rows (10 % SLOWER: every thread then pays the generic->async proxy fence, which turns out to be the
 // expensive part of a Z-row thread's iteration, not its sixteen stores).
 #include "cov_device.cuh"
+#include "herk_geometry.h"
 
 #include <algorithm>
 
@@ -64,8 +65,8 @@ constexpr int TC_M = 64;                 // channels
 constexpr int TC_ROWS = 128;             // rows of [Z; W]
 constexpr int TC_OP_STAGES = 4;          // operand ring depth: A = 64 TMEM columns (hi | lo), B = 16 KB smem (hi | lo tiles of 64 x 128 B)
 constexpr int TC_RAW_STAGES = 5;         // raw fp32 ring depth PER converter group (8 KB per stage)
-constexpr int TC_CHUNK = 4;              // stages (= 16 hi*hi MMAs) per big-accumulator chunk
-constexpr int TC_MAX_SEGS = 8;           // segments per frame (the canonical association of a frame's sum; also the widest split)
+constexpr int TC_CHUNK = HERK_CHUNK;     // stages (= 16 hi*hi MMAs) per big-accumulator chunk
+constexpr int TC_MAX_SEGS = HERK_MAX_SEGS;   // segments per frame (the canonical association of a frame's sum; also the widest split)
 constexpr int TC_TILE_BYTES = TC_M * 128; // one B tile (Z_hi or Z_lo): 64 rows x 128 B
 #ifndef DOA_HERK_EXP
 #define DOA_HERK_EXP 0      // timing experiments only (tools/herk_bound_exp.sh): bit 0 no A_lo Z_hi^T MMA, bit 1 no A_lo store, bit 2 no B tile stores
@@ -190,16 +191,11 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
   const int spf = (N + 15) / 16;                                             // stages per frame (16 complex samples each)
   // Work units of this CTA: whole frames blockIdx.x + r * gridDim.x < nfull, then at most one TAIL unit -- a range of whole
   // segments of one of the nframes - nfull frames that do not fill a round of the grid (split-K, see launch_covariance_tc).
-  const int my_frames = (nfull > (int)blockIdx.x) ? (nfull - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int my_frames = herk_whole_frames((int)blockIdx.x, (int)gridDim.x, nfull);
   const int nseg = (spf + seg_len - 1) / seg_len;
-  const bool has_tail = (int)blockIdx.x < (nframes - nfull) * tail_S;
-  int tail_idx = 0, tail_seg0 = 0, tail_start = 0, tail_count = 0;
-  if (has_tail) {
-    tail_idx = (int)blockIdx.x / tail_S;
-    tail_seg0 = ((int)blockIdx.x % tail_S) * tail_sps;
-    tail_start = tail_seg0 * seg_len;
-    tail_count = min(spf, min(nseg, tail_seg0 + tail_sps) * seg_len) - tail_start;
-  }
+  const HerkTail tl_ = herk_tail((int)blockIdx.x, nframes, nfull, tail_S, tail_sps, seg_len, spf);
+  const bool has_tail = tl_.has != 0;
+  const int tail_idx = tl_.idx, tail_seg0 = tl_.seg0, tail_start = tl_.start, tail_count = tl_.count;
   const long long total = (long long)my_frames * spf + tail_count;
 
   if (warp == 0 || warp == TC_ISSUER2_WARP) {
@@ -508,7 +504,7 @@ herk_tc64_kernel(const float2* __restrict__ in, long long frame_stride, long lon
 }  // namespace
 
 // Workspace of the split tail (below): 256 frame counters, then per shareable frame TC_MAX_SEGS partial sums of 128 x 64 floats.
-constexpr int TC_WS_FRAMES = 128;        // frames a launch may share between CTAs (at most half the grid)
+constexpr int TC_WS_FRAMES = HERK_WS_FRAMES;   // frames a launch may share between CTAs (at most half the grid)
 constexpr size_t TC_WS_CNT_BYTES = 1024;
 size_t covariance_tc_workspace_bytes() {
   return TC_WS_CNT_BYTES + (size_t)TC_WS_FRAMES * TC_MAX_SEGS * TC_ROWS * TC_M * sizeof(float);
@@ -536,18 +532,9 @@ int launch_covariance_tc(const float2* in, long long frame_stride, long long cha
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int spf = (N + 15) / 16;
-  if (((long long)nframes / sms + 2) * spf > 0x7fffffffLL) return 0;          // a CTA counts its stages in an int
-  // segment length: a multiple of the chunk, at most TC_MAX_SEGS segments per frame -- a function of N alone
-  const int seg_len = std::max(TC_CHUNK, ((spf + TC_MAX_SEGS - 1) / TC_MAX_SEGS + TC_CHUNK - 1) / TC_CHUNK * TC_CHUNK);
-  const int nseg = (spf + seg_len - 1) / seg_len;
-  int grid = std::min(nframes, sms), nfull = nframes, S = 0, sps = 0;
-  const int t = nframes % sms;
-  if (ws != nullptr && dev_option(OPT_HERK_SPLIT, 1) && t > 0 && t <= TC_WS_FRAMES && nseg >= 2 && sms / t >= 2) {
-    sps = (nseg + std::min(sms / t, nseg) - 1) / std::min(sms / t, nseg);   // segments per CTA
-    S = (nseg + sps - 1) / sps;                                               // CTAs per shared frame (every one non-empty)
-    if (S >= 2) { grid = (nframes > sms) ? sms : t * S; nfull = nframes - t; } else { S = 0; sps = 0; }
-  }
+  const HerkGeometry g = herk_geometry(nframes, N, sms, ws != nullptr && dev_option(OPT_HERK_SPLIT, 1));   // herk_geometry.h
+  if (((long long)nframes / sms + 2) * g.spf > 0x7fffffffLL) return 0;        // a CTA counts its stages in an int
+  const int grid = g.grid, nfull = g.nfull, seg_len = g.seg_len, S = g.S, sps = g.sps;
   herk_tc64_kernel<<<grid, TC_THREADS, smem, st>>>(in, frame_stride, chan_stride, N, nframes, out, (float)(1.0 / N),
                                                    (float)(0.5 / N), avg_method, gains, nfull, seg_len, S, sps,
                                                    ws ? reinterpret_cast<float*>(static_cast<char*>(ws) + TC_WS_CNT_BYTES) : nullptr,
